@@ -1,0 +1,132 @@
+/*
+ * mode_engine.h — C ABI of the B200-native MoDE denoising engine (libmode_engine.so).
+ *
+ * Scope: the EDM/DDIM denoising loop over the MoDE transformer of intuitive-robots/MoDE_Diffusion_Policy,
+ *   MoDEAgent.denoise_actions -> sample_ddim -> GCDenoiser.forward -> MoDeDiT.forward -> n_layers x NoiseBlockMoE.
+ * The reference has no FFI for this path (it is first-party Python over ATen); its plug-in seam is the pair of Hydra
+ * `_target_` strings in conf/model/mode_agent.yaml:41 and :47. Each entry point below names the reference function it
+ * replaces (paths relative to the reference checkout). The Python mirror in mode_diffusion_policy_b200/ binds these with
+ * ctypes; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - return 0 on success, negative on error; mode_last_error() returns the thread-local message of the last failure
+ *   - the caller owns every I/O buffer; the engine owns packed bf16 weights, workspace and CUDA graphs
+ *   - `*_dev` pointers are fp32 device pointers on the engine's device; `*_host` are host pointers
+ *   - work is enqueued on the caller's stream (cudaStream_t passed as void*); no hidden synchronisation except in
+ *     the *_host entry points, mode_finalize_weights and the small getters, which say so
+ *   - one engine per (device, stream) at a time; not thread-safe; independent engines may run concurrently
+ *   - there is NO CPU fallback: every entry point fails with MODE_ERR_CUDA if no sm_100 device is present
+ */
+#ifndef MODE_ENGINE_H_
+#define MODE_ENGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mode_engine mode_engine_t;
+
+enum {
+  MODE_OK = 0,
+  MODE_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  MODE_ERR_CUDA = -2,        /* CUDA runtime or driver failure (message holds the CUDA error string) */
+  MODE_ERR_STATE = -3,       /* call order violated (e.g. forward before mode_finalize_weights) */
+  MODE_ERR_UNKNOWN_NAME = -4 /* mode_set_weight: not a MoDeDiT state_dict key */
+};
+
+/* Constructor arguments of MoDeDiT (mode/models/networks/modedit.py:643-674) that shape the hot path, plus the
+ * engine's capacity. Unsupported reference options (use_proprio, use_custom_attn_mask, use_shared_expert,
+ * goal_conditioned=False, use_noise_token_as_input=False, linear_output=False) are rejected at create time. */
+typedef struct mode_config {
+  int32_t obs_dim;        /* width of each state_images token                        (conf/model/mode_agent.yaml:48) */
+  int32_t goal_dim;       /* width of the language/goal embedding                    (:49) */
+  int32_t action_dim;     /* <= 8                                                    (:51) */
+  int32_t embed_dim;      /* d, multiple of 256, <= 2048                             (:56) */
+  int32_t n_layers;       /* (:59) */
+  int32_t n_heads;        /* head dim = d / n_heads must be 32, 64 or 128            (:60) */
+  int32_t n_state_tokens; /* tokens in states['state_images'] (2 cameras in CALVIN, mode_agent.py:562-565) */
+  int32_t action_seq_len; /* (:67) */
+  int32_t num_experts;    /* <= 32                                                   (:69) */
+  int32_t top_k;          /* <= 8, <= num_experts                                    (:70) */
+  int32_t router_normalize; /* RouterCond.normalize (modedit.py:418-419)             */
+  int32_t max_batch;      /* capacity: largest B any call will use */
+  float sigma_data;       /* GCDenoiser.sigma_data (score_wrappers.py:26; conf: 0.5) */
+  float rms_eps;          /* RMSNorm eps used by every norm in the blocks: 1e-6 (modedit.py:447, :470, :720) */
+} mode_config_t;
+
+/* Replaces MoDeDiT.__init__ (modedit.py:643-739): allocates packed-weight storage and workspace on the current
+ * CUDA device. */
+int mode_create(const mode_config_t* cfg, mode_engine_t** out);
+void mode_destroy(mode_engine_t* e);
+const char* mode_last_error(void);
+
+/* Replaces nn.Module.load_state_dict for MoDeDiT: `name` is a reference state_dict key ("blocks.3.attn.key.weight",
+ * "sigma_emb.bias", ...; the full list is in DESIGN.md), `data` is contiguous fp32 with the reference shape, on the
+ * host (is_device = 0) or on the engine's device (1). The engine converts to its own layout (bf16, packed QKV,
+ * interleaved SwiGLU rows); the caller keeps ownership. "gripper_embed.weight" is accepted and ignored (unused unless
+ * use_proprio, modedit.py:684). Synchronous. */
+int mode_set_weight(mode_engine_t* e, const char* name, const void* data, int is_device, const int64_t* shape,
+                    int ndim);
+/* Verifies every tensor was provided, precomputes the sigma-embedding and router affine forms. Synchronous. */
+int mode_finalize_weights(mode_engine_t* e);
+
+/* MoDeDiT.forward(states, actions, goals, sigma) (modedit.py:741-809), eval mode: raw network output F.
+ * state_dev (B, n_state_tokens, obs_dim); goal_dev (B, goal_dim); actions_dev, out_dev (B, action_seq_len, action_dim);
+ * sigma_dev (B,) or a single value when sigma_stride == 0. */
+int mode_forward(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
+                 const float* sigma_dev, int sigma_stride, float* out_dev, int B, void* stream);
+
+/* GCDenoiser.forward (score_wrappers.py:65-80): D(x; sigma) = c_out * F(c_in * x; sigma) + c_skip * x. */
+int mode_denoise(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
+                 const float* sigma_dev, int sigma_stride, float* out_dev, int B, void* stream);
+
+/* GCDenoiser.loss forward (score_wrappers.py:45-63), eval-mode routing, no dropout: noised = action + noise * sigma;
+ * writes the scalar mean squared error to loss_dev[0] and the model output F to out_dev (may be NULL). */
+int mode_loss(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* action_dev,
+              const float* noise_dev, const float* sigma_dev, float* loss_dev, float* out_dev, int B, void* stream);
+
+/* sample_ddim (gc_sampling.py:922-951) over GCDenoiser: x_inout_dev (B, action_seq_len, action_dim) holds the initial
+ * noise (randn * sigma_max, drawn by the caller as in mode_agent.py:756) and receives the denoised actions.
+ * sigmas_host: n_plus_1 values, the last one normally 0 (get_sigmas_exponential, gc_sampling.py:35-38).
+ * The whole n-step loop is one CUDA graph launch; observation/goal tokens are embedded once per call. */
+int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                     const float* sigmas_host, int n_plus_1, int B, void* stream);
+
+/* Same as mode_sample_ddim with HOST buffers: copies inputs host->device, runs, copies the result back into
+ * x_inout_host and synchronises the stream. This is the end-to-end call a non-PyTorch host would make. */
+int mode_sample_ddim_host(mode_engine_t* e, const float* state_host, const float* goal_host, float* x_inout_host,
+                          const float* sigmas_host, int n_plus_1, int B, void* stream);
+
+/* NoiseBlockMoE.forward(x, c) (modedit.py:530-595), eval mode, for one layer: x_dev/out_dev (B, T, d) with
+ * T = 2 + n_state_tokens + action_seq_len, c_dev (B, d). */
+int mode_block_forward(mode_engine_t* e, int layer, const float* x_dev, const float* c_dev, float* out_dev, int B,
+                       void* stream);
+
+/* Routing of the most recent evaluation, layer `layer` (RouterCond.forward outputs, modedit.py:312-318):
+ * idx_host (B, top_k) int32 in torch.topk order, w_host (B, top_k) renormalised probabilities, probs_host (B, E)
+ * clamped softmax; any may be NULL. Synchronises the device. */
+int mode_get_routing(mode_engine_t* e, int layer, int B, int32_t* idx_host, float* w_host, float* probs_host);
+
+/* NoiseBlockMoE.get_expert_usage / total_tokens_processed / reset_expert_usage (modedit.py:597-605). Synchronises. */
+int mode_get_expert_usage(mode_engine_t* e, int layer, int64_t* usage_host /* [num_experts] */,
+                          int64_t* total_tokens_host /* [1] */);
+int mode_reset_expert_usage(mode_engine_t* e);
+
+/* Kernels of this library enqueued by the most recent forward/denoise/sample/block call (graph nodes count). */
+int64_t mode_last_launch_count(const mode_engine_t* e);
+
+/* Unit-test entry for the tcgen05 GEMM: out = epilogue(A[M,K] @ W[N,K]^T). a_dev/w_dev bf16, bias_dev/resid_dev fp32
+ * (may be NULL), epilogue = 0 bias->bf16, 1 resid+acc->f32, 2 swiglu->bf16 (W/bias already interleaved per 256 rows),
+ * 3 plain->bf16, 4 plain->f32. M arbitrary, N % 256 == 0, K % 64 == 0. Returns after enqueueing. */
+int mode_debug_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
+                    void* out_dev, int M, int N, int K, int epilogue, void* stream);
+/* Unit-test entry for the attention kernel: qkv_dev bf16 (B*T, 3*H*Dh), out_dev bf16 (B*T, H*Dh). */
+int mode_debug_attention(const void* qkv_dev, const float* q_gain_dev, const float* k_gain_dev, void* out_dev,
+                         int B, int T, int H, int Dh, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODE_ENGINE_H_ */

@@ -1,0 +1,211 @@
+// Fused causal self-attention for the MoDE token sequence (T <= 64 tokens: sigma | goal | images | actions).
+// Reference: Attention.forward, mode/models/networks/modedit.py:133-167 — per-head RMSNorm on q and k (:145-146),
+// F.scaled_dot_product_attention(is_causal=True) (:149), heads re-interleaved (:165).
+//
+// One warp per (sample, head). q/k/v rows are read once from the packed QKV activation (bf16, 16-byte vectors),
+// q and k are RMS-normalised in fp32 and rounded to bf16 in shared memory, QK^T and PV run on mma.sync m16n8k16
+// (0.05% of the step's FLOPs: the tensor-memory path would be all overhead for 14x14 problems), softmax in fp32.
+// Rounding points follow the flash SDPA kernel the reference dispatches to under bf16 autocast: bf16 q/k/v, fp32
+// scores, P rounded to bf16 before PV, fp32 row sum, bf16 output.
+#pragma once
+#include "ptx.cuh"
+
+namespace mode {
+
+constexpr int ATTN_WARPS = 4;
+constexpr int ATTN_MAX_TPAD = 64;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct AttnParams {
+  const __nv_bfloat16* qkv;  // [B*T, 3*d]: q | k | v, each d = H*Dh wide
+  __nv_bfloat16* out;        // [B*T, d]
+  const float* q_gain;       // [Dh]
+  const float* k_gain;       // [Dh]
+  int B, T, H;
+  float eps;                 // RMSNorm eps (1e-6)
+};
+
+// DH: head dim (32/64/128). MT: number of 16-row tiles covering T (T_pad = 16*MT).
+template <int DH, int MT>
+__global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnParams p) {
+  constexpr int TPAD = 16 * MT;
+  constexpr int LDS = DH + 8;            // padded row (bf16 elements): conflict-free ldmatrix
+  constexpr int VPR = DH / 8;            // 16-byte vectors per row
+  constexpr int ROWS_PER_IT = 32 / VPR;  // rows covered by one warp-wide vector load
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * ATTN_WARPS + warp;  // (b, h)
+  if (item >= p.B * p.H) return;
+  const int b = item / p.H, h = item % p.H;
+  const int T = p.T, d = p.H * DH;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(attn_smem) + static_cast<size_t>(warp) * 3 * TPAD * LDS;
+  __nv_bfloat16* sK = sQ + TPAD * LDS;
+  __nv_bfloat16* sV = sK + TPAD * LDS;
+
+  // ---- stage q, k (normalised) and v into shared memory
+  const int sub = lane % VPR;  // vector index inside the row
+  const float inv_sqrt_dh = rsqrtf(static_cast<float>(DH));
+  float gq[8], gk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gq[j] = p.q_gain[sub * 8 + j];
+    gk[j] = p.k_gain[sub * 8 + j];
+  }
+  for (int r0 = 0; r0 < TPAD; r0 += ROWS_PER_IT) {
+    const int row = r0 + lane / VPR;
+    const bool valid = row < T;
+    const __nv_bfloat16* src = p.qkv + (static_cast<size_t>(b) * T + row) * 3 * d + h * DH + sub * 8;
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (valid) raw = *reinterpret_cast<const uint4*>(src + which * d);
+      __nv_bfloat16* dst = (which == 0 ? sQ : which == 1 ? sK : sV) + row * LDS + sub * 8;
+      if (which < 2) {
+        float v[8];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          v[2 * j] = f.x;
+          v[2 * j + 1] = f.y;
+          ss += f.x * f.x + f.y * f.y;
+        }
+#pragma unroll
+        for (int o = VPR / 2; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        // RMSNorm.forward (modedit.py:78-80): x / clamp(||x|| * dim^-0.5, eps) * g
+        const float n = fmaxf(sqrtf(ss) * inv_sqrt_dh, p.eps);
+        const float* g = which == 0 ? gq : gk;
+        uint4 o4;
+        o4.x = pack_bf16x2(__fdiv_rn(v[0], n) * g[0], __fdiv_rn(v[1], n) * g[1]);
+        o4.y = pack_bf16x2(__fdiv_rn(v[2], n) * g[2], __fdiv_rn(v[3], n) * g[3]);
+        o4.z = pack_bf16x2(__fdiv_rn(v[4], n) * g[4], __fdiv_rn(v[5], n) * g[5]);
+        o4.w = pack_bf16x2(__fdiv_rn(v[6], n) * g[6], __fdiv_rn(v[7], n) * g[7]);
+        raw = o4;
+      }
+      *reinterpret_cast<uint4*>(dst) = raw;
+    }
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, tq = lane & 3;  // mma fragment coordinates
+  const float scale = inv_sqrt_dh;         // SDPA default scale 1/sqrt(Dh)
+  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+
+#pragma unroll 1
+  for (int mi = 0; mi < MT; ++mi) {
+    if (mi * 16 >= T) break;
+    // ---- S = Q K^T for this 16-row tile; only key tiles nj <= 2*mi+1 can be unmasked
+    float s[2 * MT][4];
+#pragma unroll
+    for (int nj = 0; nj < 2 * MT; ++nj) s[nj][0] = s[nj][1] = s[nj][2] = s[nj][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      uint32_t a0, a1, a2, a3;
+      ldmatrix_x4(sQ_a + ((mi * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8) * 2, a0, a1, a2, a3);
+#pragma unroll
+      for (int nj = 0; nj < 2 * MT; ++nj) {
+        if (nj <= 2 * mi + 1) {
+          uint32_t b0, b1;
+          ldmatrix_x2(sK_a + ((nj * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8) * 2, b0, b1);
+          mma_bf16_16816(s[nj], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+    // ---- causal softmax (fp32); rows g and g+8 of the tile live in this quad
+    const int row_lo = mi * 16 + g, row_hi = row_lo + 8;
+    float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+    for (int nj = 0; nj < 2 * MT; ++nj) {
+      if (nj <= 2 * mi + 1) {
+        const int c0 = nj * 8 + 2 * tq;
+        s[nj][0] = (c0 <= row_lo) ? s[nj][0] * scale : -INFINITY;
+        s[nj][1] = (c0 + 1 <= row_lo) ? s[nj][1] * scale : -INFINITY;
+        s[nj][2] = (c0 <= row_hi) ? s[nj][2] * scale : -INFINITY;
+        s[nj][3] = (c0 + 1 <= row_hi) ? s[nj][3] * scale : -INFINITY;
+        m_lo = fmaxf(m_lo, fmaxf(s[nj][0], s[nj][1]));
+        m_hi = fmaxf(m_hi, fmaxf(s[nj][2], s[nj][3]));
+      }
+    }
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < 2 * MT; ++nj) {
+      if (nj <= 2 * mi + 1) {
+        s[nj][0] = __expf(s[nj][0] - m_lo);
+        s[nj][1] = __expf(s[nj][1] - m_lo);
+        s[nj][2] = __expf(s[nj][2] - m_hi);
+        s[nj][3] = __expf(s[nj][3] - m_hi);
+        sum_lo += s[nj][0] + s[nj][1];
+        sum_hi += s[nj][2] + s[nj][3];
+      }
+    }
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+
+    // ---- O = P V (P rounded to bf16, unnormalised; divide by the fp32 row sum at the end)
+    float o[DH / 8][4];
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < MT; ++kj) {
+      if (kj <= mi) {
+        const uint32_t a0 = pack_bf16x2(s[2 * kj][0], s[2 * kj][1]);
+        const uint32_t a1 = pack_bf16x2(s[2 * kj][2], s[2 * kj][3]);
+        const uint32_t a2 = pack_bf16x2(s[2 * kj + 1][0], s[2 * kj + 1][1]);
+        const uint32_t a3 = pack_bf16x2(s[2 * kj + 1][2], s[2 * kj + 1][3]);
+#pragma unroll
+        for (int dn = 0; dn < DH / 8; ++dn) {
+          uint32_t b0, b1;
+          ldmatrix_x2_trans(sV_a + ((kj * 16 + (lane & 15)) * LDS + dn * 8) * 2, b0, b1);
+          mma_bf16_16816(o[dn], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+    const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+    // ---- stage O through this tile's (now dead) Q rows so the global store is 16-byte coalesced
+    __syncwarp();
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) {
+      *reinterpret_cast<uint32_t*>(sQ + row_lo * LDS + dn * 8 + 2 * tq) =
+          pack_bf16x2(o[dn][0] * inv_lo, o[dn][1] * inv_lo);
+      *reinterpret_cast<uint32_t*>(sQ + row_hi * LDS + dn * 8 + 2 * tq) =
+          pack_bf16x2(o[dn][2] * inv_hi, o[dn][3] * inv_hi);
+    }
+    __syncwarp();
+  }
+  // ---- write out [T, Dh] for this head
+  for (int r0 = 0; r0 < TPAD; r0 += ROWS_PER_IT) {
+    const int row = r0 + lane / VPR;
+    if (row < T) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sQ + row * LDS + sub * 8);
+      *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b) * T + row) * d + h * DH + sub * 8) = v;
+    }
+  }
+}
+
+}  // namespace mode

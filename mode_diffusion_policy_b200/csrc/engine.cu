@@ -1,0 +1,890 @@
+// Host side of libmode_engine.so: configuration, weight packing, workspace, routing tables, kernel sequencing,
+// CUDA-graph capture of the DDIM loop, and the C ABI declared in include/mode_engine.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mode_engine.h"
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "rowwise.cuh"
+
+using namespace mode;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU_OK(expr)                                                                                          \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess)                                                                                   \
+      return fail(MODE_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+#define RET_IF(expr)         \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != MODE_OK) return _r; \
+  } while (0)
+
+extern "C" const char* mode_last_error(void) { return g_err; }
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------ small kernels
+namespace {
+
+// fp32 rows -> packed destination (bf16 or fp32), optionally with the SwiGLU interleave:
+// source rows [0, half) are `projected`, [half, 2*half) are `gate` (SwishGLU.forward, modedit.py:88-90); destination
+// blocks of 256 rows hold 128 projected rows followed by their 128 gate rows so that one 128x256 GEMM tile contains
+// both halves of 128 hidden units and the SwiGLU product can be formed in the epilogue.
+__global__ void pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, int rows, int cols,
+                                 size_t dst_row0, int swiglu_half, int to_bf16) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * cols) return;
+  const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  int dr = r;
+  if (swiglu_half > 0) {
+    const int is_gate = r >= swiglu_half;
+    const int rr = is_gate ? r - swiglu_half : r;
+    dr = (rr / 128) * 256 + (is_gate ? 128 : 0) + (rr % 128);
+  }
+  const size_t o = (dst_row0 + dr) * static_cast<size_t>(cols) + c;
+  if (to_bf16)
+    reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(src[i]);
+  else
+    reinterpret_cast<float*>(dst)[o] = src[i];
+}
+
+// out[r] = sum_k W[r,k]*vec[k] (+ add[r]) accumulated in fp64; one warp per row. Used once at weight-load time.
+__global__ void matvec_f64_kernel(const float* __restrict__ W, const float* __restrict__ vec,
+                                  const float* __restrict__ add, float* __restrict__ out, int rows, int cols) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  double acc = 0.0;
+  for (int k = lane; k < cols; k += 32) acc += static_cast<double>(W[static_cast<size_t>(r) * cols + k]) * vec[k];
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[r] = static_cast<float>(acc + (add ? static_cast<double>(add[r]) : 0.0));
+}
+
+// Generic first router Linear for the block-level entry (arbitrary c): z[b, j] = W1[j,:] . c[b,:] + b1[j]  (fp32).
+__global__ void router_hidden_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                     const float* __restrict__ c, float* __restrict__ z, int B, int Hd, int d) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (item >= B * Hd) return;
+  const int b = item / Hd, j = item % Hd;
+  float acc = 0.f;
+  for (int k = lane; k < d; k += 32) acc = fmaf(W1[static_cast<size_t>(j) * d + k], c[static_cast<size_t>(b) * d + k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) z[item] = acc + b1[j];
+}
+
+struct ScheduleArg {
+  float v[3 * 64];
+  int n;
+};
+// Writes the per-step {sigma} and {sigma_next/sigma, expm1(-h)} tables the captured graph reads.
+__global__ void set_schedule_kernel(const ScheduleArg a, float* __restrict__ sig, float* __restrict__ coefs) {
+  const int i = threadIdx.x;
+  if (i < a.n) {
+    sig[i] = a.v[3 * i];
+    coefs[2 * i] = a.v[3 * i + 1];
+    coefs[2 * i + 1] = a.v[3 * i + 2];
+  }
+}
+
+// noised = action + noise * sigma  (GCDenoiser.loss, score_wrappers.py:59)
+__global__ void noise_actions_kernel(const float* __restrict__ action, const float* __restrict__ noise,
+                                     const float* __restrict__ sigma, float* __restrict__ out, int per_sample, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(action[i], __fmul_rn(noise[i], sigma[i / per_sample]));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ engine
+struct WeightSpec {
+  void* dst;
+  size_t dst_row0;
+  int rows, cols;
+  int swiglu_half;
+  int to_bf16;
+  bool ignore;
+  bool provided;
+};
+
+struct mode_engine {
+  mode_config_t cfg;
+  int d, L, H, Dh, E, K, T, S, A, adim, maxB, maxM, Hd, F, obs, gdim;
+  int num_sms;
+  int perm_rows, max_tiles;
+  bool finalized = false;
+  std::map<std::string, WeightSpec> specs;
+  std::vector<void*> allocs;
+
+  // packed weights
+  __nv_bfloat16 *w_qkv, *w_proj, *w_up, *w_down, *w_tok, *w_goal;
+  float *b_qkv, *b_up, *ln1_g, *ln2_g, *qn_g, *kn_g, *lnf_g, *pos;
+  float *sig_w1, *sig_b1, *sig_w2, *sig_u, *sig_v;
+  float *r_w1, *r_b1, *r_w2, *r_b2, *r_a, *r_b;
+  float *w_act, *w_out, *b_out;
+  float* stage;
+  size_t stage_elems;
+
+  // workspace
+  float *x, *cvec, *xnorm, *state_tok, *goal_tok, *x_work, *sig_dev, *coefs_dev, *tok_sqerr, *zbuf;
+  float *in_state, *in_goal, *in_x;  // device staging of the *_host entry points
+  __nv_bfloat16 *hA, *qkv, *attn, *perm, *hbuf, *ybuf, *st_bf16, *goal_bf16;
+  int *topk_idx, *sel_idx, *pos_tab, *num_tiles, *dense_counts;
+  float *topk_w, *sel_w, *probs, *logits;
+  GemmMTile *up_tiles, *down_tiles, *dense_tiles;
+  unsigned long long *usage, *tokens;
+  int dense_cap;  // tiles per dense table
+  int cur_B = -1;
+
+  CUtensorMap tm_hA, tm_attn, tm_perm, tm_h, tm_st, tm_goal;
+  CUtensorMap tm_wqkv, tm_wproj, tm_wup, tm_wdown, tm_wtok, tm_wgoal;
+
+  cudaStream_t cap_stream = nullptr;
+  std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+  std::map<std::pair<int, int>, int64_t> graph_launches;
+  int64_t launch_count = 0;
+};
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int get_encode_fn() {
+  if (g_encode) return MODE_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CU_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) return fail(MODE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return MODE_OK;
+}
+
+// K-major bf16 matrix [rows, cols]; tiles of {64 columns, box_rows rows}, 128-byte swizzle (matches make_smem_desc_sw128).
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  RET_IF(get_encode_fn());
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MODE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return MODE_OK;
+}
+
+template <typename T>
+static int dev_alloc(mode_engine* e, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  const size_t bytes = (n ? n : 1) * sizeof(T);
+  cudaError_t err = cudaMalloc(&q, bytes);
+  if (err != cudaSuccess) return fail(MODE_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+  if (zero) {
+    err = cudaMemset(q, 0, bytes);
+    if (err != cudaSuccess) return fail(MODE_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(err));
+  }
+  if (e) e->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return MODE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+static int g_attr_done = 0;
+template <int EPI>
+static int gemm_set_attr() {
+  CU_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  return MODE_OK;
+}
+static int set_kernel_attrs() {
+  if (g_attr_done) return MODE_OK;
+  RET_IF(gemm_set_attr<EPI_BIAS_BF16>());
+  RET_IF(gemm_set_attr<EPI_RESID_F32>());
+  RET_IF(gemm_set_attr<EPI_SWIGLU_BF16>());
+  RET_IF(gemm_set_attr<EPI_PLAIN_BF16>());
+  RET_IF(gemm_set_attr<EPI_PLAIN_F32>());
+  g_attr_done = 1;
+  return MODE_OK;
+}
+
+static int launch_gemm(int epi, int num_sms, cudaStream_t st, const GemmParams& p) {
+  dim3 grid(num_sms), block(GEMM_THREADS);
+  switch (epi) {
+    case EPI_BIAS_BF16: gemm_tcgen05_kernel<EPI_BIAS_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+    case EPI_RESID_F32: gemm_tcgen05_kernel<EPI_RESID_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+    case EPI_SWIGLU_BF16: gemm_tcgen05_kernel<EPI_SWIGLU_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+    case EPI_PLAIN_BF16: gemm_tcgen05_kernel<EPI_PLAIN_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+    case EPI_PLAIN_F32: gemm_tcgen05_kernel<EPI_PLAIN_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+    default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+  }
+  CU_OK(cudaGetLastError());
+  return MODE_OK;
+}
+
+// p.B == 0 only configures the kernel (opt-in shared memory); done at create time so that nothing but launches happens
+// while the DDIM loop is being captured into a CUDA graph.
+template <int DH, int MT>
+static int launch_attn_t(cudaStream_t st, const AttnParams& p) {
+  constexpr int smem = ATTN_WARPS * 3 * (16 * MT) * (DH + 8) * 2;
+  static bool attr = false;
+  if (!attr) {
+    CU_OK(cudaFuncSetAttribute(attention_kernel<DH, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  if (p.B == 0) return MODE_OK;
+  const int items = p.B * p.H;
+  attention_kernel<DH, MT><<<(items + ATTN_WARPS - 1) / ATTN_WARPS, ATTN_WARPS * 32, smem, st>>>(p);
+  CU_OK(cudaGetLastError());
+  return MODE_OK;
+}
+template <int DH>
+static int launch_attn_dh(cudaStream_t st, const AttnParams& p) {
+  const int mt = (p.T + 15) / 16;
+  switch (mt) {
+    case 1: return launch_attn_t<DH, 1>(st, p);
+    case 2: return launch_attn_t<DH, 2>(st, p);
+    case 3: return launch_attn_t<DH, 3>(st, p);
+    case 4: return launch_attn_t<DH, 4>(st, p);
+    default: return fail(MODE_ERR_INVALID, "attention supports T <= 64 tokens (got %d)", p.T);
+  }
+}
+static int launch_attn(cudaStream_t st, const AttnParams& p, int Dh) {
+  switch (Dh) {
+    case 32: return launch_attn_dh<32>(st, p);
+    case 64: return launch_attn_dh<64>(st, p);
+    case 128: return launch_attn_dh<128>(st, p);
+    default: return fail(MODE_ERR_INVALID, "head dim must be 32, 64 or 128 (got %d)", Dh);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ create / destroy
+static void add_spec(mode_engine* e, const std::string& name, void* dst, size_t row0, int rows, int cols, int half,
+                     int bf16, bool ignore = false) {
+  WeightSpec s;
+  s.dst = dst;
+  s.dst_row0 = row0;
+  s.rows = rows;
+  s.cols = cols;
+  s.swiglu_half = half;
+  s.to_bf16 = bf16;
+  s.ignore = ignore;
+  s.provided = false;
+  e->specs[name] = s;
+}
+
+extern "C" void mode_destroy(mode_engine_t* e) {
+  if (!e) return;
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
+  if (!c || !out) return fail(MODE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int dev = 0;
+  CU_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(MODE_ERR_CUDA, "this library only runs on sm_100 (B200); device %d is sm_%d%d — there is no fallback path",
+                dev, prop.major, prop.minor);
+  const int d = c->embed_dim;
+  if (d <= 0 || d % 256 != 0 || d > MAX_D) return fail(MODE_ERR_INVALID, "embed_dim must be a multiple of 256 and <= %d", MAX_D);
+  if (c->n_heads <= 0 || d % c->n_heads != 0) return fail(MODE_ERR_INVALID, "embed_dim %% n_heads != 0");
+  const int Dh = d / c->n_heads;
+  if (Dh != 32 && Dh != 64 && Dh != 128) return fail(MODE_ERR_INVALID, "head dim %d unsupported (32/64/128)", Dh);
+  if (c->num_experts < 1 || c->num_experts > MAX_EXPERTS) return fail(MODE_ERR_INVALID, "num_experts must be in [1, %d]", MAX_EXPERTS);
+  if (c->top_k < 1 || c->top_k > MAX_TOPK || c->top_k > c->num_experts) return fail(MODE_ERR_INVALID, "top_k must be in [1, min(%d, num_experts)]", MAX_TOPK);
+  if (c->action_dim < 1 || c->action_dim > 8) return fail(MODE_ERR_INVALID, "action_dim must be in [1, 8]");
+  if (c->obs_dim % 64 || c->goal_dim % 64 || c->obs_dim <= 0 || c->goal_dim <= 0)
+    return fail(MODE_ERR_INVALID, "obs_dim and goal_dim must be positive multiples of 64");
+  if (c->n_state_tokens < 1 || c->action_seq_len < 1) return fail(MODE_ERR_INVALID, "n_state_tokens / action_seq_len must be >= 1");
+  const int T = 2 + c->n_state_tokens + c->action_seq_len;
+  if (T > ATTN_MAX_TPAD) return fail(MODE_ERR_INVALID, "token sequence %d exceeds %d", T, ATTN_MAX_TPAD);
+  if (c->max_batch < 1 || c->n_layers < 1) return fail(MODE_ERR_INVALID, "max_batch / n_layers must be >= 1");
+  RET_IF(set_kernel_attrs());
+  {
+    AttnParams cfg_only{};
+    cfg_only.T = T;
+    RET_IF(launch_attn(nullptr, cfg_only, Dh));
+  }
+
+  mode_engine* e = new mode_engine();
+  e->cfg = *c;
+  e->d = d; e->L = c->n_layers; e->H = c->n_heads; e->Dh = Dh; e->E = c->num_experts; e->K = c->top_k;
+  e->T = T; e->S = c->n_state_tokens; e->A = c->action_seq_len; e->adim = c->action_dim; e->maxB = c->max_batch;
+  e->maxM = e->maxB * T; e->Hd = 2 * d; e->F = 4 * d; e->obs = c->obs_dim; e->gdim = c->goal_dim;
+  e->num_sms = prop.multiProcessorCount;
+  const int L = e->L, E = e->E, K = e->K, Hd = e->Hd, F = e->F;
+  const int maxM_pad = round_up(e->maxM, 128);
+  e->max_tiles = (K * e->maxM + 127) / 128 + E;
+  e->perm_rows = e->max_tiles * 128;
+  int rc = MODE_OK;
+#define A_(call) do { if (rc == MODE_OK) rc = (call); } while (0)
+  A_(dev_alloc(e, &e->w_qkv, (size_t)L * 3 * d * d));
+  A_(dev_alloc(e, &e->w_proj, (size_t)L * d * d));
+  A_(dev_alloc(e, &e->w_up, (size_t)L * E * 8 * d * d));
+  A_(dev_alloc(e, &e->w_down, (size_t)L * E * d * F));
+  A_(dev_alloc(e, &e->w_tok, (size_t)d * e->obs));
+  A_(dev_alloc(e, &e->w_goal, (size_t)d * e->gdim));
+  A_(dev_alloc(e, &e->b_qkv, (size_t)L * 3 * d));
+  A_(dev_alloc(e, &e->b_up, (size_t)L * E * 8 * d));
+  A_(dev_alloc(e, &e->ln1_g, (size_t)L * d));
+  A_(dev_alloc(e, &e->ln2_g, (size_t)L * d));
+  A_(dev_alloc(e, &e->qn_g, (size_t)L * Dh));
+  A_(dev_alloc(e, &e->kn_g, (size_t)L * Dh));
+  A_(dev_alloc(e, &e->lnf_g, (size_t)d));
+  A_(dev_alloc(e, &e->pos, (size_t)(1 + e->A) * d));
+  A_(dev_alloc(e, &e->sig_w1, (size_t)d));
+  A_(dev_alloc(e, &e->sig_b1, (size_t)d));
+  A_(dev_alloc(e, &e->sig_w2, (size_t)d * d));
+  A_(dev_alloc(e, &e->sig_u, (size_t)d));
+  A_(dev_alloc(e, &e->sig_v, (size_t)d));
+  A_(dev_alloc(e, &e->r_w1, (size_t)L * Hd * d));
+  A_(dev_alloc(e, &e->r_b1, (size_t)L * Hd));
+  A_(dev_alloc(e, &e->r_w2, (size_t)L * E * Hd));
+  A_(dev_alloc(e, &e->r_b2, (size_t)L * E));
+  A_(dev_alloc(e, &e->r_a, (size_t)L * Hd));
+  A_(dev_alloc(e, &e->r_b, (size_t)L * Hd));
+  A_(dev_alloc(e, &e->w_act, (size_t)d * e->adim));
+  A_(dev_alloc(e, &e->w_out, (size_t)e->adim * d));
+  A_(dev_alloc(e, &e->b_out, (size_t)e->adim));
+  e->stage_elems = (size_t)8 * d * d;
+  if ((size_t)d * e->obs > e->stage_elems) e->stage_elems = (size_t)d * e->obs;
+  if ((size_t)d * e->gdim > e->stage_elems) e->stage_elems = (size_t)d * e->gdim;
+  A_(dev_alloc(e, &e->stage, e->stage_elems, false));
+  // workspace
+  const int st_rows = round_up(e->maxB * e->S, 128), goal_rows = round_up(e->maxB, 128);
+  A_(dev_alloc(e, &e->x, (size_t)maxM_pad * d));
+  A_(dev_alloc(e, &e->cvec, (size_t)e->maxB * d));
+  A_(dev_alloc(e, &e->xnorm, (size_t)maxM_pad * d));
+  A_(dev_alloc(e, &e->state_tok, (size_t)st_rows * d));
+  A_(dev_alloc(e, &e->goal_tok, (size_t)goal_rows * d));
+  A_(dev_alloc(e, &e->x_work, (size_t)e->maxB * e->A * e->adim));
+  A_(dev_alloc(e, &e->sig_dev, 64 + (size_t)e->maxB));
+  A_(dev_alloc(e, &e->coefs_dev, 128));
+  A_(dev_alloc(e, &e->tok_sqerr, (size_t)e->maxB * e->A));
+  A_(dev_alloc(e, &e->zbuf, (size_t)e->maxB * Hd));
+  A_(dev_alloc(e, &e->in_state, (size_t)e->maxB * e->S * e->obs));
+  A_(dev_alloc(e, &e->in_goal, (size_t)e->maxB * e->gdim));
+  A_(dev_alloc(e, &e->in_x, (size_t)e->maxB * e->A * e->adim));
+  A_(dev_alloc(e, &e->hA, (size_t)maxM_pad * d));
+  A_(dev_alloc(e, &e->qkv, (size_t)maxM_pad * 3 * d));
+  A_(dev_alloc(e, &e->attn, (size_t)maxM_pad * d));
+  A_(dev_alloc(e, &e->perm, (size_t)e->perm_rows * d));
+  A_(dev_alloc(e, &e->hbuf, (size_t)e->perm_rows * F));
+  A_(dev_alloc(e, &e->ybuf, (size_t)e->perm_rows * d));
+  A_(dev_alloc(e, &e->st_bf16, (size_t)st_rows * e->obs));
+  A_(dev_alloc(e, &e->goal_bf16, (size_t)goal_rows * e->gdim));
+  A_(dev_alloc(e, &e->topk_idx, (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->sel_idx, (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->pos_tab, (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->topk_w, (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->sel_w, (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->probs, (size_t)L * e->maxB * E));
+  A_(dev_alloc(e, &e->logits, (size_t)L * e->maxB * E));
+  A_(dev_alloc(e, &e->up_tiles, (size_t)L * e->max_tiles));
+  A_(dev_alloc(e, &e->down_tiles, (size_t)L * e->max_tiles));
+  A_(dev_alloc(e, &e->num_tiles, (size_t)L));
+  e->dense_cap = maxM_pad / 128;
+  A_(dev_alloc(e, &e->dense_tiles, (size_t)3 * e->dense_cap));
+  A_(dev_alloc(e, &e->dense_counts, 3));
+  A_(dev_alloc(e, &e->usage, (size_t)L * E));
+  A_(dev_alloc(e, &e->tokens, (size_t)L));
+  // tensor maps
+  A_(make_tmap(&e->tm_hA, e->hA, maxM_pad, d, 128));
+  A_(make_tmap(&e->tm_attn, e->attn, maxM_pad, d, 128));
+  A_(make_tmap(&e->tm_perm, e->perm, e->perm_rows, d, 128));
+  A_(make_tmap(&e->tm_h, e->hbuf, e->perm_rows, F, 128));
+  A_(make_tmap(&e->tm_st, e->st_bf16, st_rows, e->obs, 128));
+  A_(make_tmap(&e->tm_goal, e->goal_bf16, goal_rows, e->gdim, 128));
+  A_(make_tmap(&e->tm_wqkv, e->w_qkv, (uint64_t)L * 3 * d, d, 256));
+  A_(make_tmap(&e->tm_wproj, e->w_proj, (uint64_t)L * d, d, 256));
+  A_(make_tmap(&e->tm_wup, e->w_up, (uint64_t)L * E * 8 * d, d, 256));
+  A_(make_tmap(&e->tm_wdown, e->w_down, (uint64_t)L * E * d, F, 256));
+  A_(make_tmap(&e->tm_wtok, e->w_tok, d, e->obs, 256));
+  A_(make_tmap(&e->tm_wgoal, e->w_goal, d, e->gdim, 256));
+  if (rc == MODE_OK && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+    rc = fail(MODE_ERR_CUDA, "cudaStreamCreate failed");
+#undef A_
+  if (rc != MODE_OK) {
+    mode_destroy(e);
+    return rc;
+  }
+  // expected state_dict (reference names and shapes; SURVEY.md §8b "Weights contract")
+  add_spec(e, "pos_emb", e->pos, 0, 1 + e->A, d, 0, 0);
+  add_spec(e, "sigma_emb.weight", e->sig_w1, 0, d, 1, 0, 0);
+  add_spec(e, "sigma_emb.bias", e->sig_b1, 0, 1, d, 0, 0);
+  add_spec(e, "sigma_linear.weight", e->sig_w2, 0, d, d, 0, 0);
+  add_spec(e, "tok_emb.weight", e->w_tok, 0, d, e->obs, 0, 1);
+  add_spec(e, "gripper_embed.weight", nullptr, 0, d, e->obs, 0, 0, true);
+  add_spec(e, "goal_emb.weight", e->w_goal, 0, d, e->gdim, 0, 1);
+  add_spec(e, "action_emb.weight", e->w_act, 0, d, e->adim, 0, 0);
+  add_spec(e, "ln.g", e->lnf_g, 0, 1, d, 0, 0);
+  add_spec(e, "out.weight", e->w_out, 0, e->adim, d, 0, 0);
+  add_spec(e, "out.bias", e->b_out, 0, 1, e->adim, 0, 0);
+  for (int l = 0; l < L; ++l) {
+    const std::string b = "blocks." + std::to_string(l) + ".";
+    add_spec(e, b + "ln_1.g", e->ln1_g + (size_t)l * d, 0, 1, d, 0, 0);
+    add_spec(e, b + "ln_2.g", e->ln2_g + (size_t)l * d, 0, 1, d, 0, 0);
+    add_spec(e, b + "attn.query.weight", e->w_qkv, (size_t)l * 3 * d, d, d, 0, 1);
+    add_spec(e, b + "attn.key.weight", e->w_qkv, (size_t)l * 3 * d + d, d, d, 0, 1);
+    add_spec(e, b + "attn.value.weight", e->w_qkv, (size_t)l * 3 * d + 2 * d, d, d, 0, 1);
+    add_spec(e, b + "attn.query.bias", e->b_qkv + (size_t)l * 3 * d, 0, 1, d, 0, 0);
+    add_spec(e, b + "attn.key.bias", e->b_qkv + (size_t)l * 3 * d + d, 0, 1, d, 0, 0);
+    add_spec(e, b + "attn.value.bias", e->b_qkv + (size_t)l * 3 * d + 2 * d, 0, 1, d, 0, 0);
+    add_spec(e, b + "attn.c_proj.weight", e->w_proj, (size_t)l * d, d, d, 0, 1);
+    add_spec(e, b + "attn.q_norm.g", e->qn_g + (size_t)l * Dh, 0, 1, Dh, 0, 0);
+    add_spec(e, b + "attn.k_norm.g", e->kn_g + (size_t)l * Dh, 0, 1, Dh, 0, 0);
+    add_spec(e, b + "router.router.mlp.0.weight", e->r_w1 + (size_t)l * Hd * d, 0, Hd, d, 0, 0);
+    add_spec(e, b + "router.router.mlp.0.bias", e->r_b1 + (size_t)l * Hd, 0, 1, Hd, 0, 0);
+    add_spec(e, b + "router.router.mlp.3.weight", e->r_w2 + (size_t)l * E * Hd, 0, E, Hd, 0, 0);
+    add_spec(e, b + "router.router.mlp.3.bias", e->r_b2 + (size_t)l * E, 0, 1, E, 0, 0);
+    for (int x = 0; x < E; ++x) {
+      const std::string eb = b + "experts.expert_" + std::to_string(x) + ".mlp.";
+      add_spec(e, eb + "0.project.weight", e->w_up, ((size_t)l * E + x) * 8 * d, 8 * d, d, F, 1);
+      // bias: a column vector packed with the same row interleave
+      add_spec(e, eb + "0.project.bias", e->b_up, ((size_t)l * E + x) * 8 * d, 8 * d, 1, F, 0);
+      add_spec(e, eb + "2.weight", e->w_down, ((size_t)l * E + x) * d, d, F, 0, 1);
+    }
+  }
+  *out = e;
+  return MODE_OK;
+}
+
+extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* data, int is_device,
+                               const int64_t* shape, int ndim) {
+  if (!e || !name || !data) return fail(MODE_ERR_INVALID, "null argument");
+  auto it = e->specs.find(name);
+  if (it == e->specs.end()) return fail(MODE_ERR_UNKNOWN_NAME, "'%s' is not a MoDeDiT state_dict key for this configuration", name);
+  WeightSpec& s = it->second;
+  size_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= (size_t)shape[i];
+  if (numel != (size_t)s.rows * s.cols)
+    return fail(MODE_ERR_INVALID, "'%s': expected %zu elements, got %zu", name, (size_t)s.rows * s.cols, numel);
+  s.provided = true;
+  e->finalized = false;
+  if (s.ignore) return MODE_OK;
+  if (numel > e->stage_elems) return fail(MODE_ERR_INVALID, "'%s' larger than the staging buffer", name);
+  CU_OK(cudaMemcpy(e->stage, data, numel * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((numel + threads - 1) / threads);
+  pack_rows_kernel<<<blocks, threads>>>(e->stage, s.dst, s.rows, s.cols, s.dst_row0, s.swiglu_half, s.to_bf16);
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaDeviceSynchronize());
+  return MODE_OK;
+}
+
+extern "C" int mode_finalize_weights(mode_engine_t* e) {
+  if (!e) return fail(MODE_ERR_INVALID, "null engine");
+  for (auto& kv : e->specs)
+    if (!kv.second.provided && !kv.second.ignore) return fail(MODE_ERR_STATE, "weight '%s' was never set", kv.first.c_str());
+  const int d = e->d, Hd = e->Hd;
+  // emb_t(s) = sigma_linear(sigma_emb(s)) = s * (W2 w1) + (W2 b1)            (modedit.py:823-832)
+  matvec_f64_kernel<<<(d + 7) / 8, 256>>>(e->sig_w2, e->sig_w1, nullptr, e->sig_u, d, d);
+  matvec_f64_kernel<<<(d + 7) / 8, 256>>>(e->sig_w2, e->sig_b1, nullptr, e->sig_v, d, d);
+  // router first Linear on c = emb_t(s): s * (W1 u) + (W1 v + b1)            (modedit.py:304-310, :336)
+  for (int l = 0; l < e->L; ++l) {
+    const float* W1 = e->r_w1 + (size_t)l * Hd * d;
+    matvec_f64_kernel<<<(Hd + 7) / 8, 256>>>(W1, e->sig_u, nullptr, e->r_a + (size_t)l * Hd, Hd, d);
+    matvec_f64_kernel<<<(Hd + 7) / 8, 256>>>(W1, e->sig_v, e->r_b1 + (size_t)l * Hd, e->r_b + (size_t)l * Hd, Hd, d);
+  }
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaDeviceSynchronize());
+  e->finalized = true;
+  return MODE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batch tables
+static int ensure_batch(mode_engine* e, int B) {
+  if (B < 1 || B > e->maxB) return fail(MODE_ERR_INVALID, "batch %d outside [1, max_batch=%d]", B, e->maxB);
+  if (!e->finalized) return fail(MODE_ERR_STATE, "mode_finalize_weights has not been called");
+  if (B == e->cur_B) return MODE_OK;
+  std::vector<GemmMTile> tiles(3 * (size_t)e->dense_cap);
+  int counts[3];
+  const int rows[3] = {B * e->T, B * e->S, B};
+  for (int k = 0; k < 3; ++k) {
+    const int n = (rows[k] + 127) / 128;
+    counts[k] = n;
+    for (int i = 0; i < n; ++i) {
+      GemmMTile t;
+      t.a_row0 = i * 128;
+      t.out_row0 = i * 128;
+      t.rows_valid = rows[k] - i * 128 < 128 ? rows[k] - i * 128 : 128;
+      t.w_row_base = 0;
+      tiles[(size_t)k * e->dense_cap + i] = t;
+    }
+  }
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(e->dense_tiles, tiles.data(), tiles.size() * sizeof(GemmMTile), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(e->dense_counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
+  e->cur_B = B;
+  return MODE_OK;
+}
+
+static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, const GemmMTile* tiles, const int* ntiles,
+                              int N, int Kdim, void* out, int ld, const float* bias, const float* resid) {
+  GemmParams p;
+  p.tmap_a = ta;
+  p.tmap_w = tw;
+  p.m_tiles = tiles;
+  p.num_m_tiles = ntiles;
+  p.n_blocks = N / GEMM_BLOCK_N;
+  p.k_blocks = Kdim / GEMM_BLOCK_K;
+  p.out = out;
+  p.ld_out = ld;
+  p.bias = bias;
+  p.resid = resid;
+  p.w_row_off = 0;
+  return p;
+}
+
+static inline unsigned row_blocks(int rows) { return (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS); }
+
+// obs / goal token embeddings: computed once per trajectory, not per denoising step.
+static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* state_dev, const float* goal_dev) {
+  const size_t n_st = (size_t)B * e->S * e->obs / 4, n_g = (size_t)B * e->gdim / 4;
+  cast_bf16_kernel<<<(unsigned)((n_st + 255) / 256), 256, 0, st>>>(state_dev, e->st_bf16, n_st);
+  cast_bf16_kernel<<<(unsigned)((n_g + 255) / 256), 256, 0, st>>>(goal_dev, e->goal_bf16, n_g);
+  CU_OK(cudaGetLastError());
+  GemmParams p = gemm_params(e->tm_st, e->tm_wtok, e->dense_tiles + e->dense_cap, e->dense_counts + 1, e->d, e->obs,
+                             e->state_tok, e->d, nullptr, nullptr);
+  RET_IF(launch_gemm(EPI_PLAIN_F32, e->num_sms, st, p));
+  p = gemm_params(e->tm_goal, e->tm_wgoal, e->dense_tiles + 2 * e->dense_cap, e->dense_counts + 2, e->d, e->gdim,
+                  e->goal_tok, e->d, nullptr, nullptr);
+  RET_IF(launch_gemm(EPI_PLAIN_F32, e->num_sms, st, p));
+  e->launch_count += 4;
+  return MODE_OK;
+}
+
+static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* z_explicit,
+                           int layer0, int n_layers) {
+  RouterParams r;
+  r.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
+  r.ra = e->r_a; r.rb = e->r_b; r.w2 = e->r_w2; r.b2 = e->r_b2;
+  r.z_explicit = z_explicit;
+  r.topk_idx = e->topk_idx; r.topk_w = e->topk_w; r.sel_idx = e->sel_idx; r.sel_w = e->sel_w;
+  r.probs = e->probs; r.logits = e->logits;
+  r.L = n_layers; r.layer0 = layer0; r.B = B; r.E = e->E; r.K = e->K; r.Hd = e->Hd; r.normalize = e->cfg.router_normalize;
+  router_kernel<<<row_blocks(n_layers * B), ROW_WARPS * 32, 0, st>>>(r);
+  PlanParams pl;
+  pl.sel_idx = e->sel_idx; pl.pos = e->pos_tab; pl.up_tiles = e->up_tiles; pl.down_tiles = e->down_tiles;
+  pl.num_tiles = e->num_tiles; pl.usage = e->usage; pl.tokens = e->tokens;
+  pl.L = e->L; pl.B = B; pl.K = e->K; pl.E = e->E; pl.T = e->T; pl.max_tiles = e->max_tiles;
+  pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0;
+  plan_kernel<<<n_layers, 256, 0, st>>>(pl);
+  CU_OK(cudaGetLastError());
+  e->launch_count += 2;
+  return MODE_OK;
+}
+
+// One NoiseBlockMoE (modedit.py:530-595) given hA = bf16(ln_1(x)+c) and routing tables for layer l.
+static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode) {
+  const int d = e->d, M = B * e->T;
+  GemmParams p = gemm_params(e->tm_hA, e->tm_wqkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->qkv, 3 * d,
+                             e->b_qkv, nullptr);
+  p.w_row_off = l * 3 * d;
+  RET_IF(launch_gemm(EPI_BIAS_BF16, e->num_sms, st, p));
+  AttnParams a;
+  a.qkv = e->qkv; a.out = e->attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
+  a.B = B; a.T = e->T; a.H = e->H; a.eps = e->cfg.rms_eps;
+  RET_IF(launch_attn(st, a, e->Dh));
+  p = gemm_params(e->tm_attn, e->tm_wproj, e->dense_tiles, e->dense_counts, d, d, e->x, d, nullptr, e->x);
+  p.w_row_off = l * d;
+  RET_IF(launch_gemm(EPI_RESID_F32, e->num_sms, st, p));
+  Ln2Params n2;
+  n2.x = e->x; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + (size_t)l * B * e->K; n2.perm = e->perm;
+  n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps;
+  ln2_permute_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(n2);
+  CU_OK(cudaGetLastError());
+  p = gemm_params(e->tm_perm, e->tm_wup, e->up_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, 8 * d, d, e->hbuf,
+                  e->F, e->b_up, nullptr);
+  RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->num_sms, st, p));
+  p = gemm_params(e->tm_h, e->tm_wdown, e->down_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, d, e->F, e->ybuf, d,
+                  nullptr, nullptr);
+  RET_IF(launch_gemm(EPI_PLAIN_BF16, e->num_sms, st, p));
+  CombineParams c;
+  c.x = e->x; c.y = e->ybuf; c.pos = e->pos_tab + (size_t)l * B * e->K; c.w = e->sel_w + (size_t)l * B * e->K;
+  c.g_next = (combine_mode == 0) ? e->ln1_g + (size_t)(l + 1) * d : e->lnf_g;
+  c.cvec = e->cvec; c.hA = e->hA; c.xnorm = e->xnorm;
+  c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps;
+  combine_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(c);
+  CU_OK(cudaGetLastError());
+  e->launch_count += 7;
+  return MODE_OK;
+}
+
+// One network evaluation: router + plan + embed + L blocks + head. head_mode as HeadParams.mode.
+static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* actions,
+                        int apply_c_in, int head_mode, float* out, const float* coefs, const float* clean) {
+  RET_IF(enqueue_routing(e, st, B, sigma, stride, nullptr, 0, e->L));
+  EmbedParams em;
+  em.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
+  em.sig_u = e->sig_u; em.sig_v = e->sig_v; em.goal_tok = e->goal_tok; em.state_tok = e->state_tok; em.pos = e->pos;
+  em.w_act = e->w_act; em.actions = actions; em.ln1_g = e->ln1_g; em.x = e->x; em.cvec = e->cvec; em.hA = e->hA;
+  em.B = B; em.T = e->T; em.S = e->S; em.A = e->A; em.action_dim = e->adim; em.d = e->d; em.apply_c_in = apply_c_in;
+  em.eps = e->cfg.rms_eps;
+  embed_kernel<<<row_blocks(B * e->T), ROW_WARPS * 32, 0, st>>>(em);
+  CU_OK(cudaGetLastError());
+  for (int l = 0; l < e->L; ++l) RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1));
+  HeadParams h;
+  h.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
+  h.xnorm = e->xnorm; h.w_out = e->w_out; h.b_out = e->b_out; h.x_act = actions; h.out = out; h.clean = clean;
+  h.tok_sqerr = e->tok_sqerr; h.coefs = coefs;
+  h.B = B; h.T = e->T; h.A = e->A; h.action_dim = e->adim; h.d = e->d; h.mode = head_mode;
+  head_kernel<<<row_blocks(B * e->A), ROW_WARPS * 32, 0, st>>>(h);
+  CU_OK(cudaGetLastError());
+  e->launch_count += 2;
+  return MODE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ public entry points
+static int eval_common(mode_engine* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
+                       const float* sigma_dev, int sigma_stride, float* out_dev, int B, void* stream, int apply_c_in,
+                       int head_mode) {
+  if (!e || !state_dev || !goal_dev || !actions_dev || !sigma_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
+  if (sigma_stride != 0 && sigma_stride != 1) return fail(MODE_ERR_INVALID, "sigma_stride must be 0 or 1");
+  RET_IF(ensure_batch(e, B));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->launch_count = 0;
+  RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
+  return enqueue_eval(e, st, B, sigma_dev, sigma_stride, actions_dev, apply_c_in, head_mode, out_dev, nullptr, nullptr);
+}
+
+extern "C" int mode_forward(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
+                            const float* sigma_dev, int sigma_stride, float* out_dev, int B, void* stream) {
+  return eval_common(e, state_dev, goal_dev, actions_dev, sigma_dev, sigma_stride, out_dev, B, stream, 0, 0);
+}
+
+extern "C" int mode_denoise(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
+                            const float* sigma_dev, int sigma_stride, float* out_dev, int B, void* stream) {
+  return eval_common(e, state_dev, goal_dev, actions_dev, sigma_dev, sigma_stride, out_dev, B, stream, 1, 1);
+}
+
+extern "C" int mode_loss(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* action_dev,
+                         const float* noise_dev, const float* sigma_dev, float* loss_dev, float* out_dev, int B,
+                         void* stream) {
+  if (!e || !state_dev || !goal_dev || !action_dev || !noise_dev || !sigma_dev || !loss_dev)
+    return fail(MODE_ERR_INVALID, "null argument");
+  RET_IF(ensure_batch(e, B));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->launch_count = 0;
+  const int per = e->A * e->adim, n = B * per;
+  noise_actions_kernel<<<(n + 255) / 256, 256, 0, st>>>(action_dev, noise_dev, sigma_dev, e->x_work, per, n);
+  CU_OK(cudaGetLastError());
+  RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
+  RET_IF(enqueue_eval(e, st, B, sigma_dev, 1, e->x_work, 1, 3, out_dev, nullptr, action_dev));
+  loss_reduce_kernel<<<1, 256, 0, st>>>(e->tok_sqerr, B * e->A, (float)n, loss_dev);
+  CU_OK(cudaGetLastError());
+  e->launch_count += 2;
+  return MODE_OK;
+}
+
+static int get_ddim_graph(mode_engine* e, int B, int n, cudaGraphExec_t* exec) {
+  const auto key = std::make_pair(B, n);
+  auto it = e->graphs.find(key);
+  if (it != e->graphs.end()) {
+    *exec = it->second;
+    e->launch_count += e->graph_launches[key];
+    return MODE_OK;
+  }
+  const int64_t before = e->launch_count;
+  cudaGraph_t graph = nullptr;
+  CU_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = MODE_OK;
+  for (int i = 0; i < n && rc == MODE_OK; ++i)
+    rc = enqueue_eval(e, e->cap_stream, B, e->sig_dev + i, 0, e->x_work, 1, 2, e->x_work, e->coefs_dev + 2 * i, nullptr);
+  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+  if (rc != MODE_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+  cudaGraphExec_t ex = nullptr;
+  ce = cudaGraphInstantiate(&ex, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+  e->graphs[key] = ex;
+  e->graph_launches[key] = e->launch_count - before;
+  *exec = ex;
+  return MODE_OK;
+}
+
+// DDIM / DPM-Solver-1 step coefficients in fp32, following the op order of sample_ddim (gc_sampling.py:936-950).
+static void ddim_schedule(const float* sigmas, int n, ScheduleArg* a) {
+  a->n = n;
+  for (int i = 0; i < n; ++i) {
+    const float s = sigmas[i], sn = sigmas[i + 1];
+    const float t = -logf(s), tn = -logf(sn);  // t_fn = sigma.log().neg(); log(0) = -inf -> tn = +inf
+    const float h = tn - t;
+    const float ratio = expf(-tn) / expf(-t);  // sigma_fn(t_next) / sigma_fn(t)
+    const float em1 = expm1f(-h);              // (-h).expm1()
+    a->v[3 * i] = s;
+    a->v[3 * i + 1] = ratio;
+    a->v[3 * i + 2] = em1;
+  }
+}
+
+extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                                const float* sigmas_host, int n_plus_1, int B, void* stream) {
+  if (!e || !state_dev || !goal_dev || !x_inout_dev || !sigmas_host) return fail(MODE_ERR_INVALID, "null argument");
+  const int n = n_plus_1 - 1;
+  if (n < 1 || n > 64) return fail(MODE_ERR_INVALID, "number of sampling steps must be in [1, 64]");
+  for (int i = 0; i < n; ++i)
+    if (!(sigmas_host[i] > 0.f)) return fail(MODE_ERR_INVALID, "sigmas[%d] must be > 0", i);
+  RET_IF(ensure_batch(e, B));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->launch_count = 0;
+  cudaGraphExec_t exec = nullptr;
+  RET_IF(get_ddim_graph(e, B, n, &exec));
+  ScheduleArg sa;
+  ddim_schedule(sigmas_host, n, &sa);
+  set_schedule_kernel<<<1, 64, 0, st>>>(sa, e->sig_dev, e->coefs_dev);
+  CU_OK(cudaGetLastError());
+  const size_t xbytes = (size_t)B * e->A * e->adim * sizeof(float);
+  CU_OK(cudaMemcpyAsync(e->x_work, x_inout_dev, xbytes, cudaMemcpyDeviceToDevice, st));
+  RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
+  CU_OK(cudaGraphLaunch(exec, st));
+  CU_OK(cudaMemcpyAsync(x_inout_dev, e->x_work, xbytes, cudaMemcpyDeviceToDevice, st));
+  e->launch_count += 1;
+  return MODE_OK;
+}
+
+extern "C" int mode_sample_ddim_host(mode_engine_t* e, const float* state_host, const float* goal_host,
+                                     float* x_inout_host, const float* sigmas_host, int n_plus_1, int B, void* stream) {
+  if (!e || !state_host || !goal_host || !x_inout_host) return fail(MODE_ERR_INVALID, "null argument");
+  RET_IF(ensure_batch(e, B));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n_state = (size_t)B * e->S * e->obs, n_goal = (size_t)B * e->gdim, n_x = (size_t)B * e->A * e->adim;
+  CU_OK(cudaMemcpyAsync(e->in_state, state_host, n_state * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(cudaMemcpyAsync(e->in_goal, goal_host, n_goal * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_OK(cudaMemcpyAsync(e->in_x, x_inout_host, n_x * sizeof(float), cudaMemcpyHostToDevice, st));
+  RET_IF(mode_sample_ddim(e, e->in_state, e->in_goal, e->in_x, sigmas_host, n_plus_1, B, stream));
+  CU_OK(cudaMemcpyAsync(x_inout_host, e->in_x, n_x * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(cudaStreamSynchronize(st));
+  return MODE_OK;
+}
+
+extern "C" int mode_block_forward(mode_engine_t* e, int layer, const float* x_dev, const float* c_dev, float* out_dev,
+                                  int B, void* stream) {
+  if (!e || !x_dev || !c_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
+  if (layer < 0 || layer >= e->L) return fail(MODE_ERR_INVALID, "layer %d out of range", layer);
+  RET_IF(ensure_batch(e, B));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->launch_count = 0;
+  const int d = e->d, M = B * e->T;
+  CU_OK(cudaMemcpyAsync(e->x, x_dev, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CU_OK(cudaMemcpyAsync(e->cvec, c_dev, (size_t)B * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // generic router input: z = W1 c + b1 for an arbitrary conditioning vector
+  router_hidden_kernel<<<(unsigned)((B * e->Hd + 7) / 8), 256, 0, st>>>(e->r_w1 + (size_t)layer * e->Hd * d,
+                                                                        e->r_b1 + (size_t)layer * e->Hd, e->cvec, e->zbuf,
+                                                                        B, e->Hd, d);
+  CU_OK(cudaGetLastError());
+  RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, e->zbuf, layer, 1));
+  Ln1Params l1;
+  l1.x = e->x; l1.cvec = e->cvec; l1.g = e->ln1_g + (size_t)layer * d; l1.hA = e->hA; l1.rows = M; l1.T = e->T; l1.d = d;
+  l1.eps = e->cfg.rms_eps;
+  ln1_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(l1);
+  CU_OK(cudaGetLastError());
+  RET_IF(enqueue_block(e, st, B, layer, 2));
+  CU_OK(cudaMemcpyAsync(out_dev, e->x, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  e->launch_count += 2;
+  return MODE_OK;
+}
+
+extern "C" int mode_get_routing(mode_engine_t* e, int layer, int B, int32_t* idx_host, float* w_host, float* probs_host) {
+  if (!e) return fail(MODE_ERR_INVALID, "null engine");
+  if (layer < 0 || layer >= e->L || B < 1 || B > e->maxB) return fail(MODE_ERR_INVALID, "layer/B out of range");
+  CU_OK(cudaDeviceSynchronize());
+  const size_t o = (size_t)layer * B * e->K;
+  if (idx_host) CU_OK(cudaMemcpy(idx_host, e->topk_idx + o, (size_t)B * e->K * sizeof(int), cudaMemcpyDeviceToHost));
+  if (w_host) CU_OK(cudaMemcpy(w_host, e->topk_w + o, (size_t)B * e->K * sizeof(float), cudaMemcpyDeviceToHost));
+  if (probs_host)
+    CU_OK(cudaMemcpy(probs_host, e->probs + (size_t)layer * B * e->E, (size_t)B * e->E * sizeof(float), cudaMemcpyDeviceToHost));
+  return MODE_OK;
+}
+
+extern "C" int mode_get_expert_usage(mode_engine_t* e, int layer, int64_t* usage_host, int64_t* total_tokens_host) {
+  if (!e || layer < 0 || layer >= e->L) return fail(MODE_ERR_INVALID, "bad engine/layer");
+  CU_OK(cudaDeviceSynchronize());
+  if (usage_host) CU_OK(cudaMemcpy(usage_host, e->usage + (size_t)layer * e->E, e->E * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (total_tokens_host) CU_OK(cudaMemcpy(total_tokens_host, e->tokens + layer, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return MODE_OK;
+}
+
+extern "C" int mode_reset_expert_usage(mode_engine_t* e) {
+  if (!e) return fail(MODE_ERR_INVALID, "null engine");
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemset(e->usage, 0, (size_t)e->L * e->E * sizeof(unsigned long long)));
+  CU_OK(cudaMemset(e->tokens, 0, (size_t)e->L * sizeof(unsigned long long)));
+  return MODE_OK;
+}
+
+extern "C" int64_t mode_last_launch_count(const mode_engine_t* e) { return e ? e->launch_count : 0; }
+
+// ------------------------------------------------------------------------------------------------ unit-test entries
+extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
+                               void* out_dev, int M, int N, int Kdim, int epilogue, void* stream) {
+  if (!a_dev || !w_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
+  if (M < 1 || N % 256 || Kdim % 64 || N < 256 || Kdim < 64) return fail(MODE_ERR_INVALID, "need N %% 256 == 0 and K %% 64 == 0");
+  RET_IF(set_kernel_attrs());
+  int dev = 0;
+  CU_OK(cudaGetDevice(&dev));
+  int sms = 0;
+  CU_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n = (M + 127) / 128;
+  std::vector<GemmMTile> tiles(n);
+  for (int i = 0; i < n; ++i) tiles[i] = GemmMTile{i * 128, i * 128, M - i * 128 < 128 ? M - i * 128 : 128, 0};
+  GemmMTile* d_tiles = nullptr;
+  int* d_n = nullptr;
+  RET_IF(dev_alloc<GemmMTile>(nullptr, &d_tiles, n, false));
+  RET_IF(dev_alloc<int>(nullptr, &d_n, 1, false));
+  CU_OK(cudaMemcpy(d_tiles, tiles.data(), n * sizeof(GemmMTile), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpy(d_n, &n, sizeof(int), cudaMemcpyHostToDevice));
+  CUtensorMap ta, tw;
+  // The caller allocates A with round_up(M, 128) rows so the TMA box never exceeds the tensor extent.
+  RET_IF(make_tmap(&ta, a_dev, round_up(M, 128), Kdim, 128));
+  RET_IF(make_tmap(&tw, w_dev, N, Kdim, 256));
+  const int ld = (epilogue == EPI_SWIGLU_BF16) ? N / 2 : N;
+  GemmParams p = gemm_params(ta, tw, d_tiles, d_n, N, Kdim, out_dev, ld, bias_dev, resid_dev);
+  int rc = launch_gemm(epilogue, sms, st, p);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(d_tiles);
+  cudaFree(d_n);
+  if (rc != MODE_OK) return rc;
+  if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "GEMM kernel failed: %s", cudaGetErrorString(ce));
+  return MODE_OK;
+}
+
+extern "C" int mode_debug_attention(const void* qkv_dev, const float* q_gain_dev, const float* k_gain_dev, void* out_dev,
+                                    int B, int T, int H, int Dh, float eps, void* stream) {
+  if (!qkv_dev || !q_gain_dev || !k_gain_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
+  AttnParams a;
+  a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv_dev);
+  a.out = reinterpret_cast<__nv_bfloat16*>(out_dev);
+  a.q_gain = q_gain_dev; a.k_gain = k_gain_dev; a.B = B; a.T = T; a.H = H; a.eps = eps;
+  return launch_attn(reinterpret_cast<cudaStream_t>(stream), a, Dh);
+}

@@ -1,0 +1,609 @@
+// HBM-bound row kernels of the MoDE denoising step: token embedding, RMSNorm (+sigma-conditioning add, + bf16 cast
+// for the next GEMM's A operand), router softmax/top-k, routing plan (counting sort by expert), token permute,
+// expert combine, output head + EDM preconditioning + DDIM update.
+// One warp per token row (d floats), 16-byte vector accesses, fp32 math, warp-shuffle reductions.
+#pragma once
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace mode {
+
+constexpr int ROW_WARPS = 8;        // warps per CTA for row kernels
+constexpr int MAX_D = 2048;         // embed_dim upper bound (register-resident row: MAX_D/128 float4 per lane)
+constexpr int MAX_VEC = MAX_D / 128;
+constexpr int MAX_EXPERTS = 32;     // one lane per expert in the router
+constexpr int MAX_TOPK = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// RMSNorm.forward, modedit.py:72-80: x / clamp(||x||_2 * dim^-0.5, min=eps) * g  (division then gain, as written)
+__device__ __forceinline__ float rms_denominator(float sumsq, float inv_sqrt_dim, float eps) {
+  return fmaxf(sqrtf(sumsq) * inv_sqrt_dim, eps);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Cast fp32 -> bf16 (A operand of the obs/goal embedding GEMMs).
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n4) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-sample scalars of one network evaluation. sigma_stride = 0 broadcasts one sigma to the whole batch
+// (samplers: sigmas[i] * s_in, gc_sampling.py:945); 1 = per-sample sigma (training loss, mode_agent.py:669).
+struct StepScalars {
+  const float* sigma;
+  int sigma_stride;
+  float sigma_data;
+};
+__device__ __forceinline__ float load_sigma(const StepScalars& s, int b) { return s.sigma[b * s.sigma_stride]; }
+
+// ------------------------------------------------------------------------------------------------------------
+// Token embedding + layer-0 ln_1 (+c): builds the input sequence (MoDeDiT.forward, modedit.py:754-790, :847-860)
+//   row 0          : emb_t = sigma_linear(sigma_emb(ln(sigma)/4))  = s*u + v   (both layers are affine in s)
+//   row 1          : goal_emb(goal) + pos[0]
+//   rows 2..2+S-1  : tok_emb(state_images) + pos[1]       (every image token shares pos row 1)
+//   rows 2+S..T-1  : action_emb(action * c_in) + pos[1 + j]
+// and writes x (fp32 residual stream) and hA = bf16(rms(x)*g_ln1 + c) for the first QKV GEMM.
+struct EmbedParams {
+  StepScalars sc;
+  const float* sig_u;      // [d]  sigma_linear.weight @ sigma_emb.weight[:,0]
+  const float* sig_v;      // [d]  sigma_linear.weight @ sigma_emb.bias
+  const float* goal_tok;   // [B, d]   fp32 goal_emb(goal)       (no pos yet; computed once per trajectory)
+  const float* state_tok;  // [B*S, d] fp32 tok_emb(state_images)
+  const float* pos;        // [1+A, d]
+  const float* w_act;      // [d, action_dim]  (nn.Linear layout)
+  const float* actions;    // [B, A, action_dim]
+  const float* ln1_g;      // [d] layer-0 ln_1 gain
+  float* x;                // [B*T, d]
+  float* cvec;             // [B, d] conditioning vector c = emb_t (consumed by later kernels)
+  __nv_bfloat16* hA;       // [B*T, d]
+  int B, T, S, A, action_dim, d;
+  int apply_c_in;          // 1: GCDenoiser.forward scales the action input by c_in (score_wrappers.py:79-80)
+  float eps;
+};
+
+__global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams p) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.B * p.T) return;
+  const int b = row / p.T, t = row % p.T;
+  const int nvec = p.d / 128;
+  const float sigma = load_sigma(p.sc, b);
+  const float s = logf(sigma) / 4.0f;  // process_sigma_embeddings, modedit.py:824
+  float4 xv[MAX_VEC], cv[MAX_VEC];
+  float ss = 0.f;
+  float act[8];
+  const int n_act = p.action_dim;
+  if (t >= 2 + p.S) {
+    float c_in = 1.0f;
+    if (p.apply_c_in) c_in = 1.0f / sqrtf(sigma * sigma + p.sc.sigma_data * p.sc.sigma_data);
+    const float* a = p.actions + (static_cast<size_t>(b) * p.A + (t - 2 - p.S)) * n_act;
+    for (int j = 0; j < n_act && j < 8; ++j) act[j] = a[j] * c_in;
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nvec) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 u = *reinterpret_cast<const float4*>(p.sig_u + col);
+      const float4 v = *reinterpret_cast<const float4*>(p.sig_v + col);
+      const float4 c = make_float4(fmaf(s, u.x, v.x), fmaf(s, u.y, v.y), fmaf(s, u.z, v.z), fmaf(s, u.w, v.w));
+      cv[i] = c;
+      float4 x;
+      if (t == 0) {
+        x = c;
+      } else if (t < 2 + p.S) {
+        const float* src = (t == 1) ? p.goal_tok + static_cast<size_t>(b) * p.d
+                                    : p.state_tok + (static_cast<size_t>(b) * p.S + (t - 2)) * p.d;
+        const float4 e = *reinterpret_cast<const float4*>(src + col);
+        const float4 pe = *reinterpret_cast<const float4*>(p.pos + (t == 1 ? 0 : 1) * p.d + col);
+        x = make_float4(e.x + pe.x, e.y + pe.y, e.z + pe.z, e.w + pe.w);
+      } else {
+        const int j = t - 2 - p.S;
+        const float4 pe = *reinterpret_cast<const float4*>(p.pos + (1 + j) * p.d + col);
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* w = p.w_act + static_cast<size_t>(col + q) * n_act;
+          float acc = 0.f;
+          for (int k = 0; k < n_act && k < 8; ++k) acc = fmaf(act[k], w[k], acc);
+          e[q] = acc;
+        }
+        x = make_float4(e[0] + pe.x, e[1] + pe.y, e[2] + pe.z, e[3] + pe.w);
+      }
+      xv[i] = x;
+      ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (i < nvec) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 x = xv[i], c = cv[i];
+      const float4 g = *reinterpret_cast<const float4*>(p.ln1_g + col);
+      *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = x;
+      if (t == 0) *reinterpret_cast<float4*>(p.cvec + static_cast<size_t>(b) * p.d + col) = c;
+      const float h0 = __fdiv_rn(x.x, n) * g.x + c.x, h1 = __fdiv_rn(x.y, n) * g.y + c.y;
+      const float h2 = __fdiv_rn(x.z, n) * g.z + c.z, h3 = __fdiv_rn(x.w, n) * g.w + c.w;
+      *reinterpret_cast<uint2*>(p.hA + static_cast<size_t>(row) * p.d + col) =
+          make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Block-level entry (NoiseBlockMoE.forward, modedit.py:530-532): hA = bf16(rms(x)*g + c) for caller-supplied x, c.
+struct Ln1Params {
+  const float* x;      // [rows, d]
+  const float* cvec;   // [B, d]
+  const float* g;      // [d]
+  __nv_bfloat16* hA;   // [rows, d]
+  int rows, T, d;
+  float eps;
+};
+__global__ void __launch_bounds__(ROW_WARPS * 32) ln1_kernel(const Ln1Params p) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const int b = row / p.T;
+  const int nvec = p.d / 128;
+  float4 xv[MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nvec) {
+      const float4 x = *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.d + (i * 32 + lane) * 4);
+      xv[i] = x;
+      ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+  ss = warp_sum(ss);
+  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nvec) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 x = xv[i];
+      const float4 g = *reinterpret_cast<const float4*>(p.g + col);
+      const float4 c = *reinterpret_cast<const float4*>(p.cvec + static_cast<size_t>(b) * p.d + col);
+      *reinterpret_cast<uint2*>(p.hA + static_cast<size_t>(row) * p.d + col) =
+          make_uint2(pack_bf16x2(__fdiv_rn(x.x, n) * g.x + c.x, __fdiv_rn(x.y, n) * g.y + c.y),
+                     pack_bf16x2(__fdiv_rn(x.z, n) * g.z + c.z, __fdiv_rn(x.w, n) * g.w + c.w));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Router: noise-conditioned top-k (RouterCond.forward, modedit.py:312-421; CondRouterMLP :170-217).
+// The router only sees c = emb_t = s*u + v (router_context_cond_only, modedit.py:328-332), so its first Linear is
+// affine in the scalar s = ln(sigma)/4:  W1 c + b1 = s*(W1 u) + (W1 v + b1) =: s*ra + rb  (ra, rb precomputed in fp64
+// at weight-load time). One warp per (layer, sample): lanes stride the 2d hidden units, GELU(erf), dot with W2 rows,
+// warp-shuffle reduce, softmax, clamp(1e-9, 1-1e-9), k rounds of arg-max (lowest index wins ties), renormalise.
+struct RouterParams {
+  StepScalars sc;
+  const float* ra;   // [L, Hd]
+  const float* rb;   // [L, Hd]
+  const float* w2;   // [L, E, Hd]
+  const float* b2;   // [L, E]
+  const float* z_explicit;  // optional [B, Hd]: pre-activation of the first Linear for an arbitrary c (block entry)
+  int* topk_idx;     // [L, B, K]  descending probability (torch.topk order)
+  float* topk_w;     // [L, B, K]  renormalised probabilities, same order
+  int* sel_idx;      // [L, B, K]  the same experts sorted ascending (the reference's accumulation order, :561-566)
+  float* sel_w;      // [L, B, K]
+  float* probs;      // [L, B, E]  clamped softmax (true_probs)
+  float* logits;     // [L, B, E]  logits - max (RouterCond.logits, :345-346)
+  int L, B, E, K, Hd;
+  int layer0;        // first layer handled (block-level entry routes a single layer)
+  int normalize;
+};
+
+__global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterParams p) {
+  const int item = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (item >= p.L * p.B) return;
+  const int l = p.layer0 + item / p.B, b = item % p.B;
+  const float s = p.z_explicit ? 0.f : logf(load_sigma(p.sc, b)) / 4.0f;
+  const float* ra = p.ra + static_cast<size_t>(l) * p.Hd;
+  const float* rb = p.rb + static_cast<size_t>(l) * p.Hd;
+  const float* w2 = p.w2 + static_cast<size_t>(l) * p.E * p.Hd;
+  float acc[MAX_EXPERTS];
+#pragma unroll
+  for (int e = 0; e < MAX_EXPERTS; ++e) acc[e] = 0.f;
+  for (int j = lane; j < p.Hd; j += 32) {
+    const float z = p.z_explicit ? p.z_explicit[static_cast<size_t>(b) * p.Hd + j] : fmaf(s, ra[j], rb[j]);
+    const float hdn = 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));  // nn.GELU() (erf form)
+#pragma unroll
+    for (int e = 0; e < MAX_EXPERTS; ++e)
+      if (e < p.E) acc[e] = fmaf(hdn, w2[static_cast<size_t>(e) * p.Hd + j], acc[e]);
+  }
+  // lane e ends up owning expert e's logit
+  float logit = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < MAX_EXPERTS; ++e) {
+    if (e < p.E) {
+      const float v = warp_sum(acc[e]);
+      if (lane == e) logit = v + p.b2[l * p.E + e];
+    }
+  }
+  float mx = logit;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float zl = logit - mx;  // (logits - max) / temperature(=1)
+  const float ex = lane < p.E ? expf(zl) : 0.f;
+  const float den = warp_sum(ex);
+  float prob = ex / den;
+  prob = fminf(fmaxf(prob, 1e-9f), 1.0f - 1e-9f);
+  const size_t pe = (static_cast<size_t>(l) * p.B + b) * p.E;
+  if (lane < p.E) {
+    p.probs[pe + lane] = prob;
+    p.logits[pe + lane] = zl;
+  }
+  // top-k: k rounds of warp arg-max, ties -> lowest expert index
+  float cand = lane < p.E ? prob : -1.f;
+  int sel[MAX_TOPK];
+  float selp[MAX_TOPK];
+  float psum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAX_TOPK; ++k) {
+    if (k < p.K) {
+      float bv = cand;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      sel[k] = bi;
+      selp[k] = bv;
+      psum += bv;
+      if (lane == bi) cand = -1.f;
+    }
+  }
+  if (lane == 0) {
+    const size_t pk = (static_cast<size_t>(l) * p.B + b) * p.K;
+    for (int k = 0; k < p.K; ++k) {
+      const float w = p.normalize ? selp[k] / psum : selp[k];
+      selp[k] = w;
+      p.topk_idx[pk + k] = sel[k];
+      p.topk_w[pk + k] = w;
+    }
+    // ascending expert order (insertion sort, K <= 8)
+    for (int i = 1; i < p.K; ++i) {
+      const int ki = sel[i];
+      const float wi = selp[i];
+      int j = i - 1;
+      while (j >= 0 && sel[j] > ki) {
+        sel[j + 1] = sel[j];
+        selp[j + 1] = selp[j];
+        --j;
+      }
+      sel[j + 1] = ki;
+      selp[j + 1] = wi;
+    }
+    for (int k = 0; k < p.K; ++k) {
+      p.sel_idx[pk + k] = sel[k];
+      p.sel_w[pk + k] = selp[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Routing plan: per layer, a stable counting sort of samples by expert. Produces
+//   pos[l, b, k]  first row of sample b's T tokens inside expert sel_idx[l,b,k]'s group (groups padded to 128 rows)
+//   up/down M-tile tables for the grouped GEMMs and their tile count
+//   expert-usage counters (NoiseBlockMoE.inference_expert_usage / total_tokens_processed, modedit.py:568-572, :594)
+// One CTA per layer; rank of a sample inside its group = exclusive block scan of "selects expert e" flags.
+struct PlanParams {
+  const int* sel_idx;            // [L, B, K]
+  int* pos;                      // [L, B, K]
+  GemmMTile* up_tiles;           // [L, max_tiles]
+  GemmMTile* down_tiles;         // [L, max_tiles]
+  int* num_tiles;                // [L]
+  unsigned long long* usage;     // [L, E]
+  unsigned long long* tokens;    // [L]
+  int L, B, K, E, T, max_tiles;
+  int up_rows_per_expert;        // 8d  (packed SwiGLU rows)
+  int down_rows_per_expert;      // d
+  int layer0;                    // first layer handled by blockIdx.x == 0 (block-level entry plans a single layer)
+};
+
+__global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
+  const int l = p.layer0 + blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int warp_tot[8];
+  __shared__ int cnt[MAX_EXPERTS];
+  __shared__ int grp_row0[MAX_EXPERTS];
+  __shared__ int grp_tile0[MAX_EXPERTS + 1];
+  const int* sel = p.sel_idx + static_cast<size_t>(l) * p.B * p.K;
+  int* pos = p.pos + static_cast<size_t>(l) * p.B * p.K;
+  // pass 1: rank of every (sample, slot) inside its expert group; stored temporarily in pos
+  for (int e = 0; e < p.E; ++e) {
+    int running = 0;
+    for (int base = 0; base < p.B; base += 256) {
+      const int b = base + tid;
+      int slot = -1;
+      if (b < p.B)
+        for (int k = 0; k < p.K; ++k)
+          if (sel[b * p.K + k] == e) slot = k;
+      const unsigned bal = __ballot_sync(0xffffffffu, slot >= 0);
+      const int pre = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) warp_tot[warp] = __popc(bal);
+      __syncthreads();
+      int woff = 0, tot = 0;
+      for (int w = 0; w < 8; ++w) {
+        if (w < warp) woff += warp_tot[w];
+        tot += warp_tot[w];
+      }
+      if (slot >= 0) pos[b * p.K + slot] = running + woff + pre;
+      running += tot;
+      __syncthreads();
+    }
+    if (tid == 0) cnt[e] = running;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int row = 0, tile = 0;
+    for (int e = 0; e < p.E; ++e) {
+      grp_row0[e] = row;
+      grp_tile0[e] = tile;
+      const int nt = (cnt[e] * p.T + 127) / 128;
+      row += nt * 128;
+      tile += nt;
+    }
+    grp_tile0[p.E] = tile;
+    p.num_tiles[l] = tile;
+    atomicAdd(p.tokens + l, static_cast<unsigned long long>(p.B) * p.T);
+  }
+  __syncthreads();
+  if (tid < p.E) atomicAdd(p.usage + static_cast<size_t>(l) * p.E + tid, static_cast<unsigned long long>(cnt[tid]) * p.T);
+  // pass 2: ranks -> row positions
+  for (int i = tid; i < p.B * p.K; i += 256) pos[i] = grp_row0[sel[i]] + pos[i] * p.T;
+  // pass 3: tile tables
+  for (int e = 0; e < p.E; ++e) {
+    const int nt = grp_tile0[e + 1] - grp_tile0[e];
+    const int rows = cnt[e] * p.T;
+    for (int i = tid; i < nt; i += 256) {
+      GemmMTile t;
+      t.a_row0 = grp_row0[e] + i * 128;
+      t.out_row0 = t.a_row0;
+      t.rows_valid = min(128, rows - i * 128);
+      t.w_row_base = (l * p.E + e) * p.up_rows_per_expert;
+      p.up_tiles[static_cast<size_t>(l) * p.max_tiles + grp_tile0[e] + i] = t;
+      t.w_row_base = (l * p.E + e) * p.down_rows_per_expert;
+      p.down_tiles[static_cast<size_t>(l) * p.max_tiles + grp_tile0[e] + i] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ln_2 + permute: x <- rms(x)*g (the block REPLACES the residual stream with its norm, modedit.py:539), and the
+// bf16 copy of each token row is written straight to its K expert groups (the gather of :563-566 done as a scatter
+// with 16-byte coalesced stores; no separate permute pass).
+struct Ln2Params {
+  float* x;               // [B*T, d] in/out
+  const float* g;         // [d]
+  const int* pos;         // [B, K] (this layer)
+  __nv_bfloat16* perm;    // [rows_perm, d]
+  int B, T, K, d;
+  float eps;
+};
+__global__ void __launch_bounds__(ROW_WARPS * 32) ln2_permute_kernel(const Ln2Params p) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.B * p.T) return;
+  const int b = row / p.T, t = row % p.T;
+  const int nvec = p.d / 128;
+  float4 xv[MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nvec) {
+      const float4 x = *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.d + (i * 32 + lane) * 4);
+      xv[i] = x;
+      ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+  ss = warp_sum(ss);
+  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+  int dst_row[MAX_TOPK];
+#pragma unroll
+  for (int k = 0; k < MAX_TOPK; ++k)
+    if (k < p.K) dst_row[k] = p.pos[b * p.K + k] + t;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nvec) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 x = xv[i];
+      const float4 g = *reinterpret_cast<const float4*>(p.g + col);
+      const float4 y = make_float4(__fdiv_rn(x.x, n) * g.x, __fdiv_rn(x.y, n) * g.y, __fdiv_rn(x.z, n) * g.z,
+                                   __fdiv_rn(x.w, n) * g.w);
+      *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = y;
+      const uint2 pk = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+#pragma unroll
+      for (int k = 0; k < MAX_TOPK; ++k)
+        if (k < p.K) *reinterpret_cast<uint2*>(p.perm + static_cast<size_t>(dst_row[k]) * p.d + col) = pk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Expert combine (+ next layer's ln_1 + c): x <- xn + sum_k w_k * y[pos_k]  accumulated in ascending expert order
+// with separately rounded products, exactly as `next_states[idx] += probs * expert(x)` does (modedit.py:561-566, :595);
+// then hA = bf16(rms(x)*g_next + c) feeds the next block's QKV GEMM. For the last block g_next is the final `ln`
+// gain (modedit.py:818) and the normalised row is written back as fp32 for the head instead.
+struct CombineParams {
+  float* x;                    // [B*T, d] in: xn, out: block output
+  const __nv_bfloat16* y;      // [rows_perm, d] expert outputs (bf16)
+  const int* pos;              // [B, K]
+  const float* w;              // [B, K] (ascending expert order)
+  const float* g_next;         // [d]
+  const float* cvec;           // [B, d]
+  __nv_bfloat16* hA;           // [B*T, d] (mode 0)
+  float* xnorm;                // [B*T, d] (mode 1: final ln output, fp32)
+  int B, T, K, d;
+  int mode;                    // 0: next block's ln_1 + c -> hA ; 1: final ln -> xnorm ; 2: none (block-level entry)
+  float eps;
+};
+__global__ void __launch_bounds__(ROW_WARPS * 32) combine_kernel(const CombineParams p) {
+  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.B * p.T) return;
+  const int b = row / p.T, t = row % p.T;
+  const int nvec = p.d / 128;
+  int src_row[MAX_TOPK];
+  float wk[MAX_TOPK];
+#pragma unroll
+  for (int k = 0; k < MAX_TOPK; ++k)
+    if (k < p.K) {
+      src_row[k] = p.pos[b * p.K + k] + t;
+      wk[k] = p.w[b * p.K + k];
+    }
+  float4 xv[MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nvec) {
+      const int col = (i * 32 + lane) * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < MAX_TOPK; ++k)
+        if (k < p.K) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(p.y + static_cast<size_t>(src_row[k]) * p.d + col);
+          const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          acc.x = __fadd_rn(acc.x, __fmul_rn(wk[k], y01.x));
+          acc.y = __fadd_rn(acc.y, __fmul_rn(wk[k], y01.y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(wk[k], y23.x));
+          acc.w = __fadd_rn(acc.w, __fmul_rn(wk[k], y23.y));
+        }
+      float4 x = *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.d + col);
+      x = make_float4(x.x + acc.x, x.y + acc.y, x.z + acc.z, x.w + acc.w);
+      *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = x;
+      xv[i] = x;
+      ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+  if (p.mode == 2) return;
+  ss = warp_sum(ss);
+  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nvec) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 x = xv[i];
+      const float4 g = *reinterpret_cast<const float4*>(p.g_next + col);
+      const float4 y = make_float4(__fdiv_rn(x.x, n) * g.x, __fdiv_rn(x.y, n) * g.y, __fdiv_rn(x.z, n) * g.z,
+                                   __fdiv_rn(x.w, n) * g.w);
+      if (p.mode == 0) {
+        const float4 c = *reinterpret_cast<const float4*>(p.cvec + static_cast<size_t>(b) * p.d + col);
+        *reinterpret_cast<uint2*>(p.hA + static_cast<size_t>(row) * p.d + col) =
+            make_uint2(pack_bf16x2(y.x + c.x, y.y + c.y), pack_bf16x2(y.z + c.z, y.w + c.w));
+      } else {
+        *reinterpret_cast<float4*>(p.xnorm + static_cast<size_t>(row) * p.d + col) = y;
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Output head + EDM preconditioning + sampler update, one warp per action token:
+//   F   = out(ln(x)[:, -A:])                                   modedit.py:806-808 (Linear(d, action_dim) + bias)
+//   D   = c_out * F + c_skip * x_act                           score_wrappers.py:79-80 (mode >= 1)
+//   x'  = ratio * x_act + coef * D                             gc_sampling.py:948-950 DDIM / DPM-Solver-1 (mode 2)
+//   err = sum (F - target)^2, target = (a - c_skip*noised)/c_out   score_wrappers.py:58-62 (mode 3, loss)
+struct HeadParams {
+  StepScalars sc;
+  const float* xnorm;      // [B*T, d] final-ln output
+  const float* w_out;      // [action_dim, d]
+  const float* b_out;      // [action_dim]
+  const float* x_act;      // [B, A, action_dim] the (unscaled) noisy actions fed to this evaluation
+  float* out;              // [B, A, action_dim]
+  const float* clean;      // mode 3: clean actions
+  float* tok_sqerr;        // mode 3: [B*A] per-token sum of squared errors (reduced deterministically afterwards)
+  const float* coefs;      // mode 2: device {sigma_next/sigma, expm1(-h)} of this step (host fp32, reference op order)
+  int B, T, A, action_dim, d;
+  int mode;                // 0 raw F, 1 denoised D, 2 DDIM update, 3 loss (out <- F)
+};
+__global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p) {
+  const int item = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (item >= p.B * p.A) return;
+  const int b = item / p.A, j = item % p.A;
+  const int row = b * p.T + (p.T - p.A) + j;
+  const int nvec = p.d / 128;
+  float acc[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) acc[a] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (i < nvec) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(p.xnorm + static_cast<size_t>(row) * p.d + col);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+        if (a < p.action_dim) {
+          const float4 w = *reinterpret_cast<const float4*>(p.w_out + static_cast<size_t>(a) * p.d + col);
+          acc[a] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[a]))));
+        }
+    }
+  float mine = 0.f;
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+    if (a < p.action_dim) {
+      const float v = warp_sum(acc[a]);
+      if (lane == a) mine = v + p.b_out[a];
+    }
+  float sq = 0.f;
+  if (lane < p.action_dim) {
+    const size_t o = (static_cast<size_t>(b) * p.A + j) * p.action_dim + lane;
+    float result = mine;
+    if (p.mode >= 1) {
+      const float sigma = load_sigma(p.sc, b);
+      const float sd = p.sc.sigma_data;
+      const float s2 = sigma * sigma + sd * sd;
+      const float c_skip = (sd * sd) / s2;
+      const float c_out = sigma * sd / sqrtf(s2);
+      const float xa = p.x_act[o];
+      if (p.mode == 3) {
+        const float target = (p.clean[o] - c_skip * xa) / c_out;
+        const float e = mine - target;
+        sq = e * e;
+      } else {
+        // inner * c_out + action * c_skip, each product rounded separately as ATen does
+        const float den = __fadd_rn(__fmul_rn(mine, c_out), __fmul_rn(xa, c_skip));
+        // (sigma_next / sigma) * action - expm1(-h) * denoised
+        result = (p.mode == 2) ? __fsub_rn(__fmul_rn(p.coefs[0], xa), __fmul_rn(p.coefs[1], den)) : den;
+      }
+    }
+    if (p.out) p.out[o] = result;
+  }
+  if (p.mode == 3) {
+    sq = warp_sum(sq);
+    if (lane == 0) p.tok_sqerr[item] = sq;
+  }
+}
+
+// Deterministic mean of the per-token squared errors: loss = sum / (B*A*action_dim)  (.pow(2).flatten(1).mean()).
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ tok_sqerr, int n, float denom,
+                                                          float* __restrict__ loss) {
+  __shared__ float part[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += tok_sqerr[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    loss[0] = t / denom;
+  }
+}
+
+}  // namespace mode

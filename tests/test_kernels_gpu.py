@@ -1,0 +1,107 @@
+"""GPU unit tests of the two tensor-core kernels through the C ABI debug entries.
+
+The checker here is a plain PyTorch fp32 restatement of the same op on the same bf16-rounded inputs (floating-point
+kernels keep a torch fp32 reference; the end-to-end parity tests use oracle/)."""
+import math
+
+import pytest
+import torch
+
+from mode_diffusion_policy_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def run_gemm(M, N, K, epi, seed=0):
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Mp = (M + 127) // 128 * 128
+    A = torch.zeros(Mp, K, dtype=torch.bfloat16)
+    A[:M] = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, generator=g) * 0.1
+    A, W, bias = A.cuda(), W.cuda(), bias.cuda()
+    ref = A[:M].float() @ W.float().t()
+    resid = None
+    if epi == 0:
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        want = (ref + bias).bfloat16().float()
+    elif epi == 1:
+        resid = torch.randn(M, N, generator=g).cuda()
+        out = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+        want = resid + ref
+    elif epi == 2:
+        out = torch.full((M, N // 2), float("nan"), dtype=torch.bfloat16, device="cuda")
+        z = (ref + bias).view(M, N // 256, 2, 128)
+        want = (z[:, :, 0] * torch.nn.functional.silu(z[:, :, 1])).reshape(M, N // 2).bfloat16().float()
+    elif epi == 3:
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        want = ref.bfloat16().float()
+    else:
+        out = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+        want = ref
+    _lib.check(lib.mode_debug_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(out), M, N, K, epi, _stream()))
+    torch.cuda.synchronize()
+    return out.float(), want
+
+
+@pytest.mark.parametrize("epi", [4, 0, 1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 1024), (448, 1024, 1024),
+                                   (100, 256, 512), (3584, 1024, 4096), (1000, 3072, 1024)])
+def test_gemm_matches_fp32_reference(M, N, K, epi):
+    got, want = run_gemm(M, N, K, epi)
+    assert torch.isfinite(got).all()
+    err = (got - want).abs()
+    scale = want.abs().max().item() + 1e-6
+    if epi in (1, 4):  # fp32 outputs: accumulation-order noise only
+        assert err.max().item() <= 2e-5 * scale * math.sqrt(K / 64), (err.max().item(), scale)
+    else:  # bf16 outputs: at most one bf16 ulp from the rounded reference
+        assert (err <= want.abs() * 2 ** -7 + 1e-6 * scale).all(), err.max().item()
+        assert (err > 0).float().mean().item() < 0.02  # almost all elements round identically
+
+
+def attention_reference(qkv, gq, gk, B, T, H, Dh, eps):
+    d = H * Dh
+    x = qkv.float().view(B, T, 3, H, Dh)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+
+    def rms(t, g):
+        n = t.norm(dim=-1, keepdim=True) * Dh ** -0.5
+        return (t / n.clamp(min=eps) * g).bfloat16().float()
+
+    q, k = rms(q, gq), rms(k, gk)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(Dh)
+    mask = torch.ones(T, T, dtype=torch.bool, device=qkv.device).tril()
+    s = s.masked_fill(~mask, float("-inf"))
+    m = s.max(dim=-1, keepdim=True).values
+    p = torch.exp(s - m)
+    o = (p.bfloat16().float() @ v) / p.sum(dim=-1, keepdim=True)
+    return o.transpose(1, 2).reshape(B * T, d)
+
+
+@pytest.mark.parametrize("B,T,H,Dh", [(3, 14, 8, 128), (2, 32, 8, 64), (5, 14, 4, 64), (2, 16, 8, 32), (1, 50, 2, 128),
+                                      (256, 14, 8, 128)])
+def test_attention_matches_reference(B, T, H, Dh):
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
+    d = H * Dh
+    qkv = torch.randn(B * T, 3 * d, generator=g).bfloat16().cuda()
+    gq = (1 + 0.1 * torch.randn(Dh, generator=g)).cuda()
+    gk = (1 + 0.1 * torch.randn(Dh, generator=g)).cuda()
+    out = torch.full((B * T, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mode_debug_attention(_ptr(qkv), _ptr(gq), _ptr(gk), _ptr(out), B, T, H, Dh, 1e-6, _stream()))
+    torch.cuda.synchronize()
+    want = attention_reference(qkv, gq, gk, B, T, H, Dh, 1e-6)
+    got = out.float()
+    assert torch.isfinite(got).all()
+    rel = (got - want).norm() / want.norm()
+    assert rel.item() < 4e-3, rel.item()  # bf16 output rounding dominates (2^-9 rms)
+    assert (got - want).abs().max().item() < 0.05
