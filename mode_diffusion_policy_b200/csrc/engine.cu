@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -871,6 +872,25 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
   const int ld = (epilogue == EPI_SWIGLU_BF16) ? N / 2 : N;
   GemmParams p = gemm_params(ta, tw, d_tiles, d_n, N, Kdim, out_dev, ld, bias_dev, resid_dev);
   int rc = launch_gemm(epilogue, sms, st, p);
+  // MODE_GEMM_BENCH_REPS=n: time n further back-to-back launches with CUDA events and print the average
+  if (rc == MODE_OK && getenv("MODE_GEMM_BENCH_REPS")) {
+    const int reps = atoi(getenv("MODE_GEMM_BENCH_REPS"));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && rc == MODE_OK; ++i) rc = launch_gemm(epilogue, sms, st, p);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * M * (double)N * Kdim;
+    printf("mode_debug_gemm M=%d N=%d K=%d epi=%d: %.3f us/launch, %.1f TFLOP/s\n", M, N, Kdim, epilogue,
+           1e3 * ms / reps, flops * reps / (ms * 1e-3) / 1e12);
+    fflush(stdout);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
   cudaError_t ce = cudaStreamSynchronize(st);
   cudaFree(d_tiles);
   cudaFree(d_n);

@@ -1,0 +1,12 @@
+"""Times the tcgen05 GEMM on the hot-path shapes through mode_debug_gemm (MODE_GEMM_BENCH_REPS)."""
+import os
+import sys
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+os.environ.setdefault("MODE_GEMM_BENCH_REPS", "20")
+from test_kernels_gpu import run_gemm  # noqa: E402
+
+for (M, N, K, epi) in [(3584, 3072, 1024, 0), (3584, 1024, 1024, 1), (3584, 16384, 1024, 2), (7168, 1024, 4096, 3),
+                       (1792, 3072, 1024, 0), (1792, 16384, 1024, 2), (8192, 8192, 8192, 3)]:
+    run_gemm(M, N, K, epi)

@@ -55,16 +55,18 @@ def run_gemm(M, N, K, epi, seed=0):
 
 @pytest.mark.parametrize("epi", [4, 0, 1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 1024), (448, 1024, 1024),
-                                   (100, 256, 512), (3584, 1024, 4096), (1000, 3072, 1024)])
+                                   (100, 256, 512), (3584, 1024, 4096), (1000, 3072, 1024),
+                                   (3584, 3072, 1024), (5000, 2048, 512)])
 def test_gemm_matches_fp32_reference(M, N, K, epi):
     got, want = run_gemm(M, N, K, epi)
     assert torch.isfinite(got).all()
     err = (got - want).abs()
     scale = want.abs().max().item() + 1e-6
-    if epi in (1, 4):  # fp32 outputs: accumulation-order noise only
-        assert err.max().item() <= 2e-5 * scale * math.sqrt(K / 64), (err.max().item(), scale)
-    else:  # bf16 outputs: at most one bf16 ulp from the rounded reference
-        assert (err <= want.abs() * 2 ** -7 + 1e-6 * scale).all(), err.max().item()
+    noise = 2e-5 * scale * math.sqrt(K / 64)  # fp32 accumulation-order noise
+    if epi in (1, 4):
+        assert err.max().item() <= noise, (err.max().item(), scale)
+    else:  # bf16 outputs: at most one bf16 ulp (plus the fp32 noise floor) from the rounded reference
+        assert (err <= want.abs() * 2 ** -7 + noise).all(), err.max().item()
         assert (err > 0).float().mean().item() < 0.02  # almost all elements round identically
 
 
