@@ -117,6 +117,15 @@ int mode_reset_expert_usage(mode_engine_t* e);
 /* Kernels of this library enqueued by the most recent forward/denoise/sample/block call (graph nodes count). */
 int64_t mode_last_launch_count(const mode_engine_t* e);
 
+/* Measurement entry: runs mode_denoise `reps` times with a CUDA-event pair around every kernel launch and returns the
+ * mean device time per evaluation (ms) and the launch count of each kernel class, MODE_PROF_CLASSES entries each:
+ * 0 router+plan, 1 embed, 2 QKV GEMM, 3 attention, 4 c_proj GEMM, 5 ln_2+permute, 6 expert up GEMM (SwiGLU),
+ * 7 expert down GEMM, 8 combine(+ln_1), 9 head, 10 obs/goal embedding. Synchronises the stream. */
+#define MODE_PROF_CLASSES 11
+int mode_profile_eval(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
+                      const float* sigma_dev, int sigma_stride, float* out_dev, int B, int reps, void* stream,
+                      float* ms_host, int32_t* launches_host);
+
 /* Unit-test entry for the tcgen05 GEMM: out = epilogue(A[M,K] @ W[N,K]^T). a_dev/w_dev bf16, bias_dev/resid_dev fp32
  * (may be NULL), epilogue = 0 bias->bf16, 1 resid+acc->f32, 2 swiglu->bf16 (W/bias already interleaved per 256 rows),
  * 3 plain->bf16, 4 plain->f32. M arbitrary, N % 256 == 0, K % 64 == 0. Returns after enqueueing. */

@@ -53,6 +53,7 @@ SYMBOLS = {
     "mode_finalize_weights": (C.c_int, [_P]),
     "mode_forward": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, _F, C.c_int, _P]),
     "mode_denoise": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, _F, C.c_int, _P]),
+    "mode_profile_eval": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, _F, C.c_int, C.c_int, _P, _P, _P]),
     "mode_loss": (C.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, C.c_int, _P]),
     "mode_sample_ddim": (C.c_int, [_P, _F, _F, _F, C.POINTER(C.c_float), C.c_int, C.c_int, _P]),
     "mode_sample_ddim_host": (C.c_int, [_P, _F, _F, _F, C.POINTER(C.c_float), C.c_int, C.c_int, _P]),

@@ -42,6 +42,7 @@ struct AttnParams {
   const float* k_gain;       // [Dh]
   int B, T, H;
   float eps;                 // RMSNorm eps (1e-6)
+  float inv_sqrt_dh;         // float(Dh ** -0.5): RMSNorm scale (modedit.py:75) and the SDPA softmax scale
 };
 
 // DH: head dim (32/64/128). MT: number of 16-row tiles covering T (T_pad = 16*MT).
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
 
   // ---- stage q, k (normalised) and v into shared memory
   const int sub = lane % VPR;  // vector index inside the row
-  const float inv_sqrt_dh = rsqrtf(static_cast<float>(DH));
+  const float inv_sqrt_dh = p.inv_sqrt_dh;
   float gq[8], gk[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {

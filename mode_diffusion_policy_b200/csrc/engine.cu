@@ -134,6 +134,7 @@ struct mode_engine {
   int d, L, H, Dh, E, K, T, S, A, adim, maxB, maxM, Hd, F, obs, gdim;
   int num_sms;
   int perm_rows, max_tiles;
+  float inv_sqrt_d, inv_sqrt_dh;
   bool finalized = false;
   std::map<std::string, WeightSpec> specs;
   std::vector<void*> allocs;
@@ -165,6 +166,31 @@ struct mode_engine {
   std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
   std::map<std::pair<int, int>, int64_t> graph_launches;
   int64_t launch_count = 0;
+
+  // optional per-kernel-class timing (mode_profile_eval): event pairs around every launch of one evaluation
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cls;
+};
+
+enum ProfClass { PC_ROUTE = 0, PC_EMBED, PC_QKV, PC_ATTN, PC_PROJ, PC_LN2, PC_UP, PC_DOWN, PC_COMBINE, PC_HEAD, PC_COND, PC_COUNT };
+
+struct ProfScope {
+  mode_engine* e;
+  cudaStream_t st;
+  ProfScope(mode_engine* e_, cudaStream_t st_, int cls) : e(e_), st(st_) {
+    if (!e->prof_on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    e->prof_ev.push_back(a);
+    e->prof_ev.push_back(b);
+    e->prof_cls.push_back(cls);
+  }
+  ~ProfScope() {
+    if (e->prof_on) cudaEventRecord(e->prof_ev.back(), st);
+  }
 };
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -338,6 +364,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   e->T = T; e->S = c->n_state_tokens; e->A = c->action_seq_len; e->adim = c->action_dim; e->maxB = c->max_batch;
   e->maxM = e->maxB * T; e->Hd = 2 * d; e->F = 4 * d; e->obs = c->obs_dim; e->gdim = c->goal_dim;
   e->num_sms = prop.multiProcessorCount;
+  e->inv_sqrt_d = static_cast<float>(pow(static_cast<double>(d), -0.5));
+  e->inv_sqrt_dh = static_cast<float>(pow(static_cast<double>(Dh), -0.5));
   const int L = e->L, E = e->E, K = e->K, Hd = e->Hd, F = e->F;
   const int maxM_pad = round_up(e->maxM, 128);
   e->max_tiles = (K * e->maxM + 127) / 128 + E;
@@ -566,6 +594,7 @@ static inline unsigned row_blocks(int rows) { return (unsigned)((rows + ROW_WARP
 
 // obs / goal token embeddings: computed once per trajectory, not per denoising step.
 static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* state_dev, const float* goal_dev) {
+  ProfScope ps(e, st, PC_COND);
   const size_t n_st = (size_t)B * e->S * e->obs / 4, n_g = (size_t)B * e->gdim / 4;
   cast_bf16_kernel<<<(unsigned)((n_st + 255) / 256), 256, 0, st>>>(state_dev, e->st_bf16, n_st);
   cast_bf16_kernel<<<(unsigned)((n_g + 255) / 256), 256, 0, st>>>(goal_dev, e->goal_bf16, n_g);
@@ -582,6 +611,7 @@ static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* sta
 
 static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* z_explicit,
                            int layer0, int n_layers) {
+  ProfScope ps(e, st, PC_ROUTE);
   RouterParams r;
   r.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   r.ra = e->r_a; r.rb = e->r_b; r.w2 = e->r_w2; r.b2 = e->r_b2;
@@ -607,31 +637,52 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   GemmParams p = gemm_params(e->tm_hA, e->tm_wqkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->qkv, 3 * d,
                              e->b_qkv, nullptr);
   p.w_row_off = l * 3 * d;
-  RET_IF(launch_gemm(EPI_BIAS_BF16, e->num_sms, st, p));
+  {
+    ProfScope ps(e, st, PC_QKV);
+    RET_IF(launch_gemm(EPI_BIAS_BF16, e->num_sms, st, p));
+  }
   AttnParams a;
   a.qkv = e->qkv; a.out = e->attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
-  a.B = B; a.T = e->T; a.H = e->H; a.eps = e->cfg.rms_eps;
-  RET_IF(launch_attn(st, a, e->Dh));
+  a.B = B; a.T = e->T; a.H = e->H; a.eps = e->cfg.rms_eps; a.inv_sqrt_dh = e->inv_sqrt_dh;
+  {
+    ProfScope ps(e, st, PC_ATTN);
+    RET_IF(launch_attn(st, a, e->Dh));
+  }
   p = gemm_params(e->tm_attn, e->tm_wproj, e->dense_tiles, e->dense_counts, d, d, e->x, d, nullptr, e->x);
   p.w_row_off = l * d;
-  RET_IF(launch_gemm(EPI_RESID_F32, e->num_sms, st, p));
+  {
+    ProfScope ps(e, st, PC_PROJ);
+    RET_IF(launch_gemm(EPI_RESID_F32, e->num_sms, st, p));
+  }
   Ln2Params n2;
   n2.x = e->x; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + (size_t)l * B * e->K; n2.perm = e->perm;
-  n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps;
-  ln2_permute_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(n2);
+  n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
+  {
+    ProfScope ps(e, st, PC_LN2);
+    ln2_permute_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(n2);
+  }
   CU_OK(cudaGetLastError());
   p = gemm_params(e->tm_perm, e->tm_wup, e->up_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, 8 * d, d, e->hbuf,
                   e->F, e->b_up, nullptr);
-  RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->num_sms, st, p));
+  {
+    ProfScope ps(e, st, PC_UP);
+    RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->num_sms, st, p));
+  }
   p = gemm_params(e->tm_h, e->tm_wdown, e->down_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, d, e->F, e->ybuf, d,
                   nullptr, nullptr);
-  RET_IF(launch_gemm(EPI_PLAIN_BF16, e->num_sms, st, p));
+  {
+    ProfScope ps(e, st, PC_DOWN);
+    RET_IF(launch_gemm(EPI_PLAIN_BF16, e->num_sms, st, p));
+  }
   CombineParams c;
   c.x = e->x; c.y = e->ybuf; c.pos = e->pos_tab + (size_t)l * B * e->K; c.w = e->sel_w + (size_t)l * B * e->K;
   c.g_next = (combine_mode == 0) ? e->ln1_g + (size_t)(l + 1) * d : e->lnf_g;
   c.cvec = e->cvec; c.hA = e->hA; c.xnorm = e->xnorm;
-  c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps;
-  combine_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(c);
+  c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
+  {
+    ProfScope ps(e, st, PC_COMBINE);
+    combine_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(c);
+  }
   CU_OK(cudaGetLastError());
   e->launch_count += 7;
   return MODE_OK;
@@ -646,8 +697,11 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   em.sig_u = e->sig_u; em.sig_v = e->sig_v; em.goal_tok = e->goal_tok; em.state_tok = e->state_tok; em.pos = e->pos;
   em.w_act = e->w_act; em.actions = actions; em.ln1_g = e->ln1_g; em.x = e->x; em.cvec = e->cvec; em.hA = e->hA;
   em.B = B; em.T = e->T; em.S = e->S; em.A = e->A; em.action_dim = e->adim; em.d = e->d; em.apply_c_in = apply_c_in;
-  em.eps = e->cfg.rms_eps;
-  embed_kernel<<<row_blocks(B * e->T), ROW_WARPS * 32, 0, st>>>(em);
+  em.eps = e->cfg.rms_eps; em.inv_sqrt_d = e->inv_sqrt_d;
+  {
+    ProfScope ps(e, st, PC_EMBED);
+    embed_kernel<<<row_blocks(B * e->T), ROW_WARPS * 32, 0, st>>>(em);
+  }
   CU_OK(cudaGetLastError());
   for (int l = 0; l < e->L; ++l) RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1));
   HeadParams h;
@@ -655,7 +709,10 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   h.xnorm = e->xnorm; h.w_out = e->w_out; h.b_out = e->b_out; h.x_act = actions; h.out = out; h.clean = clean;
   h.tok_sqerr = e->tok_sqerr; h.coefs = coefs;
   h.B = B; h.T = e->T; h.A = e->A; h.action_dim = e->adim; h.d = e->d; h.mode = head_mode;
-  head_kernel<<<row_blocks(B * e->A), ROW_WARPS * 32, 0, st>>>(h);
+  {
+    ProfScope ps(e, st, PC_HEAD);
+    head_kernel<<<row_blocks(B * e->A), ROW_WARPS * 32, 0, st>>>(h);
+  }
   CU_OK(cudaGetLastError());
   e->launch_count += 2;
   return MODE_OK;
@@ -682,6 +739,38 @@ extern "C" int mode_forward(mode_engine_t* e, const float* state_dev, const floa
 extern "C" int mode_denoise(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
                             const float* sigma_dev, int sigma_stride, float* out_dev, int B, void* stream) {
   return eval_common(e, state_dev, goal_dev, actions_dev, sigma_dev, sigma_stride, out_dev, B, stream, 1, 1);
+}
+
+extern "C" int mode_profile_eval(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* actions_dev,
+                                 const float* sigma_dev, int sigma_stride, float* out_dev, int B, int reps, void* stream,
+                                 float* ms_host, int32_t* launches_host) {
+  if (!e || !ms_host || !launches_host || reps < 1) return fail(MODE_ERR_INVALID, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < PC_COUNT; ++i) {
+    ms_host[i] = 0.f;
+    launches_host[i] = 0;
+  }
+  // one untimed pass (also validates arguments), then `reps` instrumented passes
+  RET_IF(mode_denoise(e, state_dev, goal_dev, actions_dev, sigma_dev, sigma_stride, out_dev, B, stream));
+  for (int r = 0; r < reps; ++r) {
+    e->prof_on = true;
+    int rc = mode_denoise(e, state_dev, goal_dev, actions_dev, sigma_dev, sigma_stride, out_dev, B, stream);
+    e->prof_on = false;
+    cudaError_t ce = cudaStreamSynchronize(st);
+    for (size_t i = 0; i < e->prof_cls.size(); ++i) {
+      float ms = 0.f;
+      if (rc == MODE_OK && ce == cudaSuccess) cudaEventElapsedTime(&ms, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]);
+      ms_host[e->prof_cls[i]] += ms / reps;
+      if (r == 0) launches_host[e->prof_cls[i]] += 1;
+      cudaEventDestroy(e->prof_ev[2 * i]);
+      cudaEventDestroy(e->prof_ev[2 * i + 1]);
+    }
+    e->prof_ev.clear();
+    e->prof_cls.clear();
+    if (rc != MODE_OK) return rc;
+    if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "profile pass failed: %s", cudaGetErrorString(ce));
+  }
+  return MODE_OK;
 }
 
 extern "C" int mode_loss(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* action_dev,
@@ -806,7 +895,7 @@ extern "C" int mode_block_forward(mode_engine_t* e, int layer, const float* x_de
   RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, e->zbuf, layer, 1));
   Ln1Params l1;
   l1.x = e->x; l1.cvec = e->cvec; l1.g = e->ln1_g + (size_t)layer * d; l1.hA = e->hA; l1.rows = M; l1.T = e->T; l1.d = d;
-  l1.eps = e->cfg.rms_eps;
+  l1.eps = e->cfg.rms_eps; l1.inv_sqrt_d = e->inv_sqrt_d;
   ln1_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(l1);
   CU_OK(cudaGetLastError());
   RET_IF(enqueue_block(e, st, B, layer, 2));
@@ -906,5 +995,6 @@ extern "C" int mode_debug_attention(const void* qkv_dev, const float* q_gain_dev
   a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv_dev);
   a.out = reinterpret_cast<__nv_bfloat16*>(out_dev);
   a.q_gain = q_gain_dev; a.k_gain = k_gain_dev; a.B = B; a.T = T; a.H = H; a.eps = eps;
+  a.inv_sqrt_dh = static_cast<float>(pow(static_cast<double>(Dh), -0.5));
   return launch_attn(reinterpret_cast<cudaStream_t>(stream), a, Dh);
 }

@@ -68,6 +68,7 @@ struct EmbedParams {
   int B, T, S, A, action_dim, d;
   int apply_c_in;          // 1: GCDenoiser.forward scales the action input by c_in (score_wrappers.py:79-80)
   float eps;
+  float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 
 __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams p) {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams
     }
   }
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
     if (i < nvec) {
@@ -149,6 +150,7 @@ struct Ln1Params {
   __nv_bfloat16* hA;   // [rows, d]
   int rows, T, d;
   float eps;
+  float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 __global__ void __launch_bounds__(ROW_WARPS * 32) ln1_kernel(const Ln1Params p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln1_kernel(const Ln1Params p) 
       ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i)
     if (i < nvec) {
@@ -397,6 +399,7 @@ struct Ln2Params {
   __nv_bfloat16* perm;    // [rows_perm, d]
   int B, T, K, d;
   float eps;
+  float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 __global__ void __launch_bounds__(ROW_WARPS * 32) ln2_permute_kernel(const Ln2Params p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) ln2_permute_kernel(const Ln2Pa
       ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
   int dst_row[MAX_TOPK];
 #pragma unroll
   for (int k = 0; k < MAX_TOPK; ++k)
@@ -452,6 +455,7 @@ struct CombineParams {
   int B, T, K, d;
   int mode;                    // 0: next block's ln_1 + c -> hA ; 1: final ln -> xnorm ; 2: none (block-level entry)
   float eps;
+  float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 __global__ void __launch_bounds__(ROW_WARPS * 32) combine_kernel(const CombineParams p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) combine_kernel(const CombinePa
     }
   if (p.mode == 2) return;
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, rsqrtf(static_cast<float>(p.d)), p.eps);
+  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i)
     if (i < nvec) {

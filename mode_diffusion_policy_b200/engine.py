@@ -1,0 +1,207 @@
+"""Thin object wrapper over the C ABI (include/mode_engine.h). PyTorch is used only for device memory and streams."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, asdict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+@dataclass
+class EngineConfig:
+    """Mirror of mode_config_t; field meaning follows MoDeDiT.__init__ (reference modedit.py:643-674)."""
+
+    obs_dim: int = 2048
+    goal_dim: int = 512
+    action_dim: int = 7
+    embed_dim: int = 1024
+    n_layers: int = 12
+    n_heads: int = 8
+    n_state_tokens: int = 2
+    action_seq_len: int = 10
+    num_experts: int = 4
+    top_k: int = 2
+    router_normalize: bool = True
+    max_batch: int = 256
+    sigma_data: float = 0.5
+    rms_eps: float = 1e-6
+
+    @property
+    def seq_len(self) -> int:
+        return 2 + self.n_state_tokens + self.action_seq_len
+
+
+def _f32_cuda(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.ModeError(f"{what} must be a CUDA tensor: the MoDE engine has no CPU path")
+    return t.detach().to(torch.float32).contiguous()
+
+
+class ModeEngine:
+    """One engine = packed bf16 weights + workspace + CUDA graphs on the current CUDA device."""
+
+    def __init__(self, cfg: EngineConfig):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.ModeError("no CUDA device: the MoDE engine only runs on B200 (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        c = _lib.mode_config_t(**{k: (int(v) if not isinstance(v, float) else v) for k, v in asdict(cfg).items()})
+        h = C.c_void_p()
+        _lib.check(self.lib.mode_create(C.byref(c), C.byref(h)))
+        self._h = h
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mode_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- weights
+    def load_state_dict(self, sd) -> None:
+        """sd: mapping reference-name -> numpy array or torch tensor (fp32 master weights, reference shapes)."""
+        for name, w in sd.items():
+            if isinstance(w, torch.Tensor):
+                t = w.detach().to(torch.float32).contiguous()
+                is_dev = 1 if t.is_cuda else 0
+                ptr, shape = t.data_ptr(), tuple(t.shape)
+                keep = t
+            else:
+                keep = np.ascontiguousarray(w, dtype=np.float32)
+                is_dev, ptr, shape = 0, keep.ctypes.data, keep.shape
+            shp = (C.c_int64 * len(shape))(*shape)
+            _lib.check(self.lib.mode_set_weight(self._h, name.encode(), ptr, is_dev, shp, len(shape)))
+            del keep
+        _lib.check(self.lib.mode_finalize_weights(self._h))
+
+    # ---------------------------------------------------------------- evaluations
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _prep(self, state, goal, actions, sigma):
+        state = _f32_cuda(state, "state_images")
+        goal = _f32_cuda(goal, "goal")
+        actions = _f32_cuda(actions, "actions")
+        B = actions.shape[0]
+        c = self.cfg
+        if tuple(state.shape) != (B, c.n_state_tokens, c.obs_dim):
+            raise _lib.ModeError(f"state_images must be {(B, c.n_state_tokens, c.obs_dim)}, got {tuple(state.shape)}")
+        if goal.numel() != B * c.goal_dim:
+            raise _lib.ModeError(f"goal must hold {B}x{c.goal_dim} values, got shape {tuple(goal.shape)}")
+        if tuple(actions.shape) != (B, c.action_seq_len, c.action_dim):
+            raise _lib.ModeError(f"actions must be {(B, c.action_seq_len, c.action_dim)}, got {tuple(actions.shape)}")
+        stride = 1
+        if sigma is not None:
+            sigma = _f32_cuda(sigma, "sigma").reshape(-1)
+            if sigma.numel() == 1:
+                stride = 0
+            elif sigma.numel() != B:
+                raise _lib.ModeError(f"sigma must have 1 or {B} elements, got {sigma.numel()}")
+        return state, goal, actions, sigma, stride, B
+
+    def forward(self, state, actions, goal, sigma) -> torch.Tensor:
+        """MoDeDiT.forward (raw network output F)."""
+        state, goal, actions, sigma, stride, B = self._prep(state, goal, actions, sigma)
+        out = torch.empty_like(actions)
+        _lib.check(self.lib.mode_forward(self._h, state.data_ptr(), goal.data_ptr(), actions.data_ptr(),
+                                         sigma.data_ptr(), stride, out.data_ptr(), B, self._stream()))
+        return out
+
+    def denoise(self, state, actions, goal, sigma) -> torch.Tensor:
+        """GCDenoiser.forward: D(x; sigma)."""
+        state, goal, actions, sigma, stride, B = self._prep(state, goal, actions, sigma)
+        out = torch.empty_like(actions)
+        _lib.check(self.lib.mode_denoise(self._h, state.data_ptr(), goal.data_ptr(), actions.data_ptr(),
+                                         sigma.data_ptr(), stride, out.data_ptr(), B, self._stream()))
+        return out
+
+    PROF_CLASSES = ["router+plan", "embed", "qkv_gemm", "attention", "proj_gemm", "ln2_permute", "up_gemm_swiglu",
+                    "down_gemm", "combine_ln1", "head", "cond_embed"]
+
+    def profile_eval(self, state, actions, goal, sigma, reps: int = 3):
+        """Per-kernel-class device time (ms per evaluation) and launch counts of one denoiser call."""
+        state, goal, actions, sigma, stride, B = self._prep(state, goal, actions, sigma)
+        out = torch.empty_like(actions)
+        ms = np.zeros(len(self.PROF_CLASSES), dtype=np.float32)
+        n = np.zeros(len(self.PROF_CLASSES), dtype=np.int32)
+        _lib.check(self.lib.mode_profile_eval(self._h, state.data_ptr(), goal.data_ptr(), actions.data_ptr(),
+                                              sigma.data_ptr(), stride, out.data_ptr(), B, reps, self._stream(),
+                                              ms.ctypes.data, n.ctypes.data))
+        return {k: (float(m), int(c)) for k, m, c in zip(self.PROF_CLASSES, ms, n)}
+
+    def loss(self, state, action, goal, noise, sigma):
+        """GCDenoiser.loss forward (eval-mode network). Returns (loss scalar tensor, model output)."""
+        state, goal, action, sigma, stride, B = self._prep(state, goal, action, sigma)
+        noise = _f32_cuda(noise, "noise")
+        if stride != 1 and B != 1:
+            sigma = sigma.expand(B).contiguous()
+        out = torch.empty_like(action)
+        loss = torch.empty(1, dtype=torch.float32, device=action.device)
+        _lib.check(self.lib.mode_loss(self._h, state.data_ptr(), goal.data_ptr(), action.data_ptr(), noise.data_ptr(),
+                                      sigma.data_ptr(), loss.data_ptr(), out.data_ptr(), B, self._stream()))
+        return loss[0], out
+
+    def sample_ddim(self, state, x, goal, sigmas) -> torch.Tensor:
+        """sample_ddim over GCDenoiser (whole loop = one CUDA graph). `sigmas` includes the trailing 0. Returns actions."""
+        state, goal, x, _, _, B = self._prep(state, goal, x, None)
+        x = x.clone()
+        sig = np.ascontiguousarray(torch.as_tensor(sigmas).detach().float().cpu().numpy(), dtype=np.float32)
+        _lib.check(self.lib.mode_sample_ddim(self._h, state.data_ptr(), goal.data_ptr(), x.data_ptr(),
+                                             sig.ctypes.data_as(C.POINTER(C.c_float)), len(sig), B, self._stream()))
+        return x
+
+    def sample_ddim_host(self, state: np.ndarray, x: np.ndarray, goal: np.ndarray, sigmas: np.ndarray) -> np.ndarray:
+        """Host-buffer entry (numpy or pinned torch CPU tensors): H2D, sample, D2H, synchronised. Returns actions."""
+        def host_ptr(a):
+            if isinstance(a, torch.Tensor):
+                assert not a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()
+                return a.data_ptr()
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+            return a.ctypes.data
+
+        B = x.shape[0]
+        sig = np.ascontiguousarray(sigmas, dtype=np.float32)
+        _lib.check(self.lib.mode_sample_ddim_host(self._h, host_ptr(state), host_ptr(goal), host_ptr(x),
+                                                  sig.ctypes.data_as(C.POINTER(C.c_float)), len(sig), B, self._stream()))
+        return x
+
+    def block_forward(self, layer: int, x, c) -> torch.Tensor:
+        """NoiseBlockMoE.forward(x, c) for one layer; x (B, T, d), c (B, 1, d) or (B, d)."""
+        x = _f32_cuda(x, "x")
+        c = _f32_cuda(c, "c").reshape(x.shape[0], -1)
+        if x.shape[1] != self.cfg.seq_len or x.shape[2] != self.cfg.embed_dim:
+            raise _lib.ModeError(f"x must be (B, {self.cfg.seq_len}, {self.cfg.embed_dim}), got {tuple(x.shape)}")
+        out = torch.empty_like(x)
+        _lib.check(self.lib.mode_block_forward(self._h, layer, x.data_ptr(), c.data_ptr(), out.data_ptr(), x.shape[0],
+                                               self._stream()))
+        return out
+
+    # ---------------------------------------------------------------- introspection
+    def routing(self, layer: int, B: int):
+        k, E = self.cfg.top_k, self.cfg.num_experts
+        idx = np.empty((B, k), dtype=np.int32)
+        w = np.empty((B, k), dtype=np.float32)
+        probs = np.empty((B, E), dtype=np.float32)
+        _lib.check(self.lib.mode_get_routing(self._h, layer, B, idx.ctypes.data, w.ctypes.data, probs.ctypes.data))
+        return idx, w, probs
+
+    def expert_usage(self, layer: int):
+        usage = np.zeros(self.cfg.num_experts, dtype=np.int64)
+        total = np.zeros(1, dtype=np.int64)
+        _lib.check(self.lib.mode_get_expert_usage(self._h, layer, usage.ctypes.data, total.ctypes.data))
+        return usage, int(total[0])
+
+    def reset_expert_usage(self):
+        _lib.check(self.lib.mode_reset_expert_usage(self._h))
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.mode_last_launch_count(self._h))

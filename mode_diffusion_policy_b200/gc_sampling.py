@@ -1,0 +1,341 @@
+"""Noise schedules and k-diffusion samplers with the reference's names and signatures
+(`mode.models.edm_diffusion.gc_sampling`, reference gc_sampling.py:26-994), written around one shared step helper.
+
+`sample_ddim` — the reference's default sampler (conf/model/mode_agent.yaml:9) — runs as ONE fused engine call (the
+whole sigma loop is a CUDA graph) whenever the model is the engine-backed GCDenoiser and no callback / scaler /
+extra_args intervene; every other sampler calls `model(state, action, goal, sigma)` = the engine's fused denoiser once
+per network evaluation and does its (tiny) update arithmetic in torch.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import utils
+
+
+# ---------------------------------------------------------------------------------------------------- schedules
+def append_zero(action):
+    return torch.cat([action, action.new_zeros([1])])
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
+    """Karras et al. (2022) schedule (reference gc_sampling.py:26-32)."""
+    ramp = torch.linspace(0, 1, n)
+    lo, hi = sigma_min ** (1 / rho), sigma_max ** (1 / rho)
+    return append_zero((hi + ramp * (lo - hi)) ** rho).to(device)
+
+
+def get_sigmas_exponential(n, sigma_min, sigma_max, device="cpu"):
+    """Exponential schedule, the reference default (gc_sampling.py:35-38)."""
+    return append_zero(torch.linspace(math.log(sigma_max), math.log(sigma_min), n, device=device).exp())
+
+
+def get_sigmas_linear(n, sigma_min, sigma_max, device="cpu"):
+    return append_zero(torch.linspace(sigma_max, sigma_min, n, device=device))
+
+
+def cosine_beta_schedule(n, s=0.008, device="cpu"):
+    """reference gc_sampling.py:47-58"""
+    steps = n + 1
+    x = np.linspace(0, steps, steps)
+    ac = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = np.clip(1 - (ac[1:] / ac[:-1]), a_min=0, a_max=0.999)
+    return append_zero(torch.tensor(np.flip(betas).copy(), device=device, dtype=torch.float32))
+
+
+def get_sigmas_ve(n, sigma_min=0.02, sigma_max=100, device="cpu"):
+    """reference gc_sampling.py:61-68 (note: t runs over [0, n+1] as written there)."""
+    t = torch.linspace(0, n + 1, n, device=device)
+    return append_zero(torch.sqrt((sigma_max ** 2) * ((sigma_min ** 2 / sigma_max ** 2) ** (t / (n - 1)))))
+
+
+def get_iddpm_sigmas(n, sigma_min=0.02, sigma_max=100, M=1000, j_0=0, C_1=0.001, C_2=0.008, device="cpu"):
+    """reference gc_sampling.py:71-81"""
+    idx = torch.arange(n, dtype=torch.float64, device=device)
+    u = torch.zeros(M + 1, dtype=torch.float64, device=device)
+    abar = lambda j: (0.5 * np.pi * j / M / (C_2 + 1)).sin() ** 2  # noqa: E731
+    for j in torch.arange(M, j_0, -1, device=device):
+        u[j - 1] = ((u[j] ** 2 + 1) / (abar(j - 1) / abar(j)).clip(min=C_1) - 1).sqrt()
+    uf = u[torch.logical_and(u >= sigma_min, u <= sigma_max)]
+    return append_zero(uf[((len(uf) - 1) / (n - 1) * idx).round().to(torch.int64)]).to(torch.float32)
+
+
+def get_sigmas_vp(n, beta_d=19.9, beta_min=0.1, eps_s=1e-3, device="cpu"):
+    t = torch.linspace(1, eps_s, n, device=device)
+    return append_zero(torch.sqrt(torch.exp(beta_d * t ** 2 / 2 + beta_min * t) - 1))
+
+
+# ---------------------------------------------------------------------------------------------------- helpers
+def to_d(action, sigma, denoised):
+    """Karras ODE derivative (reference gc_sampling.py:91-93)."""
+    return (action - denoised) / utils.append_dims(sigma, action.ndim)
+
+
+def default_noise_sampler(x):
+    return lambda sigma, sigma_next: torch.randn_like(x)
+
+
+def get_ancestral_step(sigma_from, sigma_to, eta=1.0):
+    """reference gc_sampling.py:102-109"""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    return (sigma_to ** 2 - sigma_up ** 2) ** 0.5, sigma_up
+
+
+def _t(sigma):  # t = -ln sigma
+    return sigma.log().neg()
+
+
+def _sig(t):
+    return t.neg().exp()
+
+
+class _Loop:
+    """Shared plumbing of every sampler: evaluates the denoiser at a scalar sigma, reports to the callback, clips."""
+
+    def __init__(self, model, state, goal, scaler, extra_args, callback, key="action"):
+        self.model, self.state, self.goal, self.scaler = model, state, goal, scaler
+        self.extra = {} if extra_args is None else extra_args
+        self.callback, self.key = callback, key
+
+    def denoise(self, x, sigma):
+        return self.model(self.state, x, self.goal, sigma * x.new_ones([x.shape[0]]), **self.extra)
+
+    def report(self, x, i, sigma, sigma_hat, denoised):
+        if self.callback is not None:
+            self.callback({self.key: x, "i": i, "sigma": sigma, "sigma_hat": sigma_hat, "denoised": denoised})
+
+    def clip(self, x):
+        return x if self.scaler is None else self.scaler.clip_output(x)
+
+
+def _churn(x, sigmas, i, s_churn, s_tmin, s_tmax, s_noise):
+    """Karras 'churn': raise the noise level to sigma_hat before the step (reference gc_sampling.py:196-201)."""
+    gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+    eps = torch.randn_like(x) * s_noise
+    sigma_hat = sigmas[i] * (gamma + 1)
+    if gamma > 0:
+        x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+    return x, sigma_hat
+
+
+def _exp_step(x, denoised, t, t_next):
+    """x <- (sigma(t')/sigma(t)) x - expm1(-(t'-t)) D : the DPM-Solver-1 / DDIM update (reference gc_sampling.py:950)."""
+    return (_sig(t_next) / _sig(t)) * x - (-(t_next - t)).expm1() * denoised
+
+
+# ---------------------------------------------------------------------------------------------------- samplers
+@torch.no_grad()
+def sample_ddim(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, eta=1.0):
+    """DPM-Solver-1 / DDIM (reference gc_sampling.py:922-951)."""
+    if scaler is None and callback is None and not extra_args and hasattr(model, "sample_ddim"):
+        return model.sample_ddim(state, action, goal, sigmas)  # fused: one CUDA-graph launch for the whole loop
+    lp = _Loop(model, state, goal, scaler, extra_args, callback)
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(action, sigmas[i])
+        lp.report(action, i, sigmas[i], sigmas[i], denoised)
+        action = _exp_step(action, denoised, _t(sigmas[i]), _t(sigmas[i + 1]))
+    return action
+
+
+@torch.no_grad()
+def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
+    """Algorithm 2 of Karras et al. without the 2nd-order correction (reference gc_sampling.py:164-211)."""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
+    for i in range(len(sigmas) - 1):
+        action, sigma_hat = _churn(action, sigmas, i, s_churn, s_tmin, s_tmax, s_noise)
+        denoised = lp.denoise(action, sigma_hat)
+        d = to_d(action, sigma_hat, denoised)
+        lp.report(action, i, sigmas[i], sigma_hat, denoised)
+        action = lp.clip(action + d * (sigmas[i + 1] - sigma_hat))
+    return action
+
+
+@torch.no_grad()
+def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                           disable=None, eta=1.0):
+    """reference gc_sampling.py:213-254"""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(action, sigmas[i])
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        lp.report(action, i, sigmas[i], sigmas[i], denoised)
+        action = action + to_d(action, sigmas[i], denoised) * (sigma_down - sigmas[i])
+        if sigma_down > 0:
+            action = action + torch.randn_like(action) * sigma_up
+        action = lp.clip(action)
+    return action
+
+
+@torch.no_grad()
+def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
+    """Algorithm 2 of Karras et al. (Heun) (reference gc_sampling.py:256-312)."""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
+    for i in range(len(sigmas) - 1):
+        action, sigma_hat = _churn(action, sigmas, i, s_churn, s_tmin, s_tmax, s_noise)
+        denoised = lp.denoise(action, sigma_hat)
+        d = to_d(action, sigma_hat, denoised)
+        lp.report(action, i, sigmas[i], sigma_hat, denoised)
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            action = action + d * dt
+        else:
+            probe = action + d * dt
+            d_2 = to_d(probe, sigmas[i + 1], lp.denoise(probe, sigmas[i + 1]))
+            action = action + (d + d_2) / 2 * dt
+        action = lp.clip(action)
+    return action
+
+
+@torch.no_grad()
+def sample_dpm_2(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
+    """DPM-Solver-2 flavoured midpoint steps (reference gc_sampling.py:314-373)."""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback)
+    for i in range(len(sigmas) - 1):
+        action, sigma_hat = _churn(action, sigmas, i, s_churn, s_tmin, s_tmax, s_noise)
+        denoised = lp.denoise(action, sigma_hat)
+        d = to_d(action, sigma_hat, denoised)
+        lp.report(action, i, sigmas[i], sigma_hat, denoised)
+        if sigmas[i + 1] == 0:
+            action = action + d * (sigmas[i + 1] - sigma_hat)
+        else:
+            sigma_mid = sigma_hat.log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            probe = action + d * (sigma_mid - sigma_hat)
+            d_2 = to_d(probe, sigma_mid, lp.denoise(probe, sigma_mid))
+            action = action + d_2 * (sigmas[i + 1] - sigma_hat)
+        action = lp.clip(action)
+    return action
+
+
+@torch.no_grad()
+def sample_dpm_2_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                           disable=None, eta=1.0):
+    """reference gc_sampling.py:375-410"""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(action, sigmas[i])
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        lp.report(action, i, sigmas[i], sigmas[i], denoised)
+        d = to_d(action, sigmas[i], denoised)
+        if sigma_down == 0:
+            action = action + d * (sigma_down - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigma_down.log(), 0.5).exp()
+            probe = action + d * (sigma_mid - sigmas[i])
+            d_2 = to_d(probe, sigma_mid, lp.denoise(probe, sigma_mid))
+            action = action + d_2 * (sigma_down - sigmas[i])
+            action = action + torch.randn_like(action) * sigma_up
+        action = lp.clip(action)
+    return action
+
+
+def linear_multistep_coeff(order, t, i, j):
+    """Integral of the j-th Lagrange basis polynomial over [t_i, t_{i+1}] (reference gc_sampling.py:413-427)."""
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+    from scipy import integrate
+
+    def basis(tau):
+        prod = 1.0
+        for k in range(order):
+            if k != j:
+                prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+
+    return integrate.quad(basis, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+@torch.no_grad()
+def sample_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, order=4):
+    """Linear multistep sampler (reference gc_sampling.py:429-466)."""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
+    sig = sigmas.detach().cpu().numpy()
+    history = []
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(action, sigmas[i])
+        history.append(to_d(action, sigmas[i], denoised))
+        history = history[-order:]
+        lp.report(action, i, sigmas[i], sigmas[i], denoised)
+        cur = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur, sig, i, j) for j in range(cur)]
+        action = lp.clip(action + sum(c * d for c, d in zip(coeffs, reversed(history))))
+    return action
+
+
+@torch.no_grad()
+def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None):
+    """DPM-Solver++(2M) (reference gc_sampling.py:699-734)."""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback)
+    old = None
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(action, sigmas[i])
+        lp.report(action, i, sigmas[i], sigmas[i], denoised)
+        t, t_next = _t(sigmas[i]), _t(sigmas[i + 1])
+        target = denoised
+        if old is not None and sigmas[i + 1] != 0:
+            r = (t - _t(sigmas[i - 1])) / (t_next - t)
+            target = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old
+        action = _exp_step(action, target, t, t_next)
+        old = denoised
+    return action
+
+
+sample_dpmpp_2_with_lms = sample_dpmpp_2m  # identical bodies in the reference (gc_sampling.py:797-831)
+
+
+@torch.no_grad()
+def sample_dpmpp_2s(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
+                    eta=1.0):
+    """DPM-Solver++(2S) (reference gc_sampling.py:955-994)."""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback)
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(action, sigmas[i])
+        lp.report(action, i, sigmas[i], sigmas[i], denoised)
+        if sigmas[i + 1] == 0:
+            action = action + to_d(action, sigmas[i], denoised) * (sigmas[i + 1] - sigmas[i])
+        else:
+            t, t_next = _t(sigmas[i]), _t(sigmas[i + 1])
+            s = t + 0.5 * (t_next - t)
+            probe = _exp_step(action, denoised, t, s)
+            action = _exp_step(action, lp.denoise(probe, _sig(s)), t, t_next)
+        action = lp.clip(action)
+    return action
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
+                              disable=None, eta=1.0, s_noise=1.0, noise_sampler=None):
+    """reference gc_sampling.py:873-919"""
+    lp = _Loop(model, state, goal, scaler, extra_args, callback)
+    noise_sampler = default_noise_sampler(action) if noise_sampler is None else noise_sampler
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(action, sigmas[i])
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        lp.report(action, i, sigmas[i], sigmas[i], denoised)
+        if sigma_down == 0:
+            action = action + to_d(action, sigmas[i], denoised) * (sigma_down - sigmas[i])
+        else:
+            t, t_next = _t(sigmas[i]), _t(sigma_down)
+            s = t + 0.5 * (t_next - t)
+            probe = _exp_step(action, denoised, t, s)
+            action = _exp_step(action, lp.denoise(probe, _sig(s)), t, t_next)
+        action = lp.clip(action + noise_sampler(sigmas[i], sigmas[i + 1]) * s_noise * sigma_up)
+    return action
+
+
+SAMPLERS = {
+    # sampler_type keys of MoDEAgent.sample_loop (reference mode_agent.py:771-840). 'dpm_fast', 'dpm_adaptive' raise in
+    # the reference (undefined names) and 'dpmpp_2m_sde' needs torchsde; they are not provided.
+    "lms": sample_lms, "heun": sample_heun, "euler": sample_euler, "ancestral": sample_dpm_2_ancestral,
+    "euler_ancestral": sample_euler_ancestral, "dpm": sample_dpm_2, "dpmpp_2s_ancestral": sample_dpmpp_2s_ancestral,
+    "dpmpp_2m": sample_dpmpp_2m, "ddim": sample_ddim, "dpmpp_2s": sample_dpmpp_2s,
+    "debugging": sample_dpmpp_2_with_lms, "dpmpp_2_with_lms": sample_dpmpp_2_with_lms,
+}

@@ -1,0 +1,77 @@
+"""Drop-in for `mode.models.edm_diffusion.score_wrappers.GCDenoiser` (reference score_wrappers.py:18-99).
+
+Swap it in with Hydra:  model._target_: mode_diffusion_policy_b200.score_wrappers.GCDenoiser
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .modedit import MoDeDiT
+
+
+def append_dims(x, target_dims):
+    """reference mode/models/edm_diffusion/utils.py:146-151"""
+    dims_to_append = target_dims - x.ndim
+    if dims_to_append < 0:
+        raise ValueError(f"input has {x.ndim} dims but target_dims is {target_dims}, which is less")
+    return x[(...,) + (None,) * dims_to_append]
+
+
+def _instantiate(inner_model):
+    if isinstance(inner_model, nn.Module):
+        return inner_model
+    try:  # the reference instantiates a Hydra config here (score_wrappers.py:28)
+        import hydra
+
+        return hydra.utils.instantiate(inner_model)
+    except ImportError:
+        cfg = dict(inner_model)
+        cfg.pop("_target_", None)
+        return MoDeDiT(**cfg)
+
+
+class GCDenoiser(nn.Module):
+    """Karras et al. preconditioner around the MoDE network; forward and loss run fused inside the CUDA engine
+    (c_in scaling in the embedding kernel, c_out/c_skip combine in the head kernel)."""
+
+    def __init__(self, inner_model, sigma_data=1.0):
+        super().__init__()
+        self.inner_model = _instantiate(inner_model)
+        self.sigma_data = sigma_data
+        if isinstance(self.inner_model, MoDeDiT):
+            self.inner_model.set_sigma_data(sigma_data)
+
+    def get_scalings(self, sigma):
+        c_skip = self.sigma_data ** 2 / (sigma ** 2 + self.sigma_data ** 2)
+        c_out = sigma * self.sigma_data / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        c_in = 1 / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        return c_skip, c_out, c_in
+
+    def _engine(self, batch):
+        m = self.inner_model
+        if m.training:
+            raise NotImplementedError("MoDE engine: training-mode forward (dropout, multinomial routing) is not built yet")
+        return m._ensure_engine(batch)
+
+    def forward(self, state, action, goal, sigma, uncond=False, **kwargs):
+        m = self.inner_model
+        goal = m._goals(goal, uncond)
+        sigma = torch.as_tensor(sigma, device=action.device)
+        return self._engine(action.shape[0]).denoise(state["state_images"], action, goal, sigma).to(action.dtype)
+
+    def loss(self, state, action, goal, noise, sigma, **kwargs):
+        """Forward value of the EDM loss (reference score_wrappers.py:45-63) with eval-mode routing. No autograd graph."""
+        m = self.inner_model
+        goal = m._goals(goal, False)
+        loss, out = self._engine(action.shape[0]).loss(state["state_images"], action, goal, noise, sigma)
+        return loss, out
+
+    def sample_ddim(self, state, action, goal, sigmas):
+        """Fused sample_ddim (reference gc_sampling.py:922-951): the whole loop is one CUDA-graph launch."""
+        m = self.inner_model
+        goal = m._goals(goal, False)
+        return self._engine(action.shape[0]).sample_ddim(state["state_images"], action, goal, sigmas).to(action.dtype)
+
+    def get_params(self):
+        return self.inner_model.parameters()

@@ -66,11 +66,18 @@ def gelu_erf(x):
     return (F32(0.5) * x * (F32(1) + _erf(x.astype(np.float64) * 0.7071067811865476).astype(F32))).astype(F32)
 
 
-def linear(x, w, b=None):
-    y = np.matmul(np.asarray(x, dtype=F32), np.asarray(w, dtype=F32).T)
+def linear(x, w, b=None, exact=False):
+    """x @ w.T (+ b). fp32 like ATen by default; `exact=True` accumulates in float64 and rounds once to fp32 — the
+    bf16 contract's definition of a tensor-core GEMM with fp32 accumulation (the exact sum, rounded), so that the
+    checker adds no accumulation-order noise of its own."""
+    x = np.asarray(x)
+    lead = x.shape[:-1]
+    dt = np.float64 if exact else F32
+    x2 = np.ascontiguousarray(x.reshape(-1, x.shape[-1]), dtype=dt)  # one big GEMM instead of a batch of small ones
+    y = np.matmul(x2, np.asarray(w, dtype=dt).T)
     if b is not None:
-        y = y + b.astype(F32)
-    return y.astype(F32)
+        y = y + b.astype(dt)
+    return y.astype(F32).reshape(*lead, -1)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -139,6 +146,29 @@ def state_dict_spec(cfg: ModeConfig):
             ]
     spec += [("ln.g", (d,)), ("out.weight", (cfg.action_dim, d)), ("out.bias", (cfg.action_dim,))]
     return spec
+
+
+def make_weights_fast(cfg: ModeConfig, seed: int = 1234, router_gain: float = 30.0) -> dict:
+    """Same distributions as make_weights but drawn as float32 uniforms directly (seconds instead of tens of seconds
+    for the 686 M-parameter model). For timing runs, where only shapes and scales matter — never for goldens."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shape in state_dict_spec(cfg):
+        u = rng.random(shape, dtype=F32)
+        u -= F32(0.5)  # U(-0.5, 0.5)
+        if name.endswith(".g"):
+            w = F32(1.0) + F32(0.1) * u
+        elif name == "pos_emb":
+            w = F32(0.07) * u
+        elif "router.router.mlp" in name:
+            w = F32(0.07) * u if name.endswith("weight") else np.zeros(shape, dtype=F32)
+            if name.endswith("mlp.3.weight"):
+                w = w * F32(router_gain)
+        else:
+            fan_in = shape[1] if len(shape) == 2 else {"sigma_emb.bias": 1}.get(name, cfg.embed_dim)
+            w = u * F32(2.0 / math.sqrt(fan_in))
+        sd[name] = w
+    return sd
 
 
 def make_weights(cfg: ModeConfig, seed: int = 1234, router_gain: float = 1.0) -> dict:
@@ -240,35 +270,41 @@ def attention(h, sd, layer, cfg: ModeConfig, prec="fp32"):
     H = cfg.n_heads
     dh = d // H
     hq = _q(h, prec)
+    ex = prec == "bf16"
     wq = lambda n: _q(sd[p + n + ".weight"], prec)  # noqa: E731
-    q = _q(linear(hq, wq("query"), sd[p + "query.bias"]), prec)
-    k = _q(linear(hq, wq("key"), sd[p + "key.bias"]), prec)
-    v = _q(linear(hq, wq("value"), sd[p + "value.bias"]), prec)
+    q = _q(linear(hq, wq("query"), sd[p + "query.bias"], ex), prec)
+    k = _q(linear(hq, wq("key"), sd[p + "key.bias"], ex), prec)
+    v = _q(linear(hq, wq("value"), sd[p + "value.bias"], ex), prec)
     split = lambda t: t.reshape(B, T, H, dh).transpose(0, 2, 1, 3)  # noqa: E731
     q, k, v = split(q), split(k), split(v)
     q = _q(rmsnorm(q, sd[p + "q_norm.g"], cfg.rms_eps), prec)
     k = _q(rmsnorm(k, sd[p + "k_norm.g"], cfg.rms_eps), prec)
-    s = np.matmul(q, k.transpose(0, 1, 3, 2)).astype(F32) * F32(1.0 / math.sqrt(dh))
+    if ex:
+        s = np.matmul(q.astype(np.float64), k.transpose(0, 1, 3, 2).astype(np.float64)).astype(F32)
+    else:
+        s = np.matmul(q, k.transpose(0, 1, 3, 2)).astype(F32)
+    s = s * F32(dh ** -0.5)
     mask = np.tril(np.ones((T, T), dtype=bool))
     s = np.where(mask, s, F32(-np.inf))
     m = s.max(axis=-1, keepdims=True)
     pexp = np.exp(s - m, dtype=F32)
     den = pexp.sum(axis=-1, keepdims=True, dtype=F32)
     if prec == "bf16":  # flash-style: unnormalised P rounded to bf16 for PV, fp32 row sum
-        o = np.matmul(bf16_round(pexp), v).astype(F32) / den
+        o = np.matmul(bf16_round(pexp).astype(np.float64), v.astype(np.float64)).astype(F32) / den
     else:
         o = np.matmul((pexp / den).astype(F32), v).astype(F32)
     o = _q(o.transpose(0, 2, 1, 3).reshape(B, T, d), prec)
-    return linear(o, _q(sd[p + "c_proj.weight"], prec))  # c_proj has no bias; resid_pdrop = 0
+    return linear(o, _q(sd[p + "c_proj.weight"], prec), None, ex)  # c_proj has no bias; resid_pdrop = 0
 
 
 def expert_mlp(x, sd, layer, e, prec="fp32"):
     """Mlp.forward with SwishGLU (modedit.py:83-90, :246-255): Linear(d,8d)+b -> proj*silu(gate) -> Linear(4d,d)."""
     p = f"blocks.{layer}.experts.expert_{e}.mlp."
-    z = linear(_q(x, prec), _q(sd[p + "0.project.weight"], prec), sd[p + "0.project.bias"])
+    ex = prec == "bf16"
+    z = linear(_q(x, prec), _q(sd[p + "0.project.weight"], prec), sd[p + "0.project.bias"], ex)
     half = z.shape[-1] // 2
     hdn = _q(z[..., :half] * silu(z[..., half:]), prec)
-    return _q(linear(hdn, _q(sd[p + "2.weight"], prec)), prec)
+    return _q(linear(hdn, _q(sd[p + "2.weight"], prec), None, ex), prec)
 
 
 def block_forward(x, c, sd, layer, cfg: ModeConfig, prec="fp32", sigma=None, return_routing=False):
@@ -309,8 +345,9 @@ def modedit_forward(sd, cfg: ModeConfig, state, actions, goal, sigma, prec="fp32
     A = cfg.action_seq_len
     pos = sd["pos_emb"]
     emb_t = sigma_embedding(sd, sigma, prec)  # (B, d)
-    goal_x = linear(_q(goal, prec), _q(sd["goal_emb.weight"], prec)) + pos[:, 0:1]
-    state_x = linear(_q(state, prec), _q(sd["tok_emb.weight"], prec)) + pos[:, 1:2]
+    ex = prec == "bf16"
+    goal_x = linear(_q(goal, prec), _q(sd["goal_emb.weight"], prec), None, ex) + pos[:, 0:1]
+    state_x = linear(_q(state, prec), _q(sd["tok_emb.weight"], prec), None, ex) + pos[:, 1:2]
     act_x = linear(actions, sd["action_emb.weight"]) + pos[:, 1:1 + A]
     x = np.concatenate([emb_t[:, None, :], goal_x, state_x, act_x], axis=1).astype(F32)
     routing = []

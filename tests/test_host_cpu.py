@@ -1,0 +1,125 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/mode_engine.h declares, the
+product path fails loudly without a GPU (no fallback), the nn.Module mirror has the reference's state_dict contract,
+and the schedule / sampler host logic matches the oracle (which is pinned to the reference by tests/test_oracle.py)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mode_oracle as O
+from mode_diffusion_policy_b200 import _lib, gc_sampling as S
+from mode_diffusion_policy_b200.modedit import MoDeDiT, NoiseBlockMoE
+from mode_diffusion_policy_b200.score_wrappers import GCDenoiser
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "mode_engine.h").read_text()
+    declared = set(re.findall(r"\b(mode_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mode_engine.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+def test_config_struct_layout_matches_header():
+    header = (ROOT / "include" / "mode_engine.h").read_text()
+    body = header[header.index("typedef struct mode_config {"):header.index("} mode_config_t;")]
+    fields = re.findall(r"^\s*(?:int32_t|float)\s+([a-z_]+);", body, flags=re.M)
+    assert fields == [f[0] for f in _lib.mode_config_t._fields_]
+    assert ctypes.sizeof(_lib.mode_config_t) == 4 * len(fields)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    lib = _lib.load()
+    cfg = _lib.mode_config_t(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=1, n_heads=4,
+                             n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2, router_normalize=1,
+                             max_batch=4, sigma_data=0.5, rms_eps=1e-6)
+    h = ctypes.c_void_p()
+    rc = lib.mode_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == -2 and not h.value  # MODE_ERR_CUDA, no engine
+    assert lib.mode_last_error()
+    from mode_diffusion_policy_b200.engine import EngineConfig, ModeEngine
+
+    with pytest.raises(_lib.ModeError):
+        ModeEngine(EngineConfig(max_batch=2))
+    m = MoDeDiT(obs_dim=128, goal_dim=64, device="cpu", goal_conditioned=True, action_dim=7, embed_dim=256,
+                embed_pdrob=0, attn_pdrop=0.3, n_layers=1, n_heads=4, goal_seq_len=1, obs_seq_len=1, action_seq_len=10,
+                state_dim=7).eval()
+    with pytest.raises(_lib.ModeError):  # no silent PyTorch path behind the module
+        m({"state_images": torch.zeros(1, 2, 128)}, torch.zeros(1, 10, 7), torch.zeros(1, 1, 64), torch.ones(1))
+
+
+def test_module_mirror_has_reference_state_dict_contract():
+    cfg = O.ModeConfig(obs_dim=128, goal_dim=64, embed_dim=256, n_layers=2, n_heads=4, num_experts=4)
+    m = MoDeDiT(obs_dim=128, goal_dim=64, device="cpu", goal_conditioned=True, action_dim=7, embed_dim=256,
+                embed_pdrob=0, attn_pdrop=0.3, n_layers=2, n_heads=4, goal_seq_len=1, obs_seq_len=1, action_seq_len=10,
+                state_dim=7, num_experts=4, top_k=2, init_style="olmoe")
+    got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert got == [(n, tuple(s)) for n, s in O.state_dict_spec(cfg)]  # names, shapes AND order (EMA zips by position)
+    den = GCDenoiser(m, sigma_data=0.5)
+    assert [k for k in den.state_dict()] == ["inner_model." + n for n, _ in O.state_dict_spec(cfg)]
+    blocks = [mod for mod in den.modules() if isinstance(mod, NoiseBlockMoE)]
+    assert len(blocks) == 2 and blocks[0].total_tokens_processed == 0
+    assert torch.equal(blocks[0].get_expert_usage(), torch.zeros(4))
+    names = dict(m.named_parameters())
+    assert all(n in names for n in ("blocks.0.router.router.mlp.3.bias", "pos_emb", "out.bias"))
+    m.freeze_router()
+    assert not any(p.requires_grad for p in m.blocks[0].router.parameters())
+    assert m.get_router_states()[1]["frozen"]
+    with pytest.raises(NotImplementedError):
+        MoDeDiT(obs_dim=128, goal_dim=64, device="cpu", goal_conditioned=True, action_dim=7, embed_dim=256,
+                embed_pdrob=0, attn_pdrop=0.3, n_layers=1, n_heads=4, goal_seq_len=1, obs_seq_len=1, action_seq_len=10,
+                state_dim=7, use_proprio=True)
+
+
+def test_schedules_match_oracle_and_reference_values():
+    s = S.get_sigmas_exponential(10, 1e-3, 80.0).numpy()
+    np.testing.assert_allclose(s, O.get_sigmas_exponential(10, 1e-3, 80.0), rtol=2e-6)
+    # SURVEY.md §8a a3 [probe of the reference]
+    np.testing.assert_allclose(s, [80, 22.82, 6.509, 1.857, 0.5296, 0.1511, 0.04309, 0.01229, 0.003506, 0.001, 0], rtol=2e-3)
+    np.testing.assert_allclose(S.get_sigmas_karras(10, 1e-3, 80.0).numpy(), O.get_sigmas_karras(10, 1e-3, 80.0), rtol=1e-5)
+    np.testing.assert_allclose(S.get_sigmas_linear(5, 1e-3, 80.0).numpy(), O.get_sigmas_linear(5, 1e-3, 80.0), rtol=1e-6)
+    for fn in (S.get_sigmas_vp, S.cosine_beta_schedule):
+        v = fn(8)
+        assert v.shape == (9,) and v[-1] == 0
+
+
+class _ToyDenoiser:
+    """D(x; sigma) = x / (1 + sigma^2): the exact denoiser of N(0, 1) data — lets the sampler logic run on CPU."""
+
+    def __call__(self, state, x, goal, sigma, **kw):
+        return x / (1 + sigma.view(-1, 1, 1) ** 2)
+
+
+def test_samplers_host_logic():
+    torch.manual_seed(0)
+    model = _ToyDenoiser()
+    sig = S.get_sigmas_exponential(10, 1e-3, 80.0)
+    x0 = torch.randn(4, 10, 7) * 80.0
+    # ddim against the oracle's coefficient table (pinned to the reference through the goldens)
+    x = x0.numpy().copy()
+    for i, (ratio, em1) in enumerate(O.ddim_coefficients(sig.numpy())):
+        den = x / (1 + sig[i].item() ** 2)
+        x = (ratio * x - em1 * den).astype(np.float32)
+    got = S.sample_ddim(model, None, x0, None, sig)
+    np.testing.assert_allclose(got.numpy(), x, rtol=2e-5, atol=1e-6)
+    # every deterministic sampler lands on (numerically) the same sample of the probability-flow ODE
+    ref = S.sample_heun(model, None, x0, None, S.get_sigmas_exponential(200, 1e-3, 80.0)).numpy()
+    for name in ("euler", "heun", "dpm", "dpmpp_2m", "dpmpp_2s", "lms", "ddim", "dpmpp_2_with_lms"):
+        out = S.SAMPLERS[name](model, None, x0, None, S.get_sigmas_exponential(60, 1e-3, 80.0)).numpy()
+        assert np.abs(out - ref).max() < 0.15 * np.abs(ref).max() + 1e-3, name
+    for name in ("euler_ancestral", "ancestral", "dpmpp_2s_ancestral"):
+        out = S.SAMPLERS[name](model, None, x0, None, sig)
+        assert torch.isfinite(out).all() and out.shape == x0.shape
+    calls = []
+    S.sample_ddim(model, None, x0, None, sig, callback=lambda d: calls.append(d["i"]))
+    assert calls == list(range(10))
+    down, up = S.get_ancestral_step(2.0, 1.0)
+    assert abs(down ** 2 + up ** 2 - 1.0) < 1e-6
