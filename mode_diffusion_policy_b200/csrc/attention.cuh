@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
 #pragma unroll
         for (int o = VPR / 2; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         // RMSNorm.forward (modedit.py:78-80): x / clamp(||x|| * dim^-0.5, eps) * g
-        const float n = fmaxf(sqrtf(ss) * inv_sqrt_dh, p.eps);
+        const float rn = 1.0f / fmaxf(sqrtf(ss) * inv_sqrt_dh, p.eps);  // one division per row
         const float* g = which == 0 ? gq : gk;
         uint4 o4;
-        o4.x = pack_bf16x2(__fdiv_rn(v[0], n) * g[0], __fdiv_rn(v[1], n) * g[1]);
-        o4.y = pack_bf16x2(__fdiv_rn(v[2], n) * g[2], __fdiv_rn(v[3], n) * g[3]);
-        o4.z = pack_bf16x2(__fdiv_rn(v[4], n) * g[4], __fdiv_rn(v[5], n) * g[5]);
-        o4.w = pack_bf16x2(__fdiv_rn(v[6], n) * g[6], __fdiv_rn(v[7], n) * g[7]);
+        o4.x = pack_bf16x2((v[0] * rn) * g[0], (v[1] * rn) * g[1]);
+        o4.y = pack_bf16x2((v[2] * rn) * g[2], (v[3] * rn) * g[3]);
+        o4.z = pack_bf16x2((v[4] * rn) * g[4], (v[5] * rn) * g[5]);
+        o4.w = pack_bf16x2((v[6] * rn) * g[6], (v[7] * rn) * g[7]);
         raw = o4;
       }
       *reinterpret_cast<uint4*>(dst) = raw;

@@ -53,10 +53,14 @@ namespace {
 // blocks of 256 rows hold 128 projected rows followed by their 128 gate rows so that one 128x256 GEMM tile contains
 // both halves of 128 hidden units and the SwiGLU product can be formed in the epilogue.
 __global__ void pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, int rows, int cols,
-                                 size_t dst_row0, int swiglu_half, int to_bf16) {
+                                 size_t dst_row0, int swiglu_half, int to_bf16, int transpose) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<size_t>(rows) * cols) return;
   const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  if (transpose) {
+    reinterpret_cast<float*>(dst)[static_cast<size_t>(c) * rows + r] = src[i];
+    return;
+  }
   int dr = r;
   if (swiglu_half > 0) {
     const int is_gate = r >= swiglu_half;
@@ -126,6 +130,7 @@ struct WeightSpec {
   int swiglu_half;
   int to_bf16;
   bool ignore;
+  bool transpose;  // store [cols, rows] (fp32 only)
   bool provided;
 };
 
@@ -161,6 +166,8 @@ struct mode_engine {
 
   CUtensorMap tm_hA, tm_attn, tm_perm, tm_h, tm_st, tm_goal;
   CUtensorMap tm_wqkv, tm_wproj, tm_wup, tm_wdown, tm_wtok, tm_wgoal;
+  CUtensorMap to_h, to_y;                          // grouped outputs (padded rows, fixed extent)
+  CUtensorMap to_qkv, to_x, to_state, to_goal;     // dense outputs: extent = exact rows of the current batch
 
   cudaStream_t cap_stream = nullptr;
   std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
@@ -205,20 +212,29 @@ static int get_encode_fn() {
   return MODE_OK;
 }
 
-// K-major bf16 matrix [rows, cols]; tiles of {64 columns, box_rows rows}, 128-byte swizzle (matches make_smem_desc_sw128).
-static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// Row-major matrix [rows, cols] of bf16 (elem_bytes 2) or fp32 (4); tiles of {128 bytes of columns, box_rows rows},
+// 128-byte swizzle (matches make_smem_desc_sw128 for operands and the epilogue staging layout for outputs).
+static int make_tmap_ex(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int elem_bytes) {
   RET_IF(get_encode_fn());
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {128u / (uint32_t)elem_bytes, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(MODE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
-                (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return fail(MODE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u elem=%d", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, box_rows, elem_bytes);
   return MODE_OK;
+}
+// GEMM operand map: K-major bf16, box {64 columns, box_rows}
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_ex(m, base, rows, cols, box_rows, 2);
+}
+// GEMM output map: one epilogue warp stores 32 rows x 128 bytes per bulk tensor store
+static int make_out_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, int elem_bytes) {
+  return make_tmap_ex(m, base, rows, cols, 32, elem_bytes);
 }
 
 template <typename T>
@@ -306,7 +322,7 @@ static int launch_attn(cudaStream_t st, const AttnParams& p, int Dh) {
 
 // ------------------------------------------------------------------------------------------------ create / destroy
 static void add_spec(mode_engine* e, const std::string& name, void* dst, size_t row0, int rows, int cols, int half,
-                     int bf16, bool ignore = false) {
+                     int bf16, bool ignore = false, bool transpose = false) {
   WeightSpec s;
   s.dst = dst;
   s.dst_row0 = row0;
@@ -315,6 +331,7 @@ static void add_spec(mode_engine* e, const std::string& name, void* dst, size_t 
   s.swiglu_half = half;
   s.to_bf16 = bf16;
   s.ignore = ignore;
+  s.transpose = transpose;
   s.provided = false;
   e->specs[name] = s;
 }
@@ -455,6 +472,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(make_tmap(&e->tm_wdown, e->w_down, (uint64_t)L * E * d, F, 256));
   A_(make_tmap(&e->tm_wtok, e->w_tok, d, e->obs, 256));
   A_(make_tmap(&e->tm_wgoal, e->w_goal, d, e->gdim, 256));
+  A_(make_out_tmap(&e->to_h, e->hbuf, e->perm_rows, F, 2));
+  A_(make_out_tmap(&e->to_y, e->ybuf, e->perm_rows, d, 2));
   if (rc == MODE_OK && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
     rc = fail(MODE_ERR_CUDA, "cudaStreamCreate failed");
 #undef A_
@@ -470,7 +489,7 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   add_spec(e, "tok_emb.weight", e->w_tok, 0, d, e->obs, 0, 1);
   add_spec(e, "gripper_embed.weight", nullptr, 0, d, e->obs, 0, 0, true);
   add_spec(e, "goal_emb.weight", e->w_goal, 0, d, e->gdim, 0, 1);
-  add_spec(e, "action_emb.weight", e->w_act, 0, d, e->adim, 0, 0);
+  add_spec(e, "action_emb.weight", e->w_act, 0, d, e->adim, 0, 0, false, true);  // stored transposed [adim, d]
   add_spec(e, "ln.g", e->lnf_g, 0, 1, d, 0, 0);
   add_spec(e, "out.weight", e->w_out, 0, e->adim, d, 0, 0);
   add_spec(e, "out.bias", e->b_out, 0, 1, e->adim, 0, 0);
@@ -520,7 +539,8 @@ extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* d
   CU_OK(cudaMemcpy(e->stage, data, numel * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
   const int threads = 256;
   const unsigned blocks = (unsigned)((numel + threads - 1) / threads);
-  pack_rows_kernel<<<blocks, threads>>>(e->stage, s.dst, s.rows, s.cols, s.dst_row0, s.swiglu_half, s.to_bf16);
+  pack_rows_kernel<<<blocks, threads>>>(e->stage, s.dst, s.rows, s.cols, s.dst_row0, s.swiglu_half, s.to_bf16,
+                                        s.transpose ? 1 : 0);
   CU_OK(cudaGetLastError());
   CU_OK(cudaDeviceSynchronize());
   return MODE_OK;
@@ -569,26 +589,48 @@ static int ensure_batch(mode_engine* e, int B) {
   CU_OK(cudaDeviceSynchronize());
   CU_OK(cudaMemcpy(e->dense_tiles, tiles.data(), tiles.size() * sizeof(GemmMTile), cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(e->dense_counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
+  // output maps clip at the exact row count, so partially filled 32-row store boxes never touch rows >= M
+  RET_IF(make_out_tmap(&e->to_qkv, e->qkv, rows[0], 3 * e->d, 2));
+  RET_IF(make_out_tmap(&e->to_x, e->x, rows[0], e->d, 4));
+  RET_IF(make_out_tmap(&e->to_state, e->state_tok, rows[1], e->d, 4));
+  RET_IF(make_out_tmap(&e->to_goal, e->goal_tok, rows[2], e->d, 4));
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);  // captured kernels embed the old maps
+  e->graphs.clear();
+  e->graph_launches.clear();
   e->cur_B = B;
   return MODE_OK;
 }
 
-static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, const GemmMTile* tiles, const int* ntiles,
-                              int N, int Kdim, void* out, int ld, const float* bias, const float* resid) {
+static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout,
+                              const GemmMTile* tiles, const int* ntiles, int N, int Kdim, const float* bias) {
   GemmParams p;
   p.tmap_a = ta;
   p.tmap_w = tw;
+  p.tmap_out = tout;
   p.m_tiles = tiles;
   p.num_m_tiles = ntiles;
   p.n_blocks = N / GEMM_BLOCK_N;
   p.k_blocks = Kdim / GEMM_BLOCK_K;
-  p.out = out;
-  p.ld_out = ld;
   p.bias = bias;
-  p.resid = resid;
   p.w_row_off = 0;
   return p;
 }
+
+// embed_dim is a multiple of 256 -> d/128 float4 vectors per lane, compile-time for register-resident rows
+#define LAUNCH_ROW_KERNEL(KERNEL, d, grid, st, params)                                        \
+  do {                                                                                        \
+    switch ((d) / 128) {                                                                      \
+      case 2: KERNEL<2><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
+      case 4: KERNEL<4><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
+      case 6: KERNEL<6><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
+      case 8: KERNEL<8><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
+      case 10: KERNEL<10><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
+      case 12: KERNEL<12><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
+      case 14: KERNEL<14><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
+      case 16: KERNEL<16><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
+      default: return fail(MODE_ERR_INVALID, "embed_dim %d unsupported by the row kernels", (d)); \
+    }                                                                                         \
+  } while (0)
 
 static inline unsigned row_blocks(int rows) { return (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS); }
 
@@ -599,11 +641,11 @@ static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* sta
   cast_bf16_kernel<<<(unsigned)((n_st + 255) / 256), 256, 0, st>>>(state_dev, e->st_bf16, n_st);
   cast_bf16_kernel<<<(unsigned)((n_g + 255) / 256), 256, 0, st>>>(goal_dev, e->goal_bf16, n_g);
   CU_OK(cudaGetLastError());
-  GemmParams p = gemm_params(e->tm_st, e->tm_wtok, e->dense_tiles + e->dense_cap, e->dense_counts + 1, e->d, e->obs,
-                             e->state_tok, e->d, nullptr, nullptr);
+  GemmParams p = gemm_params(e->tm_st, e->tm_wtok, e->to_state, e->dense_tiles + e->dense_cap, e->dense_counts + 1,
+                             e->d, e->obs, nullptr);
   RET_IF(launch_gemm(EPI_PLAIN_F32, e->num_sms, st, p));
-  p = gemm_params(e->tm_goal, e->tm_wgoal, e->dense_tiles + 2 * e->dense_cap, e->dense_counts + 2, e->d, e->gdim,
-                  e->goal_tok, e->d, nullptr, nullptr);
+  p = gemm_params(e->tm_goal, e->tm_wgoal, e->to_goal, e->dense_tiles + 2 * e->dense_cap, e->dense_counts + 2, e->d,
+                  e->gdim, nullptr);
   RET_IF(launch_gemm(EPI_PLAIN_F32, e->num_sms, st, p));
   e->launch_count += 4;
   return MODE_OK;
@@ -619,7 +661,8 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   r.topk_idx = e->topk_idx; r.topk_w = e->topk_w; r.sel_idx = e->sel_idx; r.sel_w = e->sel_w;
   r.probs = e->probs; r.logits = e->logits;
   r.L = n_layers; r.layer0 = layer0; r.B = B; r.E = e->E; r.K = e->K; r.Hd = e->Hd; r.normalize = e->cfg.router_normalize;
-  router_kernel<<<row_blocks(n_layers * B), ROW_WARPS * 32, 0, st>>>(r);
+  const int distinct_rows = (stride == 0 && !z_explicit) ? 1 : B;
+  router_kernel<<<n_layers * distinct_rows, ROW_WARPS * 32, 0, st>>>(r);
   PlanParams pl;
   pl.sel_idx = e->sel_idx; pl.pos = e->pos_tab; pl.up_tiles = e->up_tiles; pl.down_tiles = e->down_tiles;
   pl.num_tiles = e->num_tiles; pl.usage = e->usage; pl.tokens = e->tokens;
@@ -634,8 +677,7 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
 // One NoiseBlockMoE (modedit.py:530-595) given hA = bf16(ln_1(x)+c) and routing tables for layer l.
 static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode) {
   const int d = e->d, M = B * e->T;
-  GemmParams p = gemm_params(e->tm_hA, e->tm_wqkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->qkv, 3 * d,
-                             e->b_qkv, nullptr);
+  GemmParams p = gemm_params(e->tm_hA, e->tm_wqkv, e->to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
   {
     ProfScope ps(e, st, PC_QKV);
@@ -648,7 +690,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     ProfScope ps(e, st, PC_ATTN);
     RET_IF(launch_attn(st, a, e->Dh));
   }
-  p = gemm_params(e->tm_attn, e->tm_wproj, e->dense_tiles, e->dense_counts, d, d, e->x, d, nullptr, e->x);
+  p = gemm_params(e->tm_attn, e->tm_wproj, e->to_x, e->dense_tiles, e->dense_counts, d, d, nullptr);  // x += acc
   p.w_row_off = l * d;
   {
     ProfScope ps(e, st, PC_PROJ);
@@ -659,17 +701,17 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_LN2);
-    ln2_permute_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(n2);
+    LAUNCH_ROW_KERNEL(ln2_permute_kernel, d, row_blocks(M), st, n2);
   }
   CU_OK(cudaGetLastError());
-  p = gemm_params(e->tm_perm, e->tm_wup, e->up_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, 8 * d, d, e->hbuf,
-                  e->F, e->b_up, nullptr);
+  p = gemm_params(e->tm_perm, e->tm_wup, e->to_h, e->up_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, 8 * d, d,
+                  e->b_up);
   {
     ProfScope ps(e, st, PC_UP);
     RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->num_sms, st, p));
   }
-  p = gemm_params(e->tm_h, e->tm_wdown, e->down_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, d, e->F, e->ybuf, d,
-                  nullptr, nullptr);
+  p = gemm_params(e->tm_h, e->tm_wdown, e->to_y, e->down_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, d, e->F,
+                  nullptr);
   {
     ProfScope ps(e, st, PC_DOWN);
     RET_IF(launch_gemm(EPI_PLAIN_BF16, e->num_sms, st, p));
@@ -681,7 +723,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_COMBINE);
-    combine_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(c);
+    LAUNCH_ROW_KERNEL(combine_kernel, d, row_blocks(M), st, c);
   }
   CU_OK(cudaGetLastError());
   e->launch_count += 7;
@@ -695,12 +737,12 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   EmbedParams em;
   em.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   em.sig_u = e->sig_u; em.sig_v = e->sig_v; em.goal_tok = e->goal_tok; em.state_tok = e->state_tok; em.pos = e->pos;
-  em.w_act = e->w_act; em.actions = actions; em.ln1_g = e->ln1_g; em.x = e->x; em.cvec = e->cvec; em.hA = e->hA;
+  em.w_act_t = e->w_act; em.actions = actions; em.ln1_g = e->ln1_g; em.x = e->x; em.cvec = e->cvec; em.hA = e->hA;
   em.B = B; em.T = e->T; em.S = e->S; em.A = e->A; em.action_dim = e->adim; em.d = e->d; em.apply_c_in = apply_c_in;
   em.eps = e->cfg.rms_eps; em.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_EMBED);
-    embed_kernel<<<row_blocks(B * e->T), ROW_WARPS * 32, 0, st>>>(em);
+    LAUNCH_ROW_KERNEL(embed_kernel, e->d, row_blocks(B * e->T), st, em);
   }
   CU_OK(cudaGetLastError());
   for (int l = 0; l < e->L; ++l) RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1));
@@ -711,7 +753,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   h.B = B; h.T = e->T; h.A = e->A; h.action_dim = e->adim; h.d = e->d; h.mode = head_mode;
   {
     ProfScope ps(e, st, PC_HEAD);
-    head_kernel<<<row_blocks(B * e->A), ROW_WARPS * 32, 0, st>>>(h);
+    LAUNCH_ROW_KERNEL(head_kernel, e->d, row_blocks(B * e->A), st, h);
   }
   CU_OK(cudaGetLastError());
   e->launch_count += 2;
@@ -896,7 +938,7 @@ extern "C" int mode_block_forward(mode_engine_t* e, int layer, const float* x_de
   Ln1Params l1;
   l1.x = e->x; l1.cvec = e->cvec; l1.g = e->ln1_g + (size_t)layer * d; l1.hA = e->hA; l1.rows = M; l1.T = e->T; l1.d = d;
   l1.eps = e->cfg.rms_eps; l1.inv_sqrt_d = e->inv_sqrt_d;
-  ln1_kernel<<<row_blocks(M), ROW_WARPS * 32, 0, st>>>(l1);
+  LAUNCH_ROW_KERNEL(ln1_kernel, d, row_blocks(M), st, l1);
   CU_OK(cudaGetLastError());
   RET_IF(enqueue_block(e, st, B, layer, 2));
   CU_OK(cudaMemcpyAsync(out_dev, e->x, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -958,8 +1000,15 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
   // The caller allocates A with round_up(M, 128) rows so the TMA box never exceeds the tensor extent.
   RET_IF(make_tmap(&ta, a_dev, round_up(M, 128), Kdim, 128));
   RET_IF(make_tmap(&tw, w_dev, N, Kdim, 256));
-  const int ld = (epilogue == EPI_SWIGLU_BF16) ? N / 2 : N;
-  GemmParams p = gemm_params(ta, tw, d_tiles, d_n, N, Kdim, out_dev, ld, bias_dev, resid_dev);
+  const int n_out = (epilogue == EPI_SWIGLU_BF16) ? N / 2 : N;
+  const int out_bytes = (epilogue == EPI_RESID_F32 || epilogue == EPI_PLAIN_F32) ? 4 : 2;
+  CUtensorMap tout;
+  RET_IF(make_out_tmap(&tout, out_dev, M, n_out, out_bytes));
+  if (epilogue == EPI_RESID_F32) {  // the kernel accumulates into the output: seed it with the residual
+    if (!resid_dev) return fail(MODE_ERR_INVALID, "resid epilogue needs resid_dev");
+    CU_OK(cudaMemcpyAsync(out_dev, resid_dev, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  GemmParams p = gemm_params(ta, tw, tout, d_tiles, d_n, N, Kdim, bias_dev);
   int rc = launch_gemm(epilogue, sms, st, p);
   // MODE_GEMM_BENCH_REPS=n: time n further back-to-back launches with CUDA events and print the average
   if (rc == MODE_OK && getenv("MODE_GEMM_BENCH_REPS")) {

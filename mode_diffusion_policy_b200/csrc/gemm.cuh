@@ -25,11 +25,14 @@ constexpr int GEMM_B_BYTES = GEMM_BLOCK_N * GEMM_BLOCK_K * 2;  // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_TMEM_COLS = 512;  // two 256-column accumulators
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_EPI_BUF_BYTES = 32 * 128;  // one warp's staging tile: 32 rows x 128 B (SWIZZLE_128B box of the TMA store)
+constexpr int GEMM_EPI_BYTES = 4 * 2 * GEMM_EPI_BUF_BYTES;  // 4 epilogue warps, double-buffered
+constexpr int GEMM_SMEM_BYTES =
+    GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*barriers*/ + GEMM_EPI_BYTES + 1024 /*align slack*/;
 
 enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,    // out_bf16 = acc + bias[w_row]                       (packed QKV projection)
-  EPI_RESID_F32 = 1,    // out_f32  = resid_f32 + acc   (in-place allowed)    (attention c_proj + residual)
+  EPI_RESID_F32 = 1,    // out_f32 += acc  (TMA reduce-add into the residual stream) (attention c_proj + residual)
   EPI_SWIGLU_BF16 = 2,  // out_bf16[., nb*128+j] = (acc[j]+b[j]) * silu(acc[128+j]+b[128+j])   (expert up-projection)
   EPI_PLAIN_BF16 = 3,   // out_bf16 = acc                                      (expert down-projection)
   EPI_PLAIN_F32 = 4,    // out_f32  = acc                                      (obs/goal token embeddings)
@@ -50,14 +53,118 @@ struct alignas(64) GemmParams {
   const int* num_m_tiles;      // device scalar (grouped GEMMs build it on the GPU)
   int n_blocks;                // N / 256
   int k_blocks;                // K / 64
-  void* out;                   // bf16 or f32, row-major
-  int ld_out;                  // elements
+  CUtensorMap tmap_out;        // output [rows, N_out] bf16 (box {64, 32}) or f32 (box {32, 32}), SWIZZLE_128B
   const float* bias;           // indexed by weight row (packed like the weights), may be null
-  const float* resid;          // EPI_RESID_F32 only; may alias out
   int w_row_off;               // added to every tile's w_row_base (layer offset of dense projections)
 };
 
 __device__ __forceinline__ float silu_f(float g) { return __fdividef(g, 1.0f + __expf(-g)); }
+
+// Fused epilogue of one warp's 32 accumulator rows x 256 columns. Each lane owns one row (TMEM lane); values go
+// TMEM -> registers -> epilogue math -> a 32 x 128 B staging tile in shared memory laid out in the TMA SWIZZLE_128B
+// pattern (16-byte chunk j of row r lives at chunk j ^ (r & 7): conflict-free v4 stores) -> ONE bulk tensor store
+// (or reduce-add) per chunk issued by lane 0, double-buffered with bulk async-groups. Global writes are therefore
+// full 128-byte rows instead of 32 scattered 16-byte pieces per instruction.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t taddr, uint32_t stage_smem, int lane,
+                                                   int out_row0, int w_row, int nb, uint32_t& n_stores) {
+  const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+  auto chunk_addr = [&](uint32_t buf, uint32_t j) { return buf + row_off + ((j ^ sw) << 4); };
+  auto begin_chunk = [&]() -> uint32_t {
+    // the store issued two chunks ago read this buffer: wait until at most one store is still reading smem
+    if (lane == 0) bulk_wait_group_read<1>();
+    __syncwarp();
+    return stage_smem + (n_stores & 1u) * GEMM_EPI_BUF_BYTES;
+  };
+  auto end_chunk = [&](uint32_t buf, int col) {
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (EPI == EPI_RESID_F32)
+        tma_reduce_add_2d(&p.tmap_out, buf, col, out_row0);
+      else
+        tma_store_2d(&p.tmap_out, buf, col, out_row0);
+      bulk_commit_group();
+    }
+    ++n_stores;
+  };
+
+  if constexpr (EPI == EPI_SWIGLU_BF16) {
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {  // 64 hidden units per store
+      const uint32_t buf = begin_chunk();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c32 = c * 64 + hh * 32;
+        uint32_t rp[32], rg[32];
+        tmem_ld_32x32(taddr + c32, rp);
+        tmem_ld_32x32(taddr + 128 + c32, rg);
+        tmem_ld_wait();
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + w_row + c32);
+        const float4* bg = reinterpret_cast<const float4*>(p.bias + w_row + 128 + c32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 b0 = __ldg(bp + 2 * j + u), b1 = __ldg(bg + 2 * j + u);
+            const int o = 8 * j + 4 * u;
+            const float h0 = (__uint_as_float(rp[o + 0]) + b0.x) * silu_f(__uint_as_float(rg[o + 0]) + b1.x);
+            const float h1 = (__uint_as_float(rp[o + 1]) + b0.y) * silu_f(__uint_as_float(rg[o + 1]) + b1.y);
+            const float h2 = (__uint_as_float(rp[o + 2]) + b0.z) * silu_f(__uint_as_float(rg[o + 2]) + b1.z);
+            const float h3 = (__uint_as_float(rp[o + 3]) + b0.w) * silu_f(__uint_as_float(rg[o + 3]) + b1.w);
+            pk[2 * u] = pack_bf16x2(h0, h1);
+            pk[2 * u + 1] = pack_bf16x2(h2, h3);
+          }
+          st_shared_v4(chunk_addr(buf, hh * 4 + j), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      end_chunk(buf, nb * 128 + c * 64);
+    }
+  } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_PLAIN_BF16) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {  // 64 output columns per store
+      const uint32_t buf = begin_chunk();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c32 = c * 64 + hh * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+          if constexpr (EPI == EPI_BIAS_BF16) {
+            const float4* b = reinterpret_cast<const float4*>(p.bias + w_row + c32);
+            const float4 b0 = __ldg(b + 2 * j), b1 = __ldg(b + 2 * j + 1);
+            pk[0] = pack_bf16x2(__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
+            pk[1] = pack_bf16x2(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
+            pk[2] = pack_bf16x2(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
+            pk[3] = pack_bf16x2(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              pk[u] = pack_bf16x2(__uint_as_float(r[8 * j + 2 * u]), __uint_as_float(r[8 * j + 2 * u + 1]));
+          }
+          st_shared_v4(chunk_addr(buf, hh * 4 + j), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      end_chunk(buf, nb * GEMM_BLOCK_N + c * 64);
+    }
+  } else {  // fp32 outputs: 32 columns (128 B) per store
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t buf = begin_chunk();
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st_shared_v4(chunk_addr(buf, j), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      end_chunk(buf, nb * GEMM_BLOCK_N + c * 32);
+    }
+  }
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
@@ -65,6 +172,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = smem_u32(smem);
+  // layout: [stage ring][256 B barriers][epilogue staging]; barriers sit in a 1 KB slot so the staging stays 1 KB-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
   const uint32_t bar_base = smem_u32(bars);
   // barrier slots: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address word
@@ -73,6 +181,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + 2 + s); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+  const uint32_t epi_smem = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + 1024;  // 1024-aligned: stages are 48 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,6 +189,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_w);
+    tma_prefetch_desc(&p.tmap_out);
     for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -162,7 +272,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row_in_tile = q * 32 + lane;
+    const uint32_t stage_smem = epi_smem + static_cast<uint32_t>(q) * 2 * GEMM_EPI_BUF_BYTES;
+    uint32_t n_stores = 0;
     int iter = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++iter) {
       const int mt = t % n_m, nb = t / n_m;
@@ -171,93 +282,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const uint32_t aphase = (iter >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const bool row_ok = row_in_tile < tile.rows_valid;
-      const size_t out_row = static_cast<size_t>(tile.out_row0 + row_in_tile);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
-      const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N;
-
-      if constexpr (EPI == EPI_SWIGLU_BF16) {
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ld_out + nb * 128;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t rp[32], rg[32];
-          tmem_ld_32x32(taddr + c * 32, rp);
-          tmem_ld_32x32(taddr + 128 + c * 32, rg);
-          tmem_ld_wait();
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + w_row + c * 32);
-          const float4* bg = reinterpret_cast<const float4*>(p.bias + w_row + 128 + c * 32);
-          uint32_t packed[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b0 = __ldg(bp + j), b1 = __ldg(bg + j);
-            const float h0 = (__uint_as_float(rp[4 * j + 0]) + b0.x) * silu_f(__uint_as_float(rg[4 * j + 0]) + b1.x);
-            const float h1 = (__uint_as_float(rp[4 * j + 1]) + b0.y) * silu_f(__uint_as_float(rg[4 * j + 1]) + b1.y);
-            const float h2 = (__uint_as_float(rp[4 * j + 2]) + b0.z) * silu_f(__uint_as_float(rg[4 * j + 2]) + b1.z);
-            const float h3 = (__uint_as_float(rp[4 * j + 3]) + b0.w) * silu_f(__uint_as_float(rg[4 * j + 3]) + b1.w);
-            packed[2 * j] = pack_bf16x2(h0, h1);
-            packed[2 * j + 1] = pack_bf16x2(h2, h3);
-          }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < GEMM_BLOCK_N / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          const int col = nb * GEMM_BLOCK_N + c * 32;
-          if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_PLAIN_BF16) {
-            uint32_t packed[16];
-            if constexpr (EPI == EPI_BIAS_BF16) {
-              const float4* b = reinterpret_cast<const float4*>(p.bias + w_row + c * 32);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = __ldg(b + j);
-                packed[2 * j] = pack_bf16x2(__uint_as_float(r[4 * j]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y);
-                packed[2 * j + 1] =
-                    pack_bf16x2(__uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                packed[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-            }
-            if (row_ok) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ld_out + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            }
-          } else {  // fp32 outputs
-            if (row_ok) {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ld_out + col);
-              if constexpr (EPI == EPI_RESID_F32) {
-                const float4* src = reinterpret_cast<const float4*>(p.resid + out_row * p.ld_out + col);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 x = src[j];
-                  dst[j] = make_float4(x.x + __uint_as_float(r[4 * j]), x.y + __uint_as_float(r[4 * j + 1]),
-                                       x.z + __uint_as_float(r[4 * j + 2]), x.w + __uint_as_float(r[4 * j + 3]));
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-              }
-            }
-          }
-        }
+      if (q * 32 < tile.rows_valid) {  // warp-uniform: this warp's 32 rows hold at least one real row
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
+        const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N;
+        gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + q * 32, w_row, nb, n_stores);
       }
-      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld): hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
     }
+    if (lane == 0) bulk_wait_group<0>();  // outstanding stores must land before the CTA retires
   }
 
   tc_fence_before();

@@ -20,9 +20,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// RMSNorm.forward, modedit.py:72-80: x / clamp(||x||_2 * dim^-0.5, min=eps) * g  (division then gain, as written)
-__device__ __forceinline__ float rms_denominator(float sumsq, float inv_sqrt_dim, float eps) {
-  return fmaxf(sqrtf(sumsq) * inv_sqrt_dim, eps);
+// RMSNorm.forward, modedit.py:72-80: x / clamp(||x||_2 * dim^-0.5, min=eps) * g. Returns 1/denominator: one IEEE
+// division per row, then a multiply per element (differs from the per-element division by <= 1 fp32 ulp).
+__device__ __forceinline__ float rms_inv_denominator(float sumsq, float inv_sqrt_dim, float eps) {
+  return 1.0f / fmaxf(sqrtf(sumsq) * inv_sqrt_dim, eps);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -59,7 +60,7 @@ struct EmbedParams {
   const float* goal_tok;   // [B, d]   fp32 goal_emb(goal)       (no pos yet; computed once per trajectory)
   const float* state_tok;  // [B*S, d] fp32 tok_emb(state_images)
   const float* pos;        // [1+A, d]
-  const float* w_act;      // [d, action_dim]  (nn.Linear layout)
+  const float* w_act_t;    // [action_dim, d]: action_emb.weight transposed at load time (coalesced float4 loads)
   const float* actions;    // [B, A, action_dim]
   const float* ln1_g;      // [d] layer-0 ln_1 gain
   float* x;                // [B*T, d]
@@ -71,15 +72,15 @@ struct EmbedParams {
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 
+template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
   const int b = row / p.T, t = row % p.T;
-  const int nvec = p.d / 128;
   const float sigma = load_sigma(p.sc, b);
   const float s = logf(sigma) / 4.0f;  // process_sigma_embeddings, modedit.py:824
-  float4 xv[MAX_VEC], cv[MAX_VEC];
+  float4 xv[NVEC], cv[NVEC];
   float ss = 0.f;
   float act[8];
   const int n_act = p.action_dim;
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams
     for (int j = 0; j < n_act && j < 8; ++j) act[j] = a[j] * c_in;
   }
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
+    {
       const int col = (i * 32 + lane) * 4;
       const float4 u = *reinterpret_cast<const float4*>(p.sig_u + col);
       const float4 v = *reinterpret_cast<const float4*>(p.sig_v + col);
@@ -110,12 +111,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams
         const int j = t - 2 - p.S;
         const float4 pe = *reinterpret_cast<const float4*>(p.pos + (1 + j) * p.d + col);
         float e[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float* w = p.w_act + static_cast<size_t>(col + q) * n_act;
-          float acc = 0.f;
-          for (int k = 0; k < n_act && k < 8; ++k) acc = fmaf(act[k], w[k], acc);
-          e[q] = acc;
+        for (int k = 0; k < n_act && k < 8; ++k) {
+          const float4 w = *reinterpret_cast<const float4*>(p.w_act_t + static_cast<size_t>(k) * p.d + col);
+          e[0] = fmaf(act[k], w.x, e[0]);
+          e[1] = fmaf(act[k], w.y, e[1]);
+          e[2] = fmaf(act[k], w.z, e[2]);
+          e[3] = fmaf(act[k], w.w, e[3]);
         }
         x = make_float4(e[0] + pe.x, e[1] + pe.y, e[2] + pe.z, e[3] + pe.w);
       }
@@ -124,17 +125,17 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams
     }
   }
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
+  const float rn = rms_inv_denominator(ss, p.inv_sqrt_d, p.eps);
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
+    {
       const int col = (i * 32 + lane) * 4;
       const float4 x = xv[i], c = cv[i];
       const float4 g = *reinterpret_cast<const float4*>(p.ln1_g + col);
       *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = x;
       if (t == 0) *reinterpret_cast<float4*>(p.cvec + static_cast<size_t>(b) * p.d + col) = c;
-      const float h0 = __fdiv_rn(x.x, n) * g.x + c.x, h1 = __fdiv_rn(x.y, n) * g.y + c.y;
-      const float h2 = __fdiv_rn(x.z, n) * g.z + c.z, h3 = __fdiv_rn(x.w, n) * g.w + c.w;
+      const float h0 = (x.x * rn) * g.x + c.x, h1 = (x.y * rn) * g.y + c.y;
+      const float h2 = (x.z * rn) * g.z + c.z, h3 = (x.w * rn) * g.w + c.w;
       *reinterpret_cast<uint2*>(p.hA + static_cast<size_t>(row) * p.d + col) =
           make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
     }
@@ -152,33 +153,31 @@ struct Ln1Params {
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
+template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) ln1_kernel(const Ln1Params p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.rows) return;
   const int b = row / p.T;
-  const int nvec = p.d / 128;
-  float4 xv[MAX_VEC];
+  float4 xv[NVEC];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
       const float4 x = *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.d + (i * 32 + lane) * 4);
       xv[i] = x;
       ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
+  const float rn = rms_inv_denominator(ss, p.inv_sqrt_d, p.eps);
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
       const int col = (i * 32 + lane) * 4;
       const float4 x = xv[i];
       const float4 g = *reinterpret_cast<const float4*>(p.g + col);
       const float4 c = *reinterpret_cast<const float4*>(p.cvec + static_cast<size_t>(b) * p.d + col);
       *reinterpret_cast<uint2*>(p.hA + static_cast<size_t>(row) * p.d + col) =
-          make_uint2(pack_bf16x2(__fdiv_rn(x.x, n) * g.x + c.x, __fdiv_rn(x.y, n) * g.y + c.y),
-                     pack_bf16x2(__fdiv_rn(x.z, n) * g.z + c.z, __fdiv_rn(x.w, n) * g.w + c.w));
+          make_uint2(pack_bf16x2((x.x * rn) * g.x + c.x, (x.y * rn) * g.y + c.y),
+                     pack_bf16x2((x.z * rn) * g.z + c.z, (x.w * rn) * g.w + c.w));
     }
 }
 
@@ -206,11 +205,14 @@ struct RouterParams {
   int normalize;
 };
 
+// One CTA (8 warps) per (layer, distinct sigma row): each warp covers Hd/8 hidden units, partial logits are reduced
+// through shared memory, warp 0 finishes. With sigma_stride == 0 (samplers) there is ONE distinct row per layer; its
+// result is broadcast to all B samples' table slots.
 __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterParams p) {
-  const int item = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (item >= p.L * p.B) return;
-  const int l = p.layer0 + item / p.B, b = item % p.B;
+  __shared__ float part[ROW_WARPS][MAX_EXPERTS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.sc.sigma_stride == 0 && !p.z_explicit ? 1 : p.B;  // distinct rows
+  const int l = p.layer0 + blockIdx.x / R, b = blockIdx.x % R;
   const float s = p.z_explicit ? 0.f : logf(load_sigma(p.sc, b)) / 4.0f;
   const float* ra = p.ra + static_cast<size_t>(l) * p.Hd;
   const float* rb = p.rb + static_cast<size_t>(l) * p.Hd;
@@ -218,21 +220,29 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterPara
   float acc[MAX_EXPERTS];
 #pragma unroll
   for (int e = 0; e < MAX_EXPERTS; ++e) acc[e] = 0.f;
-  for (int j = lane; j < p.Hd; j += 32) {
+  for (int j = threadIdx.x; j < p.Hd; j += ROW_WARPS * 32) {
     const float z = p.z_explicit ? p.z_explicit[static_cast<size_t>(b) * p.Hd + j] : fmaf(s, ra[j], rb[j]);
     const float hdn = 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));  // nn.GELU() (erf form)
 #pragma unroll
     for (int e = 0; e < MAX_EXPERTS; ++e)
       if (e < p.E) acc[e] = fmaf(hdn, w2[static_cast<size_t>(e) * p.Hd + j], acc[e]);
   }
-  // lane e ends up owning expert e's logit
-  float logit = -INFINITY;
 #pragma unroll
   for (int e = 0; e < MAX_EXPERTS; ++e) {
     if (e < p.E) {
       const float v = warp_sum(acc[e]);
-      if (lane == e) logit = v + p.b2[l * p.E + e];
+      if (lane == 0) part[warp][e] = v;
     }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  // lane e owns expert e's logit; fixed summation order over the 8 warps
+  float logit = -INFINITY;
+  if (lane < p.E) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) v += part[w][lane];
+    logit = v + p.b2[l * p.E + lane];
   }
   float mx = logit;
 #pragma unroll
@@ -242,18 +252,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterPara
   const float den = warp_sum(ex);
   float prob = ex / den;
   prob = fminf(fmaxf(prob, 1e-9f), 1.0f - 1e-9f);
-  const size_t pe = (static_cast<size_t>(l) * p.B + b) * p.E;
-  if (lane < p.E) {
-    p.probs[pe + lane] = prob;
-    p.logits[pe + lane] = zl;
-  }
   // top-k: k rounds of warp arg-max, ties -> lowest expert index
   float cand = lane < p.E ? prob : -1.f;
-  int sel[MAX_TOPK];
-  float selp[MAX_TOPK];
+  int sel[MAX_TOPK], srt[MAX_TOPK];
+  float selp[MAX_TOPK], srtp[MAX_TOPK];
   float psum = 0.f;
 #pragma unroll
   for (int k = 0; k < MAX_TOPK; ++k) {
+    sel[k] = 0;
+    selp[k] = 0.f;
     if (k < p.K) {
       float bv = cand;
       int bi = lane;
@@ -272,31 +279,53 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterPara
       if (lane == bi) cand = -1.f;
     }
   }
-  if (lane == 0) {
-    const size_t pk = (static_cast<size_t>(l) * p.B + b) * p.K;
-    for (int k = 0; k < p.K; ++k) {
-      const float w = p.normalize ? selp[k] / psum : selp[k];
-      selp[k] = w;
-      p.topk_idx[pk + k] = sel[k];
-      p.topk_w[pk + k] = w;
+  // renormalise (modedit.py:418-419) and build the ascending-expert order by rank counting (K <= 8, registers only)
+#pragma unroll
+  for (int k = 0; k < MAX_TOPK; ++k)
+    if (k < p.K && p.normalize) selp[k] = selp[k] / psum;
+#pragma unroll
+  for (int k = 0; k < MAX_TOPK; ++k) {
+    srt[k] = 0;
+    srtp[k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < MAX_TOPK; ++k) {
+    if (k < p.K) {
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < MAX_TOPK; ++j)
+        if (j < p.K && sel[j] < sel[k]) ++rank;
+#pragma unroll
+      for (int j = 0; j < MAX_TOPK; ++j)
+        if (j == rank) {
+          srt[j] = sel[k];
+          srtp[j] = selp[k];
+        }
     }
-    // ascending expert order (insertion sort, K <= 8)
-    for (int i = 1; i < p.K; ++i) {
-      const int ki = sel[i];
-      const float wi = selp[i];
-      int j = i - 1;
-      while (j >= 0 && sel[j] > ki) {
-        sel[j + 1] = sel[j];
-        selp[j + 1] = selp[j];
-        --j;
+  }
+  // write this row's result to its own slot, or to every sample's slot when one sigma serves the whole batch
+  const int n_dst = (R == 1) ? p.B : 1;
+  if (lane < p.E) {  // stage through shared memory (part[] is dead after the logit reduction above)
+    part[0][lane] = prob;
+    part[1][lane] = zl;
+  }
+  __syncwarp();
+  for (int i = lane; i < n_dst * p.E; i += 32) {
+    const int bb = (R == 1) ? i / p.E : b, e = i % p.E;
+    const size_t o = (static_cast<size_t>(l) * p.B + bb) * p.E + e;
+    p.probs[o] = part[0][e];
+    p.logits[o] = part[1][e];
+  }
+  for (int bb = (R == 1 ? lane : (lane == 0 ? b : p.B)); bb < (R == 1 ? p.B : b + 1); bb += 32) {
+    const size_t pk = (static_cast<size_t>(l) * p.B + bb) * p.K;
+#pragma unroll
+    for (int k = 0; k < MAX_TOPK; ++k)
+      if (k < p.K) {
+        p.topk_idx[pk + k] = sel[k];
+        p.topk_w[pk + k] = selp[k];
+        p.sel_idx[pk + k] = srt[k];
+        p.sel_w[pk + k] = srtp[k];
       }
-      sel[j + 1] = ki;
-      selp[j + 1] = wi;
-    }
-    for (int k = 0; k < p.K; ++k) {
-      p.sel_idx[pk + k] = sel[k];
-      p.sel_w[pk + k] = selp[k];
-    }
   }
 }
 
@@ -401,35 +430,33 @@ struct Ln2Params {
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
+template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) ln2_permute_kernel(const Ln2Params p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
   const int b = row / p.T, t = row % p.T;
-  const int nvec = p.d / 128;
-  float4 xv[MAX_VEC];
+  float4 xv[NVEC];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
       const float4 x = *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.d + (i * 32 + lane) * 4);
       xv[i] = x;
       ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
+  const float rn = rms_inv_denominator(ss, p.inv_sqrt_d, p.eps);
   int dst_row[MAX_TOPK];
 #pragma unroll
   for (int k = 0; k < MAX_TOPK; ++k)
     if (k < p.K) dst_row[k] = p.pos[b * p.K + k] + t;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
       const int col = (i * 32 + lane) * 4;
       const float4 x = xv[i];
       const float4 g = *reinterpret_cast<const float4*>(p.g + col);
-      const float4 y = make_float4(__fdiv_rn(x.x, n) * g.x, __fdiv_rn(x.y, n) * g.y, __fdiv_rn(x.z, n) * g.z,
-                                   __fdiv_rn(x.w, n) * g.w);
+      const float4 y = make_float4((x.x * rn) * g.x, (x.y * rn) * g.y, (x.z * rn) * g.z,
+                                   (x.w * rn) * g.w);
       *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = y;
       const uint2 pk = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
 #pragma unroll
@@ -457,12 +484,12 @@ struct CombineParams {
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
+template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) combine_kernel(const CombineParams p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
   const int b = row / p.T, t = row % p.T;
-  const int nvec = p.d / 128;
   int src_row[MAX_TOPK];
   float wk[MAX_TOPK];
 #pragma unroll
@@ -471,11 +498,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) combine_kernel(const CombinePa
       src_row[k] = p.pos[b * p.K + k] + t;
       wk[k] = p.w[b * p.K + k];
     }
-  float4 xv[MAX_VEC];
+  float4 xv[NVEC];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
       const int col = (i * 32 + lane) * 4;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -497,15 +523,14 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) combine_kernel(const CombinePa
     }
   if (p.mode == 2) return;
   ss = warp_sum(ss);
-  const float n = rms_denominator(ss, p.inv_sqrt_d, p.eps);
+  const float rn = rms_inv_denominator(ss, p.inv_sqrt_d, p.eps);
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
       const int col = (i * 32 + lane) * 4;
       const float4 x = xv[i];
       const float4 g = *reinterpret_cast<const float4*>(p.g_next + col);
-      const float4 y = make_float4(__fdiv_rn(x.x, n) * g.x, __fdiv_rn(x.y, n) * g.y, __fdiv_rn(x.z, n) * g.z,
-                                   __fdiv_rn(x.w, n) * g.w);
+      const float4 y = make_float4((x.x * rn) * g.x, (x.y * rn) * g.y, (x.z * rn) * g.z,
+                                   (x.w * rn) * g.w);
       if (p.mode == 0) {
         const float4 c = *reinterpret_cast<const float4*>(p.cvec + static_cast<size_t>(b) * p.d + col);
         *reinterpret_cast<uint2*>(p.hA + static_cast<size_t>(row) * p.d + col) =
@@ -535,19 +560,18 @@ struct HeadParams {
   int B, T, A, action_dim, d;
   int mode;                // 0 raw F, 1 denoised D, 2 DDIM update, 3 loss (out <- F)
 };
+template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p) {
   const int item = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (item >= p.B * p.A) return;
   const int b = item / p.A, j = item % p.A;
   const int row = b * p.T + (p.T - p.A) + j;
-  const int nvec = p.d / 128;
   float acc[8];
 #pragma unroll
   for (int a = 0; a < 8; ++a) acc[a] = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
-    if (i < nvec) {
+  for (int i = 0; i < NVEC; ++i) {
       const int col = (i * 32 + lane) * 4;
       const float4 x = *reinterpret_cast<const float4*>(p.xnorm + static_cast<size_t>(row) * p.d + col);
 #pragma unroll
