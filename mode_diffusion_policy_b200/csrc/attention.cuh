@@ -26,6 +26,10 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -62,9 +66,24 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
   __nv_bfloat16* sK = sQ + TPAD * LDS;
   __nv_bfloat16* sV = sK + TPAD * LDS;
 
-  // ---- stage q, k (normalised) and v into shared memory
+  // ---- stage q, k, v into shared memory: all rows are requested up front with cp.async (no register staging, the
+  //      whole 3 x T x Dh tile is in flight at once), then q and k are RMS-normalised in place
   const int sub = lane % VPR;  // vector index inside the row
   const float inv_sqrt_dh = p.inv_sqrt_dh;
+  for (int r0 = 0; r0 < TPAD; r0 += ROWS_PER_IT) {
+    const int row = r0 + lane / VPR;
+    const __nv_bfloat16* src = p.qkv + (static_cast<size_t>(b) * T + row) * 3 * d + h * DH + sub * 8;
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      __nv_bfloat16* dst = (which == 0 ? sQ : which == 1 ? sK : sV) + row * LDS + sub * 8;
+      if (row < T)
+        cp_async_16(smem_u32(dst), src + which * d);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_wait_all();
+  __syncwarp();
   float gq[8], gk[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -73,37 +92,31 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
   }
   for (int r0 = 0; r0 < TPAD; r0 += ROWS_PER_IT) {
     const int row = r0 + lane / VPR;
-    const bool valid = row < T;
-    const __nv_bfloat16* src = p.qkv + (static_cast<size_t>(b) * T + row) * 3 * d + h * DH + sub * 8;
 #pragma unroll
-    for (int which = 0; which < 3; ++which) {
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (valid) raw = *reinterpret_cast<const uint4*>(src + which * d);
-      __nv_bfloat16* dst = (which == 0 ? sQ : which == 1 ? sK : sV) + row * LDS + sub * 8;
-      if (which < 2) {
-        float v[8];
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        float ss = 0.f;
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* ptr = (which == 0 ? sQ : sK) + row * LDS + sub * 8;
+      const uint4 raw = *reinterpret_cast<const uint4*>(ptr);
+      float v[8];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h2[j]);
-          v[2 * j] = f.x;
-          v[2 * j + 1] = f.y;
-          ss += f.x * f.x + f.y * f.y;
-        }
-#pragma unroll
-        for (int o = VPR / 2; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        // RMSNorm.forward (modedit.py:78-80): x / clamp(||x|| * dim^-0.5, eps) * g
-        const float rn = 1.0f / fmaxf(sqrtf(ss) * inv_sqrt_dh, p.eps);  // one division per row
-        const float* g = which == 0 ? gq : gk;
-        uint4 o4;
-        o4.x = pack_bf16x2((v[0] * rn) * g[0], (v[1] * rn) * g[1]);
-        o4.y = pack_bf16x2((v[2] * rn) * g[2], (v[3] * rn) * g[3]);
-        o4.z = pack_bf16x2((v[4] * rn) * g[4], (v[5] * rn) * g[5]);
-        o4.w = pack_bf16x2((v[6] * rn) * g[6], (v[7] * rn) * g[7]);
-        raw = o4;
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+        ss += f.x * f.x + f.y * f.y;
       }
-      *reinterpret_cast<uint4*>(dst) = raw;
+#pragma unroll
+      for (int o = VPR / 2; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      // RMSNorm.forward (modedit.py:78-80): x / clamp(||x|| * dim^-0.5, eps) * g   (one division per row)
+      const float rn = 1.0f / fmaxf(sqrtf(ss) * inv_sqrt_dh, p.eps);
+      const float* g = which == 0 ? gq : gk;
+      uint4 o4;
+      o4.x = pack_bf16x2((v[0] * rn) * g[0], (v[1] * rn) * g[1]);
+      o4.y = pack_bf16x2((v[2] * rn) * g[2], (v[3] * rn) * g[3]);
+      o4.z = pack_bf16x2((v[4] * rn) * g[4], (v[5] * rn) * g[5]);
+      o4.w = pack_bf16x2((v[6] * rn) * g[6], (v[7] * rn) * g[7]);
+      *reinterpret_cast<uint4*>(ptr) = o4;
     }
   }
   __syncwarp();

@@ -140,6 +140,8 @@ struct mode_engine {
   int num_sms;
   int perm_rows, max_tiles;
   float inv_sqrt_d, inv_sqrt_dh;
+  bool pair;   // CTA-pair GEMM kernel (MODE_GEMM_CTA_PAIR, default on)
+  int tile_m;  // rows per M-tile: 256 with CTA pairs, 128 otherwise
   bool finalized = false;
   std::map<std::string, WeightSpec> specs;
   std::vector<void*> allocs;
@@ -259,8 +261,18 @@ static int gemm_set_attr() {
   CU_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   return MODE_OK;
 }
+template <int EPI>
+static int gemm2_set_attr() {
+  CU_OK(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+  return MODE_OK;
+}
 static int set_kernel_attrs() {
   if (g_attr_done) return MODE_OK;
+  RET_IF(gemm2_set_attr<EPI_BIAS_BF16>());
+  RET_IF(gemm2_set_attr<EPI_RESID_F32>());
+  RET_IF(gemm2_set_attr<EPI_SWIGLU_BF16>());
+  RET_IF(gemm2_set_attr<EPI_PLAIN_BF16>());
+  RET_IF(gemm2_set_attr<EPI_PLAIN_F32>());
   RET_IF(gemm_set_attr<EPI_BIAS_BF16>());
   RET_IF(gemm_set_attr<EPI_RESID_F32>());
   RET_IF(gemm_set_attr<EPI_SWIGLU_BF16>());
@@ -270,15 +282,27 @@ static int set_kernel_attrs() {
   return MODE_OK;
 }
 
-static int launch_gemm(int epi, int num_sms, cudaStream_t st, const GemmParams& p) {
-  dim3 grid(num_sms), block(GEMM_THREADS);
-  switch (epi) {
-    case EPI_BIAS_BF16: gemm_tcgen05_kernel<EPI_BIAS_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-    case EPI_RESID_F32: gemm_tcgen05_kernel<EPI_RESID_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-    case EPI_SWIGLU_BF16: gemm_tcgen05_kernel<EPI_SWIGLU_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-    case EPI_PLAIN_BF16: gemm_tcgen05_kernel<EPI_PLAIN_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-    case EPI_PLAIN_F32: gemm_tcgen05_kernel<EPI_PLAIN_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-    default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+// pair = true: CTA-pair kernel (cta_group::2, 256-row M-tiles, cluster of 2); false: single-CTA kernel (128-row tiles)
+static int launch_gemm(int epi, bool pair, int num_sms, cudaStream_t st, const GemmParams& p) {
+  dim3 grid(pair ? (num_sms & ~1) : num_sms), block(GEMM_THREADS);
+  if (pair) {
+    switch (epi) {
+      case EPI_BIAS_BF16: gemm_tcgen05_2cta_kernel<EPI_BIAS_BF16><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
+      case EPI_RESID_F32: gemm_tcgen05_2cta_kernel<EPI_RESID_F32><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
+      case EPI_SWIGLU_BF16: gemm_tcgen05_2cta_kernel<EPI_SWIGLU_BF16><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
+      case EPI_PLAIN_BF16: gemm_tcgen05_2cta_kernel<EPI_PLAIN_BF16><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
+      case EPI_PLAIN_F32: gemm_tcgen05_2cta_kernel<EPI_PLAIN_F32><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
+      default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+    }
+  } else {
+    switch (epi) {
+      case EPI_BIAS_BF16: gemm_tcgen05_kernel<EPI_BIAS_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+      case EPI_RESID_F32: gemm_tcgen05_kernel<EPI_RESID_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+      case EPI_SWIGLU_BF16: gemm_tcgen05_kernel<EPI_SWIGLU_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+      case EPI_PLAIN_BF16: gemm_tcgen05_kernel<EPI_PLAIN_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+      case EPI_PLAIN_F32: gemm_tcgen05_kernel<EPI_PLAIN_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+      default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+    }
   }
   CU_OK(cudaGetLastError());
   return MODE_OK;
@@ -384,9 +408,14 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   e->inv_sqrt_d = static_cast<float>(pow(static_cast<double>(d), -0.5));
   e->inv_sqrt_dh = static_cast<float>(pow(static_cast<double>(Dh), -0.5));
   const int L = e->L, E = e->E, K = e->K, Hd = e->Hd, F = e->F;
-  const int maxM_pad = round_up(e->maxM, 128);
-  e->max_tiles = (K * e->maxM + 127) / 128 + E;
-  e->perm_rows = e->max_tiles * 128;
+  const int maxM_pad = round_up(e->maxM, 256);
+  {
+    const char* env = getenv("MODE_GEMM_CTA_PAIR");
+    e->pair = env ? atoi(env) != 0 : true;
+    e->tile_m = e->pair ? 256 : 128;
+  }
+  e->max_tiles = (K * e->maxM + e->tile_m - 1) / e->tile_m + E;
+  e->perm_rows = e->max_tiles * e->tile_m;
   int rc = MODE_OK;
 #define A_(call) do { if (rc == MODE_OK) rc = (call); } while (0)
   A_(dev_alloc(e, &e->w_qkv, (size_t)L * 3 * d * d));
@@ -422,7 +451,7 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   if ((size_t)d * e->gdim > e->stage_elems) e->stage_elems = (size_t)d * e->gdim;
   A_(dev_alloc(e, &e->stage, e->stage_elems, false));
   // workspace
-  const int st_rows = round_up(e->maxB * e->S, 128), goal_rows = round_up(e->maxB, 128);
+  const int st_rows = round_up(e->maxB * e->S, 256), goal_rows = round_up(e->maxB, 256);
   A_(dev_alloc(e, &e->x, (size_t)maxM_pad * d));
   A_(dev_alloc(e, &e->cvec, (size_t)e->maxB * d));
   A_(dev_alloc(e, &e->xnorm, (size_t)maxM_pad * d));
@@ -454,7 +483,7 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(dev_alloc(e, &e->up_tiles, (size_t)L * e->max_tiles));
   A_(dev_alloc(e, &e->down_tiles, (size_t)L * e->max_tiles));
   A_(dev_alloc(e, &e->num_tiles, (size_t)L));
-  e->dense_cap = maxM_pad / 128;
+  e->dense_cap = maxM_pad / 128;  // enough for either tile size
   A_(dev_alloc(e, &e->dense_tiles, (size_t)3 * e->dense_cap));
   A_(dev_alloc(e, &e->dense_counts, 3));
   A_(dev_alloc(e, &e->usage, (size_t)L * E));
@@ -466,12 +495,12 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(make_tmap(&e->tm_h, e->hbuf, e->perm_rows, F, 128));
   A_(make_tmap(&e->tm_st, e->st_bf16, st_rows, e->obs, 128));
   A_(make_tmap(&e->tm_goal, e->goal_bf16, goal_rows, e->gdim, 128));
-  A_(make_tmap(&e->tm_wqkv, e->w_qkv, (uint64_t)L * 3 * d, d, 256));
-  A_(make_tmap(&e->tm_wproj, e->w_proj, (uint64_t)L * d, d, 256));
-  A_(make_tmap(&e->tm_wup, e->w_up, (uint64_t)L * E * 8 * d, d, 256));
-  A_(make_tmap(&e->tm_wdown, e->w_down, (uint64_t)L * E * d, F, 256));
-  A_(make_tmap(&e->tm_wtok, e->w_tok, d, e->obs, 256));
-  A_(make_tmap(&e->tm_wgoal, e->w_goal, d, e->gdim, 256));
+  A_(make_tmap(&e->tm_wqkv, e->w_qkv, (uint64_t)L * 3 * d, d, e->pair ? 128 : 256));
+  A_(make_tmap(&e->tm_wproj, e->w_proj, (uint64_t)L * d, d, e->pair ? 128 : 256));
+  A_(make_tmap(&e->tm_wup, e->w_up, (uint64_t)L * E * 8 * d, d, e->pair ? 128 : 256));
+  A_(make_tmap(&e->tm_wdown, e->w_down, (uint64_t)L * E * d, F, e->pair ? 128 : 256));
+  A_(make_tmap(&e->tm_wtok, e->w_tok, d, e->obs, e->pair ? 128 : 256));
+  A_(make_tmap(&e->tm_wgoal, e->w_goal, d, e->gdim, e->pair ? 128 : 256));
   A_(make_out_tmap(&e->to_h, e->hbuf, e->perm_rows, F, 2));
   A_(make_out_tmap(&e->to_y, e->ybuf, e->perm_rows, d, 2));
   if (rc == MODE_OK && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -575,13 +604,14 @@ static int ensure_batch(mode_engine* e, int B) {
   int counts[3];
   const int rows[3] = {B * e->T, B * e->S, B};
   for (int k = 0; k < 3; ++k) {
-    const int n = (rows[k] + 127) / 128;
+    const int tm = e->tile_m;
+    const int n = (rows[k] + tm - 1) / tm;
     counts[k] = n;
     for (int i = 0; i < n; ++i) {
       GemmMTile t;
-      t.a_row0 = i * 128;
-      t.out_row0 = i * 128;
-      t.rows_valid = rows[k] - i * 128 < 128 ? rows[k] - i * 128 : 128;
+      t.a_row0 = i * tm;
+      t.out_row0 = i * tm;
+      t.rows_valid = rows[k] - i * tm < tm ? rows[k] - i * tm : tm;
       t.w_row_base = 0;
       tiles[(size_t)k * e->dense_cap + i] = t;
     }
@@ -643,10 +673,10 @@ static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* sta
   CU_OK(cudaGetLastError());
   GemmParams p = gemm_params(e->tm_st, e->tm_wtok, e->to_state, e->dense_tiles + e->dense_cap, e->dense_counts + 1,
                              e->d, e->obs, nullptr);
-  RET_IF(launch_gemm(EPI_PLAIN_F32, e->num_sms, st, p));
+  RET_IF(launch_gemm(EPI_PLAIN_F32, e->pair, e->num_sms, st, p));
   p = gemm_params(e->tm_goal, e->tm_wgoal, e->to_goal, e->dense_tiles + 2 * e->dense_cap, e->dense_counts + 2, e->d,
                   e->gdim, nullptr);
-  RET_IF(launch_gemm(EPI_PLAIN_F32, e->num_sms, st, p));
+  RET_IF(launch_gemm(EPI_PLAIN_F32, e->pair, e->num_sms, st, p));
   e->launch_count += 4;
   return MODE_OK;
 }
@@ -667,7 +697,7 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   pl.sel_idx = e->sel_idx; pl.pos = e->pos_tab; pl.up_tiles = e->up_tiles; pl.down_tiles = e->down_tiles;
   pl.num_tiles = e->num_tiles; pl.usage = e->usage; pl.tokens = e->tokens;
   pl.L = e->L; pl.B = B; pl.K = e->K; pl.E = e->E; pl.T = e->T; pl.max_tiles = e->max_tiles;
-  pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0;
+  pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0; pl.tile_m = e->tile_m;
   plan_kernel<<<n_layers, 256, 0, st>>>(pl);
   CU_OK(cudaGetLastError());
   e->launch_count += 2;
@@ -681,7 +711,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   p.w_row_off = l * 3 * d;
   {
     ProfScope ps(e, st, PC_QKV);
-    RET_IF(launch_gemm(EPI_BIAS_BF16, e->num_sms, st, p));
+    RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
   }
   AttnParams a;
   a.qkv = e->qkv; a.out = e->attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
@@ -694,7 +724,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   p.w_row_off = l * d;
   {
     ProfScope ps(e, st, PC_PROJ);
-    RET_IF(launch_gemm(EPI_RESID_F32, e->num_sms, st, p));
+    RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
   Ln2Params n2;
   n2.x = e->x; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + (size_t)l * B * e->K; n2.perm = e->perm;
@@ -708,13 +738,13 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
                   e->b_up);
   {
     ProfScope ps(e, st, PC_UP);
-    RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->num_sms, st, p));
+    RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
   }
   p = gemm_params(e->tm_h, e->tm_wdown, e->to_y, e->down_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, d, e->F,
                   nullptr);
   {
     ProfScope ps(e, st, PC_DOWN);
-    RET_IF(launch_gemm(EPI_PLAIN_BF16, e->num_sms, st, p));
+    RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, p));
   }
   CombineParams c;
   c.x = e->x; c.y = e->ybuf; c.pos = e->pos_tab + (size_t)l * B * e->K; c.w = e->sel_w + (size_t)l * B * e->K;
@@ -980,6 +1010,9 @@ extern "C" int64_t mode_last_launch_count(const mode_engine_t* e) { return e ? e
 extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                                void* out_dev, int M, int N, int Kdim, int epilogue, void* stream) {
   if (!a_dev || !w_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
+  const bool pair = (epilogue & 0x100) != 0;  // bit 8 selects the CTA-pair kernel
+  epilogue &= 0xff;
+  const int tm = pair ? 256 : 128;
   if (M < 1 || N % 256 || Kdim % 64 || N < 256 || Kdim < 64) return fail(MODE_ERR_INVALID, "need N %% 256 == 0 and K %% 64 == 0");
   RET_IF(set_kernel_attrs());
   int dev = 0;
@@ -987,9 +1020,9 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
   int sms = 0;
   CU_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int n = (M + 127) / 128;
+  const int n = (M + tm - 1) / tm;
   std::vector<GemmMTile> tiles(n);
-  for (int i = 0; i < n; ++i) tiles[i] = GemmMTile{i * 128, i * 128, M - i * 128 < 128 ? M - i * 128 : 128, 0};
+  for (int i = 0; i < n; ++i) tiles[i] = GemmMTile{i * tm, i * tm, M - i * tm < tm ? M - i * tm : tm, 0};
   GemmMTile* d_tiles = nullptr;
   int* d_n = nullptr;
   RET_IF(dev_alloc<GemmMTile>(nullptr, &d_tiles, n, false));
@@ -997,9 +1030,9 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
   CU_OK(cudaMemcpy(d_tiles, tiles.data(), n * sizeof(GemmMTile), cudaMemcpyHostToDevice));
   CU_OK(cudaMemcpy(d_n, &n, sizeof(int), cudaMemcpyHostToDevice));
   CUtensorMap ta, tw;
-  // The caller allocates A with round_up(M, 128) rows so the TMA box never exceeds the tensor extent.
-  RET_IF(make_tmap(&ta, a_dev, round_up(M, 128), Kdim, 128));
-  RET_IF(make_tmap(&tw, w_dev, N, Kdim, 256));
+  // The caller allocates A with round_up(M, 256) rows so the TMA box never exceeds the tensor extent.
+  RET_IF(make_tmap(&ta, a_dev, round_up(M, 256), Kdim, 128));
+  RET_IF(make_tmap(&tw, w_dev, N, Kdim, pair ? 128 : 256));
   const int n_out = (epilogue == EPI_SWIGLU_BF16) ? N / 2 : N;
   const int out_bytes = (epilogue == EPI_RESID_F32 || epilogue == EPI_PLAIN_F32) ? 4 : 2;
   CUtensorMap tout;
@@ -1009,7 +1042,7 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
     CU_OK(cudaMemcpyAsync(out_dev, resid_dev, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   GemmParams p = gemm_params(ta, tw, tout, d_tiles, d_n, N, Kdim, bias_dev);
-  int rc = launch_gemm(epilogue, sms, st, p);
+  int rc = launch_gemm(epilogue, pair, sms, st, p);
   // MODE_GEMM_BENCH_REPS=n: time n further back-to-back launches with CUDA events and print the average
   if (rc == MODE_OK && getenv("MODE_GEMM_BENCH_REPS")) {
     const int reps = atoi(getenv("MODE_GEMM_BENCH_REPS"));
@@ -1017,13 +1050,13 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
-    for (int i = 0; i < reps && rc == MODE_OK; ++i) rc = launch_gemm(epilogue, sms, st, p);
+    for (int i = 0; i < reps && rc == MODE_OK; ++i) rc = launch_gemm(epilogue, pair, sms, st, p);
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     const double flops = 2.0 * M * (double)N * Kdim;
-    printf("mode_debug_gemm M=%d N=%d K=%d epi=%d: %.3f us/launch, %.1f TFLOP/s\n", M, N, Kdim, epilogue,
+    printf("mode_debug_gemm%s M=%d N=%d K=%d epi=%d: %.3f us/launch, %.1f TFLOP/s\n", pair ? "[pair]" : "", M, N, Kdim, epilogue,
            1e3 * ms / reps, flops * reps / (ms * 1e-3) / 1e12);
     fflush(stdout);
     cudaEventDestroy(e0);

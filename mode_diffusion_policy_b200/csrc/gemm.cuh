@@ -302,4 +302,158 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster compute one 256 x 256 tile. Each CTA loads its own
+// 128 A rows and HALF of the weight tile (128 of the 256 N rows); the tensor core reads both halves, so the L2->SM
+// traffic per MMA drops from 48 KB to 32 KB per k-block and six stages fit in shared memory. The leader CTA (rank 0)
+// issues the MMAs for the pair; both CTAs run a TMA producer and an epilogue over their own 128 accumulator rows.
+// M-tiles in the table are 256 rows here.
+constexpr int G2_STAGES = 6;
+constexpr int G2_HALF_N = GEMM_BLOCK_N / 2;
+constexpr int G2_B_BYTES = G2_HALF_N * GEMM_BLOCK_K * 2;       // 16 KB
+constexpr int G2_STAGE_BYTES = GEMM_A_BYTES + G2_B_BYTES;      // 32 KB
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + GEMM_EPI_BYTES + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * G2_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * G2_STAGES + 2 + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
+  const uint32_t epi_smem = smem_base + G2_STAGES * G2_STAGE_BYTES + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    tma_prefetch_desc(&p.tmap_w);
+    tma_prefetch_desc(&p.tmap_out);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(full_bar(s), 2);   // leader's: one arrival per CTA's producer (+ both CTAs' TMA bytes)
+      mbar_init(empty_bar(s), 1);  // each CTA's own: the pair's MMA commit is multicast to both
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);     // each CTA's own (multicast commit)
+      mbar_init(tempty_bar(s), 256);  // leader's: all 2 x 128 epilogue threads of the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(smem_u32(tmem_ptr_smem), GEMM_TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n_m = *p.num_m_tiles;
+  const int total = n_m * p.n_blocks;
+  const int k_blocks = p.k_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        const int mt = t % n_m, nb = t / n_m;
+        const GemmMTile tile = p.m_tiles[mt];
+        const int a_row = tile.a_row0 + static_cast<int>(rank) * GEMM_BLOCK_M;
+        const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N + static_cast<int>(rank) * G2_HALF_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * G2_STAGE_BYTES;
+          const uint32_t b_dst = a_dst + GEMM_A_BYTES;
+          const uint32_t leader_full = mapa_cluster(full_bar(stage), 0);
+          if (rank == 0)
+            mbar_arrive_expect_tx(full_bar(stage), 2 * G2_STAGE_BYTES);
+          else
+            mbar_arrive_cluster(leader_full);
+          tma_load_2d_2sm(a_dst, &p.tmap_a, leader_full, kb * GEMM_BLOCK_K, a_row);
+          tma_load_2d_2sm(b_dst, &p.tmap_w, leader_full, kb * GEMM_BLOCK_K, w_row);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, GEMM_BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = pair; t < total; t += n_pairs, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * GEMM_BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * G2_STAGE_BYTES;
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + GEMM_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
+            umma_bf16_2cta(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+          umma_commit_2cta(empty_bar(stage), 0b11);  // frees the stage in BOTH CTAs
+          if (kb == k_blocks - 1) umma_commit_2cta(tfull_bar(as), 0b11);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    const uint32_t stage_smem = epi_smem + static_cast<uint32_t>(q) * 2 * GEMM_EPI_BUF_BYTES;
+    uint32_t n_stores = 0;
+    int iter = 0;
+    for (int t = pair; t < total; t += n_pairs, ++iter) {
+      const int mt = t % n_m, nb = t / n_m;
+      const GemmMTile tile = p.m_tiles[mt];
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row0 = static_cast<int>(rank) * GEMM_BLOCK_M + q * 32;  // first row of this warp inside the 256-row tile
+      if (row0 < tile.rows_valid) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
+        const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N;
+        gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, w_row, nb, n_stores);
+      }
+      tc_fence_before();
+      if (rank == 0)
+        mbar_arrive(tempty_bar(as));
+      else
+        mbar_arrive_cluster(mapa_cluster(tempty_bar(as), 0));
+    }
+    if (lane == 0) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be arriving on the leader's barriers / reading its smem via the MMA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, GEMM_TMEM_COLS);
+  }
+}
+
 }  // namespace mode

@@ -73,14 +73,14 @@ struct EmbedParams {
 };
 
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedParams p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
   const int b = row / p.T, t = row % p.T;
   const float sigma = load_sigma(p.sc, b);
   const float s = logf(sigma) / 4.0f;  // process_sigma_embeddings, modedit.py:824
-  float4 xv[NVEC], cv[NVEC];
+  float4 xv[NVEC];
   float ss = 0.f;
   float act[8];
   const int n_act = p.action_dim;
@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams
       const float4 u = *reinterpret_cast<const float4*>(p.sig_u + col);
       const float4 v = *reinterpret_cast<const float4*>(p.sig_v + col);
       const float4 c = make_float4(fmaf(s, u.x, v.x), fmaf(s, u.y, v.y), fmaf(s, u.z, v.z), fmaf(s, u.w, v.w));
-      cv[i] = c;
       float4 x;
       if (t == 0) {
         x = c;
@@ -130,7 +129,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) embed_kernel(const EmbedParams
   for (int i = 0; i < NVEC; ++i) {
     {
       const int col = (i * 32 + lane) * 4;
-      const float4 x = xv[i], c = cv[i];
+      const float4 x = xv[i];
+      const float4 u = *reinterpret_cast<const float4*>(p.sig_u + col);
+      const float4 v = *reinterpret_cast<const float4*>(p.sig_v + col);
+      const float4 c = make_float4(fmaf(s, u.x, v.x), fmaf(s, u.y, v.y), fmaf(s, u.z, v.z), fmaf(s, u.w, v.w));
       const float4 g = *reinterpret_cast<const float4*>(p.ln1_g + col);
       *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = x;
       if (t == 0) *reinterpret_cast<float4*>(p.cvec + static_cast<size_t>(b) * p.d + col) = c;
@@ -154,7 +156,7 @@ struct Ln1Params {
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32) ln1_kernel(const Ln1Params p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln1_kernel(const Ln1Params p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.rows) return;
@@ -347,6 +349,7 @@ struct PlanParams {
   int up_rows_per_expert;        // 8d  (packed SwiGLU rows)
   int down_rows_per_expert;      // d
   int layer0;                    // first layer handled by blockIdx.x == 0 (block-level entry plans a single layer)
+  int tile_m;                    // rows per GEMM M-tile (128 single-CTA, 256 CTA-pair): groups are padded to it
 };
 
 __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
@@ -388,8 +391,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
     for (int e = 0; e < p.E; ++e) {
       grp_row0[e] = row;
       grp_tile0[e] = tile;
-      const int nt = (cnt[e] * p.T + 127) / 128;
-      row += nt * 128;
+      const int nt = (cnt[e] * p.T + p.tile_m - 1) / p.tile_m;
+      row += nt * p.tile_m;
       tile += nt;
     }
     grp_tile0[p.E] = tile;
@@ -406,9 +409,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
     const int rows = cnt[e] * p.T;
     for (int i = tid; i < nt; i += 256) {
       GemmMTile t;
-      t.a_row0 = grp_row0[e] + i * 128;
+      t.a_row0 = grp_row0[e] + i * p.tile_m;
       t.out_row0 = t.a_row0;
-      t.rows_valid = min(128, rows - i * 128);
+      t.rows_valid = min(p.tile_m, rows - i * p.tile_m);
       t.w_row_base = (l * p.E + e) * p.up_rows_per_expert;
       p.up_tiles[static_cast<size_t>(l) * p.max_tiles + grp_tile0[e] + i] = t;
       t.w_row_base = (l * p.E + e) * p.down_rows_per_expert;
@@ -431,7 +434,7 @@ struct Ln2Params {
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32) ln2_permute_kernel(const Ln2Params p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln2Params p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
@@ -485,7 +488,7 @@ struct CombineParams {
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32) combine_kernel(const CombineParams p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const CombineParams p) {
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;

@@ -10,3 +10,4 @@ from test_kernels_gpu import run_gemm  # noqa: E402
 for (M, N, K, epi) in [(3584, 3072, 1024, 0), (3584, 1024, 1024, 1), (3584, 16384, 1024, 2), (7168, 1024, 4096, 3),
                        (1792, 3072, 1024, 0), (1792, 16384, 1024, 2), (8192, 8192, 8192, 3)]:
     run_gemm(M, N, K, epi)
+    run_gemm(M, N, K, epi, pair=True)

@@ -20,10 +20,10 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_gemm(M, N, K, epi, seed=0):
+def run_gemm(M, N, K, epi, seed=0, pair=False):
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
-    Mp = (M + 127) // 128 * 128
+    Mp = (M + 255) // 256 * 256
     A = torch.zeros(Mp, K, dtype=torch.bfloat16)
     A[:M] = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
     W = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
@@ -48,7 +48,7 @@ def run_gemm(M, N, K, epi, seed=0):
     else:
         out = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
         want = ref
-    _lib.check(lib.mode_debug_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(out), M, N, K, epi, _stream()))
+    _lib.check(lib.mode_debug_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(out), M, N, K, epi | (0x100 if pair else 0), _stream()))
     torch.cuda.synchronize()
     return out.float(), want
 
@@ -57,8 +57,9 @@ def run_gemm(M, N, K, epi, seed=0):
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 1024), (448, 1024, 1024),
                                    (100, 256, 512), (3584, 1024, 4096), (1000, 3072, 1024),
                                    (3584, 3072, 1024), (5000, 2048, 512)])
-def test_gemm_matches_fp32_reference(M, N, K, epi):
-    got, want = run_gemm(M, N, K, epi)
+@pytest.mark.parametrize("pair", [False, True], ids=["cta1", "cta2"])
+def test_gemm_matches_fp32_reference(M, N, K, epi, pair):
+    got, want = run_gemm(M, N, K, epi, pair=pair)
     assert torch.isfinite(got).all()
     err = (got - want).abs()
     scale = want.abs().max().item() + 1e-6
