@@ -168,6 +168,8 @@ struct mode_engine {
 
   CUtensorMap tm_hA, tm_attn, tm_perm, tm_h, tm_st, tm_goal;
   CUtensorMap tm_wqkv, tm_wproj, tm_wup, tm_wdown, tm_wtok, tm_wgoal;
+  float4* sk_partials;  // stream-K workspace: 128 KB per CTA of the GEMM grid
+  int* sk_flags;
   CUtensorMap to_h, to_y;                          // grouped outputs (padded rows, fixed extent)
   CUtensorMap to_qkv, to_x, to_state, to_goal;     // dense outputs: extent = exact rows of the current batch
 
@@ -486,6 +488,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   e->dense_cap = maxM_pad / 128;  // enough for either tile size
   A_(dev_alloc(e, &e->dense_tiles, (size_t)3 * e->dense_cap));
   A_(dev_alloc(e, &e->dense_counts, 3));
+  A_(dev_alloc(e, &e->sk_partials, (size_t)e->num_sms * 8 * 8 * 128, false));
+  A_(dev_alloc(e, &e->sk_flags, (size_t)e->num_sms * 4));
   A_(dev_alloc(e, &e->usage, (size_t)L * E));
   A_(dev_alloc(e, &e->tokens, (size_t)L));
   // tensor maps
@@ -643,7 +647,18 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.k_blocks = Kdim / GEMM_BLOCK_K;
   p.bias = bias;
   p.w_row_off = 0;
+  p.sk_enable = 0;
+  p.sk_partials = nullptr;
+  p.sk_flags = nullptr;
   return p;
+}
+// stream-K over the last partial wave pays when the GEMM has more than one wave of tiles (QKV, expert up/down)
+static void enable_stream_k(mode_engine* e, GemmParams& p) {
+  static const bool off = getenv("MODE_GEMM_STREAM_K") && atoi(getenv("MODE_GEMM_STREAM_K")) == 0;
+  if (!e->pair || off) return;
+  p.sk_enable = 1;
+  p.sk_partials = e->sk_partials;
+  p.sk_flags = e->sk_flags;
 }
 
 // embed_dim is a multiple of 256 -> d/128 float4 vectors per lane, compile-time for register-resident rows
@@ -709,6 +724,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   const int d = e->d, M = B * e->T;
   GemmParams p = gemm_params(e->tm_hA, e->tm_wqkv, e->to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
+  enable_stream_k(e, p);
   {
     ProfScope ps(e, st, PC_QKV);
     RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
@@ -736,12 +752,14 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   CU_OK(cudaGetLastError());
   p = gemm_params(e->tm_perm, e->tm_wup, e->to_h, e->up_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, 8 * d, d,
                   e->b_up);
+  enable_stream_k(e, p);
   {
     ProfScope ps(e, st, PC_UP);
     RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
   }
   p = gemm_params(e->tm_h, e->tm_wdown, e->to_y, e->down_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, d, e->F,
                   nullptr);
+  enable_stream_k(e, p);
   {
     ProfScope ps(e, st, PC_DOWN);
     RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, p));
@@ -1010,7 +1028,8 @@ extern "C" int64_t mode_last_launch_count(const mode_engine_t* e) { return e ? e
 extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                                void* out_dev, int M, int N, int Kdim, int epilogue, void* stream) {
   if (!a_dev || !w_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
-  const bool pair = (epilogue & 0x100) != 0;  // bit 8 selects the CTA-pair kernel
+  const bool pair = (epilogue & 0x100) != 0;      // bit 8 selects the CTA-pair kernel
+  const bool stream_k = (epilogue & 0x200) != 0;  // bit 9 enables stream-K on the last partial wave (pair kernel)
   epilogue &= 0xff;
   const int tm = pair ? 256 : 128;
   if (M < 1 || N % 256 || Kdim % 64 || N < 256 || Kdim < 64) return fail(MODE_ERR_INVALID, "need N %% 256 == 0 and K %% 64 == 0");
@@ -1042,6 +1061,17 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
     CU_OK(cudaMemcpyAsync(out_dev, resid_dev, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   GemmParams p = gemm_params(ta, tw, tout, d_tiles, d_n, N, Kdim, bias_dev);
+  static float4* dbg_parts = nullptr;
+  static int* dbg_flags = nullptr;
+  if (pair && stream_k) {
+    if (!dbg_parts) {
+      RET_IF(dev_alloc<float4>(nullptr, &dbg_parts, (size_t)sms * 8 * 8 * 128, false));
+      RET_IF(dev_alloc<int>(nullptr, &dbg_flags, (size_t)sms * 4, true));
+    }
+    p.sk_enable = 1;
+    p.sk_partials = dbg_parts;
+    p.sk_flags = dbg_flags;
+  }
   int rc = launch_gemm(epilogue, pair, sms, st, p);
   // MODE_GEMM_BENCH_REPS=n: time n further back-to-back launches with CUDA events and print the average
   if (rc == MODE_OK && getenv("MODE_GEMM_BENCH_REPS")) {
@@ -1056,7 +1086,7 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     const double flops = 2.0 * M * (double)N * Kdim;
-    printf("mode_debug_gemm%s M=%d N=%d K=%d epi=%d: %.3f us/launch, %.1f TFLOP/s\n", pair ? "[pair]" : "", M, N, Kdim, epilogue,
+    printf("mode_debug_gemm%s%s M=%d N=%d K=%d epi=%d: %.3f us/launch, %.1f TFLOP/s\n", pair ? "[pair]" : "", (pair && stream_k) ? "[sk]" : "", M, N, Kdim, epilogue,
            1e3 * ms / reps, flops * reps / (ms * 1e-3) / 1e12);
     fflush(stdout);
     cudaEventDestroy(e0);

@@ -56,6 +56,58 @@ struct alignas(64) GemmParams {
   CUtensorMap tmap_out;        // output [rows, N_out] bf16 (box {64, 32}) or f32 (box {32, 32}), SWIZZLE_128B
   const float* bias;           // indexed by weight row (packed like the weights), may be null
   int w_row_off;               // added to every tile's w_row_base (layer offset of dense projections)
+  // stream-K over the last, partial wave of tiles (CTA-pair kernel only; see SkIter)
+  int sk_enable;
+  float4* sk_partials;         // [grid CTAs][8 chunks][8 vec][128 rows] fp32 partial accumulators (128 KB per CTA)
+  int* sk_flags;               // [grid CTAs][4 epilogue warps], 0 between kernels
+};
+
+// Work decomposition of the CTA-pair kernel. Tiles of full waves are data-parallel (tile = worker + i * P). The last,
+// partial wave (R = T mod P tiles) is processed stream-K style: its R * KB k-block units are divided evenly over the
+// workers, so a tile may be produced by several workers. The worker that owns a tile's first k-block finishes the
+// tile (it adds the other workers' fp32 partial accumulators before the normal epilogue); it handles that segment LAST
+// while the contributors handle theirs FIRST in the stream-K phase, so waits are short and cannot deadlock.
+struct SkIter {
+  int w, P, T, KB, T_dp, P_sk, units;  // worker, workers, tiles, k-blocks/tile, data-parallel tiles, sk workers, sk units
+  int i_dp, u, u_end;
+  __device__ SkIter(int worker, int workers, int tiles, int kblocks, int sk_enable) {
+    w = worker; P = workers; T = tiles; KB = kblocks;
+    const int R = T % P;
+    // stream-K only when there is at least one full wave before the remainder (otherwise plain data-parallel)
+    const bool sk = sk_enable && R > 0 && T > P;
+    T_dp = sk ? T - R : T;
+    P_sk = sk ? min(P, R * 4) : 0;  // at most 4 contributors per tile
+    units = sk ? R * KB : 0;
+    i_dp = 0;
+    u = (sk && w < P_sk) ? static_cast<int>(static_cast<long long>(w) * units / P_sk) : 0;
+    u_end = (sk && w < P_sk) ? static_cast<int>(static_cast<long long>(w + 1) * units / P_sk) : 0;
+  }
+  __device__ int sk_begin(int worker) const { return static_cast<int>(static_cast<long long>(worker) * units / P_sk); }
+  // next segment: tile index, k-block range [kb0, kb1)
+  __device__ bool next(int& tile, int& kb0, int& kb1) {
+    const int t = w + i_dp * P;
+    if (t < T_dp) {
+      ++i_dp;
+      tile = t; kb0 = 0; kb1 = KB;
+      return true;
+    }
+    if (u < u_end) {
+      const int tt = u / KB;
+      kb0 = u - tt * KB;
+      kb1 = min(KB, kb0 + (u_end - u));
+      tile = T_dp + tt;
+      u += kb1 - kb0;
+      return true;
+    }
+    return false;
+  }
+  // workers after `w` that hold a part of stream-K tile `tile` (only meaningful for a segment with kb0 == 0 < kb1 < KB)
+  __device__ int contributors(int tile) const {
+    const int tile_end = (tile - T_dp + 1) * KB;
+    int n = 0;
+    while (w + 1 + n < P_sk && sk_begin(w + 1 + n) < tile_end) ++n;
+    return n;
+  }
 };
 
 __device__ __forceinline__ float silu_f(float g) { return __fdividef(g, 1.0f + __expf(-g)); }
@@ -65,9 +117,61 @@ __device__ __forceinline__ float silu_f(float g) { return __fdividef(g, 1.0f + _
 // pattern (16-byte chunk j of row r lives at chunk j ^ (r & 7): conflict-free v4 stores) -> ONE bulk tensor store
 // (or reduce-add) per chunk issued by lane 0, double-buffered with bulk async-groups. Global writes are therefore
 // full 128-byte rows instead of 32 scattered 16-byte pieces per instruction.
+// Partial accumulators in global memory: chunk c (32 columns), vector j (4 columns), row r -> float4 index
+// (c*8 + j)*128 + r: consecutive lanes (rows) touch consecutive 16-byte words, i.e. fully coalesced both ways.
+struct SkParts {
+  const float4* base;  // first contributor's slot, this CTA rank (contributors are 2 CTA slots apart)
+  int n;               // number of contributors (0: plain tile)
+  int row;             // row of this lane inside the CTA's 128-row half
+};
+__device__ __forceinline__ void load_acc32(uint32_t taddr_col, uint32_t (&r)[32], const SkParts& sk, int chunk) {
+  tmem_ld_32x32(taddr_col, r);
+  tmem_ld_wait();
+  for (int i = 0; i < sk.n; ++i) {
+    const float4* src = sk.base + static_cast<size_t>(i) * 2 * (8 * 8 * 128) + (chunk * 8) * 128 + sk.row;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 v = __ldcg(src + j * 128);
+      r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + v.x);
+      r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+      r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+      r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+    }
+  }
+}
+// A contributor's segment: dump this warp's 32 x 256 fp32 accumulator rows to its slot and publish them.
+__device__ __forceinline__ void store_partial_warp(uint32_t taddr, float4* slot, int* flag, int row, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      __stcg(slot + (c * 8 + j) * 128 + row,
+             make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                         __uint_as_float(r[4 * j + 3])));
+  }
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(flag, 1);
+}
+__device__ __forceinline__ void wait_flag(const int* flag) {
+  uint32_t spins = 0;
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (!v && ++spins > MODE_SPIN_LIMIT) {
+      printf("mode: stream-K partial wait timed out (block %d)\n", blockIdx.x);
+      __trap();
+    }
+  } while (!v);
+}
+
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t taddr, uint32_t stage_smem, int lane,
-                                                   int out_row0, int w_row, int nb, uint32_t& n_stores) {
+                                                   int out_row0, int w_row, int nb, uint32_t& n_stores,
+                                                   const SkParts sk = SkParts{nullptr, 0, 0}) {
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
   auto chunk_addr = [&](uint32_t buf, uint32_t j) { return buf + row_off + ((j ^ sw) << 4); };
@@ -98,9 +202,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t
       for (int hh = 0; hh < 2; ++hh) {
         const int c32 = c * 64 + hh * 32;
         uint32_t rp[32], rg[32];
-        tmem_ld_32x32(taddr + c32, rp);
-        tmem_ld_32x32(taddr + 128 + c32, rg);
-        tmem_ld_wait();
+        load_acc32(taddr + c32, rp, sk, c32 / 32);
+        load_acc32(taddr + 128 + c32, rg, sk, (128 + c32) / 32);
         const float4* bp = reinterpret_cast<const float4*>(p.bias + w_row + c32);
         const float4* bg = reinterpret_cast<const float4*>(p.bias + w_row + 128 + c32);
 #pragma unroll
@@ -130,8 +233,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t
       for (int hh = 0; hh < 2; ++hh) {
         const int c32 = c * 64 + hh * 32;
         uint32_t r[32];
-        tmem_ld_32x32(taddr + c32, r);
-        tmem_ld_wait();
+        load_acc32(taddr + c32, r, sk, c32 / 32);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t pk[4];
@@ -157,8 +259,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t
     for (int c = 0; c < 8; ++c) {
       const uint32_t buf = begin_chunk();
       uint32_t r[32];
-      tmem_ld_32x32(taddr + c * 32, r);
-      tmem_ld_wait();
+      load_acc32(taddr + c * 32, r, sk, c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) st_shared_v4(chunk_addr(buf, j), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
       end_chunk(buf, nb * GEMM_BLOCK_N + c * 32);
@@ -366,12 +467,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       // ===================== TMA producer (both CTAs) =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < total; t += n_pairs) {
+      SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable);
+      int t, kb0, kb1;
+      while (it.next(t, kb0, kb1)) {
         const int mt = t % n_m, nb = t / n_m;
         const GemmMTile tile = p.m_tiles[mt];
         const int a_row = tile.a_row0 + static_cast<int>(rank) * GEMM_BLOCK_M;
         const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N + static_cast<int>(rank) * G2_HALF_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * G2_STAGE_BYTES;
           const uint32_t b_dst = a_dst + GEMM_A_BYTES;
@@ -396,13 +499,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int t = pair; t < total; t += n_pairs, ++iter) {
+      SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable);
+      int t, kb0, kb1;
+      for (; it.next(t, kb0, kb1); ++iter) {
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * GEMM_BLOCK_N;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * G2_STAGE_BYTES;
@@ -410,9 +515,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + GEMM_A_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
-            umma_bf16_2cta(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+            umma_bf16_2cta(tmem_d, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit_2cta(empty_bar(stage), 0b11);  // frees the stage in BOTH CTAs
-          if (kb == k_blocks - 1) umma_commit_2cta(tfull_bar(as), 0b11);
+          if (kb == kb1 - 1) umma_commit_2cta(tfull_bar(as), 0b11);
           if (++stage == G2_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -426,7 +531,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     const uint32_t stage_smem = epi_smem + static_cast<uint32_t>(q) * 2 * GEMM_EPI_BUF_BYTES;
     uint32_t n_stores = 0;
     int iter = 0;
-    for (int t = pair; t < total; t += n_pairs, ++iter) {
+    SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable);
+    int t, kb0, kb1;
+    constexpr size_t kSlot = 8 * 8 * 128;  // float4 per CTA slot
+    for (; it.next(t, kb0, kb1); ++iter) {
       const int mt = t % n_m, nb = t / n_m;
       const GemmMTile tile = p.m_tiles[mt];
       const int as = iter & 1;
@@ -437,7 +545,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       if (row0 < tile.rows_valid) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
         const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N;
-        gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, w_row, nb, n_stores);
+        if (kb0 != 0) {
+          // contributor: publish the partial accumulator of this segment in this CTA's slot
+          store_partial_warp(taddr, p.sk_partials + static_cast<size_t>(blockIdx.x) * kSlot, p.sk_flags + blockIdx.x * 4 + q,
+                             q * 32 + lane, lane);
+        } else {
+          SkParts sk{nullptr, 0, q * 32 + lane};
+          if (kb1 != k_blocks) {  // finisher of a split tile: collect the contributors' partials first
+            sk.n = it.contributors(t);
+            const int first = 2 * (pair + 1) + static_cast<int>(rank);
+            sk.base = p.sk_partials + static_cast<size_t>(first) * kSlot;
+            for (int i = 0; i < sk.n; ++i) wait_flag(p.sk_flags + (first + 2 * i) * 4 + q);
+          }
+          gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, w_row, nb, n_stores, sk);
+          if (sk.n > 0) {
+            __syncwarp();
+            if (lane == 0)
+              for (int i = 0; i < sk.n; ++i) p.sk_flags[(2 * (pair + 1 + i) + static_cast<int>(rank)) * 4 + q] = 0;
+          }
+        }
       }
       tc_fence_before();
       if (rank == 0)

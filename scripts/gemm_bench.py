@@ -11,3 +11,4 @@ for (M, N, K, epi) in [(3584, 3072, 1024, 0), (3584, 1024, 1024, 1), (3584, 1638
                        (1792, 3072, 1024, 0), (1792, 16384, 1024, 2), (8192, 8192, 8192, 3)]:
     run_gemm(M, N, K, epi)
     run_gemm(M, N, K, epi, pair=True)
+    run_gemm(M, N, K, epi, pair=True, stream_k=True)

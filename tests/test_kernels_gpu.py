@@ -20,7 +20,7 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_gemm(M, N, K, epi, seed=0, pair=False):
+def run_gemm(M, N, K, epi, seed=0, pair=False, stream_k=False):
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
     Mp = (M + 255) // 256 * 256
@@ -48,7 +48,7 @@ def run_gemm(M, N, K, epi, seed=0, pair=False):
     else:
         out = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
         want = ref
-    _lib.check(lib.mode_debug_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(out), M, N, K, epi | (0x100 if pair else 0), _stream()))
+    _lib.check(lib.mode_debug_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(out), M, N, K, epi | (0x100 if pair else 0) | (0x200 if stream_k else 0), _stream()))
     torch.cuda.synchronize()
     return out.float(), want
 
@@ -56,10 +56,10 @@ def run_gemm(M, N, K, epi, seed=0, pair=False):
 @pytest.mark.parametrize("epi", [4, 0, 1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 1024), (448, 1024, 1024),
                                    (100, 256, 512), (3584, 1024, 4096), (1000, 3072, 1024),
-                                   (3584, 3072, 1024), (5000, 2048, 512)])
-@pytest.mark.parametrize("pair", [False, True], ids=["cta1", "cta2"])
-def test_gemm_matches_fp32_reference(M, N, K, epi, pair):
-    got, want = run_gemm(M, N, K, epi, pair=pair)
+                                   (3584, 3072, 1024), (5000, 2048, 512), (7168, 1024, 4096), (3584, 8192, 1024)])
+@pytest.mark.parametrize("mode", ["cta1", "cta2", "cta2_streamk"])
+def test_gemm_matches_fp32_reference(M, N, K, epi, mode):
+    got, want = run_gemm(M, N, K, epi, pair=mode != "cta1", stream_k=mode == "cta2_streamk")
     assert torch.isfinite(got).all()
     err = (got - want).abs()
     scale = want.abs().max().item() + 1e-6
