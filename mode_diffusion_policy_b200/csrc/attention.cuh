@@ -52,6 +52,7 @@ struct AttnParams {
 // DH: head dim (32/64/128). MT: number of 16-row tiles covering T (T_pad = 16*MT).
 template <int DH, int MT>
 __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnParams p) {
+  pdl_trigger();
   constexpr int TPAD = 16 * MT;
   constexpr int LDS = DH + 8;            // padded row (bf16 elements): conflict-free ldmatrix
   constexpr int VPR = DH / 8;            // 16-byte vectors per row
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
   __nv_bfloat16* sK = sQ + TPAD * LDS;
   __nv_bfloat16* sV = sK + TPAD * LDS;
 
+  pdl_wait();
   // ---- stage q, k, v into shared memory: all rows are requested up front with cp.async (no register staging, the
   //      whole 3 x T x Dh tile is in flight at once), then q and k are RMS-normalised in place
   const int sub = lane % VPR;  // vector index inside the row

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <map>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -257,6 +258,25 @@ static int dev_alloc(mode_engine* e, T** p, size_t n, bool zero = true) {
 }
 
 // ------------------------------------------------------------------------------------------------ launches
+// All hot-path kernels go through cudaLaunchKernelEx with programmatic stream serialization (PDL): see ptx.cuh.
+static bool pdl_enabled() {
+  static const bool on = !(getenv("MODE_PDL") && atoi(getenv("MODE_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 static int g_attr_done = 0;
 template <int EPI>
 static int gemm_set_attr() {
@@ -289,20 +309,20 @@ static int launch_gemm(int epi, bool pair, int num_sms, cudaStream_t st, const G
   dim3 grid(pair ? (num_sms & ~1) : num_sms), block(GEMM_THREADS);
   if (pair) {
     switch (epi) {
-      case EPI_BIAS_BF16: gemm_tcgen05_2cta_kernel<EPI_BIAS_BF16><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
-      case EPI_RESID_F32: gemm_tcgen05_2cta_kernel<EPI_RESID_F32><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
-      case EPI_SWIGLU_BF16: gemm_tcgen05_2cta_kernel<EPI_SWIGLU_BF16><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
-      case EPI_PLAIN_BF16: gemm_tcgen05_2cta_kernel<EPI_PLAIN_BF16><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
-      case EPI_PLAIN_F32: gemm_tcgen05_2cta_kernel<EPI_PLAIN_F32><<<grid, block, G2_SMEM_BYTES, st>>>(p); break;
+      case EPI_BIAS_BF16: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_BIAS_BF16>, grid, block, G2_SMEM_BYTES, st, p)); break;
+      case EPI_RESID_F32: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_RESID_F32>, grid, block, G2_SMEM_BYTES, st, p)); break;
+      case EPI_SWIGLU_BF16: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_SWIGLU_BF16>, grid, block, G2_SMEM_BYTES, st, p)); break;
+      case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_PLAIN_BF16>, grid, block, G2_SMEM_BYTES, st, p)); break;
+      case EPI_PLAIN_F32: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_PLAIN_F32>, grid, block, G2_SMEM_BYTES, st, p)); break;
       default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
     }
   } else {
     switch (epi) {
-      case EPI_BIAS_BF16: gemm_tcgen05_kernel<EPI_BIAS_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-      case EPI_RESID_F32: gemm_tcgen05_kernel<EPI_RESID_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-      case EPI_SWIGLU_BF16: gemm_tcgen05_kernel<EPI_SWIGLU_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-      case EPI_PLAIN_BF16: gemm_tcgen05_kernel<EPI_PLAIN_BF16><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
-      case EPI_PLAIN_F32: gemm_tcgen05_kernel<EPI_PLAIN_F32><<<grid, block, GEMM_SMEM_BYTES, st>>>(p); break;
+      case EPI_BIAS_BF16: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_BIAS_BF16>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
+      case EPI_RESID_F32: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_RESID_F32>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
+      case EPI_SWIGLU_BF16: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_SWIGLU_BF16>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
+      case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_PLAIN_BF16>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
+      case EPI_PLAIN_F32: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_PLAIN_F32>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
       default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
     }
   }
@@ -322,7 +342,7 @@ static int launch_attn_t(cudaStream_t st, const AttnParams& p) {
   }
   if (p.B == 0) return MODE_OK;
   const int items = p.B * p.H;
-  attention_kernel<DH, MT><<<(items + ATTN_WARPS - 1) / ATTN_WARPS, ATTN_WARPS * 32, smem, st>>>(p);
+  CU_OK(launch_k(attention_kernel<DH, MT>, dim3((items + ATTN_WARPS - 1) / ATTN_WARPS), dim3(ATTN_WARPS * 32), smem, st, p));
   CU_OK(cudaGetLastError());
   return MODE_OK;
 }
@@ -652,10 +672,13 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.sk_flags = nullptr;
   return p;
 }
-// stream-K over the last partial wave pays when the GEMM has more than one wave of tiles (QKV, expert up/down)
+// Stream-K over the last partial wave (QKV, expert up/down). Correct (tests/test_kernels_gpu.py) but OFF by default:
+// measured on B200 the fp32 partial round trip costs as much as the removed tail (profiles/r01_gemm_variants.log), and
+// splitting K makes the accumulation order depend on the batch size, which would break the bit-exact batch-split
+// invariance of the sampler. MODE_GEMM_STREAM_K=1 turns it on for experiments.
 static void enable_stream_k(mode_engine* e, GemmParams& p) {
-  static const bool off = getenv("MODE_GEMM_STREAM_K") && atoi(getenv("MODE_GEMM_STREAM_K")) == 0;
-  if (!e->pair || off) return;
+  static const bool on = getenv("MODE_GEMM_STREAM_K") && atoi(getenv("MODE_GEMM_STREAM_K")) != 0;
+  if (!e->pair || !on) return;
   p.sk_enable = 1;
   p.sk_partials = e->sk_partials;
   p.sk_flags = e->sk_flags;
@@ -665,14 +688,14 @@ static void enable_stream_k(mode_engine* e, GemmParams& p) {
 #define LAUNCH_ROW_KERNEL(KERNEL, d, grid, st, params)                                        \
   do {                                                                                        \
     switch ((d) / 128) {                                                                      \
-      case 2: KERNEL<2><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
-      case 4: KERNEL<4><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
-      case 6: KERNEL<6><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
-      case 8: KERNEL<8><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                  \
-      case 10: KERNEL<10><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
-      case 12: KERNEL<12><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
-      case 14: KERNEL<14><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
-      case 16: KERNEL<16><<<(grid), ROW_WARPS * 32, 0, (st)>>>(params); break;                \
+      case 2: CU_OK(launch_k(KERNEL<2>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                  \
+      case 4: CU_OK(launch_k(KERNEL<4>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                  \
+      case 6: CU_OK(launch_k(KERNEL<6>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                  \
+      case 8: CU_OK(launch_k(KERNEL<8>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                  \
+      case 10: CU_OK(launch_k(KERNEL<10>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                \
+      case 12: CU_OK(launch_k(KERNEL<12>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                \
+      case 14: CU_OK(launch_k(KERNEL<14>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                \
+      case 16: CU_OK(launch_k(KERNEL<16>, dim3(grid), dim3(ROW_WARPS * 32), 0, (st), params)); break;                \
       default: return fail(MODE_ERR_INVALID, "embed_dim %d unsupported by the row kernels", (d)); \
     }                                                                                         \
   } while (0)
@@ -707,13 +730,13 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   r.probs = e->probs; r.logits = e->logits;
   r.L = n_layers; r.layer0 = layer0; r.B = B; r.E = e->E; r.K = e->K; r.Hd = e->Hd; r.normalize = e->cfg.router_normalize;
   const int distinct_rows = (stride == 0 && !z_explicit) ? 1 : B;
-  router_kernel<<<n_layers * distinct_rows, ROW_WARPS * 32, 0, st>>>(r);
+  CU_OK(launch_k(router_kernel, dim3(n_layers * distinct_rows), dim3(ROW_WARPS * 32), 0, st, r));
   PlanParams pl;
   pl.sel_idx = e->sel_idx; pl.pos = e->pos_tab; pl.up_tiles = e->up_tiles; pl.down_tiles = e->down_tiles;
   pl.num_tiles = e->num_tiles; pl.usage = e->usage; pl.tokens = e->tokens;
   pl.L = e->L; pl.B = B; pl.K = e->K; pl.E = e->E; pl.T = e->T; pl.max_tiles = e->max_tiles;
   pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0; pl.tile_m = e->tile_m;
-  plan_kernel<<<n_layers, 256, 0, st>>>(pl);
+  CU_OK(launch_k(plan_kernel, dim3(n_layers), dim3(256), 0, st, pl));
   CU_OK(cudaGetLastError());
   e->launch_count += 2;
   return MODE_OK;

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  pdl_wait();  // setup above overlapped the previous kernel's tail; its outputs are read from here on
   const int n_m = *p.num_m_tiles;
   const int total = n_m * p.n_blocks;
   const int k_blocks = p.k_blocks;
@@ -434,6 +436,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
@@ -458,6 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  pdl_wait();  // setup above overlapped the previous kernel's tail; its outputs are read from here on
   const int n_m = *p.num_m_tiles;
   const int total = n_m * p.n_blocks;
   const int k_blocks = p.k_blocks;

@@ -36,6 +36,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the denoising step is launched with programmaticStreamSerializationAllowed: it may become resident
+// while its predecessor drains. pdl_trigger() lets the successor start launching; pdl_wait() blocks until the
+// predecessor has completed and its memory is visible — nothing produced by earlier kernels is touched before it.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

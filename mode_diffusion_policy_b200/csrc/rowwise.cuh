@@ -74,6 +74,8 @@ struct EmbedParams {
 
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
@@ -157,6 +159,8 @@ struct Ln1Params {
 };
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln1_kernel(const Ln1Params p) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.rows) return;
@@ -211,6 +215,8 @@ struct RouterParams {
 // through shared memory, warp 0 finishes. With sigma_stride == 0 (samplers) there is ONE distinct row per layer; its
 // result is broadcast to all B samples' table slots.
 __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[ROW_WARPS][MAX_EXPERTS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = p.sc.sigma_stride == 0 && !p.z_explicit ? 1 : p.B;  // distinct rows
@@ -353,6 +359,8 @@ struct PlanParams {
 };
 
 __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int l = p.layer0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int warp_tot[8];
@@ -435,6 +443,8 @@ struct Ln2Params {
 };
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln2Params p) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
@@ -489,6 +499,8 @@ struct CombineParams {
 };
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const CombineParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
@@ -565,6 +577,8 @@ struct HeadParams {
 };
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int item = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (item >= p.B * p.A) return;
