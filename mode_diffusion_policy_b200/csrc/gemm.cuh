@@ -27,8 +27,10 @@ constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_TMEM_COLS = 512;  // two 256-column accumulators
 constexpr int GEMM_EPI_BUF_BYTES = 32 * 128;  // one warp's staging tile: 32 rows x 128 B (SWIZZLE_128B box of the TMA store)
 constexpr int GEMM_EPI_BYTES = 4 * 2 * GEMM_EPI_BUF_BYTES;  // 4 epilogue warps, double-buffered
-constexpr int GEMM_SMEM_BYTES =
-    GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*barriers*/ + GEMM_EPI_BYTES + 1024 /*align slack*/;
+constexpr int GEMM_BIAS_BYTES = 2 * GEMM_BLOCK_N * 4;  // per-tile bias slice, double-buffered with the accumulators
+constexpr int GEMM_TAIL_BYTES = GEMM_EPI_BYTES + GEMM_BIAS_BYTES + 256 /*barriers*/;
+// shared memory layout (1024-byte aligned base): [stage ring][epilogue staging 32 KB][bias 2 KB][mbarriers + tmem ptr]
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_TAIL_BYTES;
 
 enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,    // out_bf16 = acc + bias[w_row]                       (packed QKV projection)
@@ -110,7 +112,14 @@ struct SkIter {
   }
 };
 
-__device__ __forceinline__ float silu_f(float g) { return __fdividef(g, 1.0f + __expf(-g)); }
+// silu(g) = g / (1 + 2^(-g*log2 e)) with the SFU's ex2/rcp approximations (~2^-22 relative error each; the result is
+// rounded to bf16 right after). 5 instructions per element: the SwiGLU epilogue must stay below the MMA time of a tile.
+__device__ __forceinline__ float silu_f(float g) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(g * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return g * r;
+}
 
 // Fused epilogue of one warp's 32 accumulator rows x 256 columns. Each lane owns one row (TMEM lane); values go
 // TMEM -> registers -> epilogue math -> a 32 x 128 B staging tile in shared memory laid out in the TMA SWIZZLE_128B
@@ -170,7 +179,7 @@ __device__ __forceinline__ void wait_flag(const int* flag) {
 
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t taddr, uint32_t stage_smem, int lane,
-                                                   int out_row0, int w_row, int nb, uint32_t& n_stores,
+                                                   int out_row0, const float* sbias, int nb, uint32_t& n_stores,
                                                    const SkParts sk = SkParts{nullptr, 0, 0}) {
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -204,14 +213,14 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t
         uint32_t rp[32], rg[32];
         load_acc32(taddr + c32, rp, sk, c32 / 32);
         load_acc32(taddr + 128 + c32, rg, sk, (128 + c32) / 32);
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + w_row + c32);
-        const float4* bg = reinterpret_cast<const float4*>(p.bias + w_row + 128 + c32);
+        const float4* bp = reinterpret_cast<const float4*>(sbias + c32);
+        const float4* bg = reinterpret_cast<const float4*>(sbias + 128 + c32);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t pk[4];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const float4 b0 = __ldg(bp + 2 * j + u), b1 = __ldg(bg + 2 * j + u);
+            const float4 b0 = bp[2 * j + u], b1 = bg[2 * j + u];
             const int o = 8 * j + 4 * u;
             const float h0 = (__uint_as_float(rp[o + 0]) + b0.x) * silu_f(__uint_as_float(rg[o + 0]) + b1.x);
             const float h1 = (__uint_as_float(rp[o + 1]) + b0.y) * silu_f(__uint_as_float(rg[o + 1]) + b1.y);
@@ -238,8 +247,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t
         for (int j = 0; j < 4; ++j) {
           uint32_t pk[4];
           if constexpr (EPI == EPI_BIAS_BF16) {
-            const float4* b = reinterpret_cast<const float4*>(p.bias + w_row + c32);
-            const float4 b0 = __ldg(b + 2 * j), b1 = __ldg(b + 2 * j + 1);
+            const float4* b = reinterpret_cast<const float4*>(sbias + c32);
+            const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
             pk[0] = pack_bf16x2(__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
             pk[1] = pack_bf16x2(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
             pk[2] = pack_bf16x2(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
@@ -267,14 +276,24 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t
   }
 }
 
+// The 128 epilogue threads copy the tile's 256 bias values into shared memory BEFORE they wait for the accumulator, so
+// the global-load latency hides behind the tile's MMAs; named barrier 1 (epilogue warps only) publishes them.
+template <int EPI>
+__device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int w_row, int epi_tid) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_SWIGLU_BF16) {
+    sbias[epi_tid] = __ldg(p.bias + w_row + epi_tid);
+    sbias[128 + epi_tid] = __ldg(p.bias + w_row + 128 + epi_tid);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = smem_u32(smem);
-  // layout: [stage ring][256 B barriers][epilogue staging]; barriers sit in a 1 KB slot so the staging stays 1 KB-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  if ((smem_base & 1023u) != 0) __trap();
+  float* sbias_all = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_BYTES + GEMM_BIAS_BYTES);
   const uint32_t bar_base = smem_u32(bars);
   // barrier slots: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -282,7 +301,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + 2 + s); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
-  const uint32_t epi_smem = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES + 1024;  // 1024-aligned: stages are 48 KB
+  const uint32_t epi_smem = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES;  // 1024-aligned: stages are 48 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -383,12 +402,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const GemmMTile tile = p.m_tiles[mt];
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
+      float* sbias = sbias_all + as * GEMM_BLOCK_N;
+      stage_bias<EPI>(p, sbias, p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N, q * 32 + lane);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       if (q * 32 < tile.rows_valid) {  // warp-uniform: this warp's 32 rows hold at least one real row
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
-        const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N;
-        gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + q * 32, w_row, nb, n_stores);
+        gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + q * 32, sbias, nb, n_stores);
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld): hand it back to the MMA warp
       tc_fence_before();
@@ -415,22 +435,23 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_HALF_N = GEMM_BLOCK_N / 2;
 constexpr int G2_B_BYTES = G2_HALF_N * GEMM_BLOCK_K * 2;       // 16 KB
 constexpr int G2_STAGE_BYTES = GEMM_A_BYTES + G2_B_BYTES;      // 32 KB
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + GEMM_EPI_BYTES + 1024;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + GEMM_TAIL_BYTES;
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm_tcgen05_2cta_kernel(const __grid_constant__ GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  if ((smem_base & 1023u) != 0) __trap();
+  float* sbias_all = reinterpret_cast<float*>(smem + G2_STAGES * G2_STAGE_BYTES + GEMM_EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES + GEMM_EPI_BYTES + GEMM_BIAS_BYTES);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * G2_STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * G2_STAGES + 2 + s); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
-  const uint32_t epi_smem = smem_base + G2_STAGES * G2_STAGE_BYTES + 1024;
+  const uint32_t epi_smem = smem_base + G2_STAGES * G2_STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -543,12 +564,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       const GemmMTile tile = p.m_tiles[mt];
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
+      float* sbias = sbias_all + as * GEMM_BLOCK_N;
+      stage_bias<EPI>(p, sbias, p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N, q * 32 + lane);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row0 = static_cast<int>(rank) * GEMM_BLOCK_M + q * 32;  // first row of this warp inside the 256-row tile
       if (row0 < tile.rows_valid) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
-        const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N;
         if (kb0 != 0) {
           // contributor: publish the partial accumulator of this segment in this CTA's slot
           store_partial_warp(taddr, p.sk_partials + static_cast<size_t>(blockIdx.x) * kSlot, p.sk_flags + blockIdx.x * 4 + q,
@@ -561,7 +583,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             sk.base = p.sk_partials + static_cast<size_t>(first) * kSlot;
             for (int i = 0; i < sk.n; ++i) wait_flag(p.sk_flags + (first + 2 * i) * 4 + q);
           }
-          gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, w_row, nb, n_stores, sk);
+          gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, sbias, nb, n_stores, sk);
           if (sk.n > 0) {
             __syncwarp();
             if (lane == 0)
