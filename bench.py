@@ -151,6 +151,7 @@ def main():
     import torch.distributed as dist
 
     from oracle import mode_oracle as O  # inputs/weights generator + cpu_baseline leg only
+    from mode_diffusion_policy_b200 import parallel
     from mode_diffusion_policy_b200.engine import EngineConfig, ModeEngine
 
     if not torch.cuda.is_available():
@@ -204,10 +205,8 @@ def main():
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(hx.numpy(), out.cpu().numpy()), "host entry and device entry disagree"
 
-    t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    # the job is as slow as its slowest rank: MAX over ranks of the device time, whole-job units / that time
+    ms, e2e_ms = parallel.max_over_ranks([ms, e2e_s * 1e3], "cuda")
     value = world * args.steps * N_SAMPLING_STEPS / (ms * 1e-3)
     e2e_value = world * args.steps * N_SAMPLING_STEPS / (e2e_ms * 1e-3)
 
@@ -234,6 +233,10 @@ def main():
             if name in flops and kms > 0:
                 kernels[name]["tflops"] = round(flops[name] * n / (kms * 1e-3) / 1e12, 1)
         step_flops = algorithmic_flops_per_denoising_step(cfg, B)
+        traffic = None  # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture
+        tr = ROOT / "profiles" / "ncu_traffic.json"
+        if tr.exists() and B == B_PER_GPU:
+            traffic = json.loads(tr.read_text()).get("up_gemm_swiglu_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -249,7 +252,7 @@ def main():
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EPI_SWIGLU_BF16> (grouped expert up-projection)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "flops_per_launch": up_flops, "us_per_launch": 1e3 * up_ms / up_n},
             "step_roofline": {"algorithmic_tflop_per_denoising_step": step_flops / 1e12,
                               "achieved_tflops": step_flops * value / world / 1e12,
