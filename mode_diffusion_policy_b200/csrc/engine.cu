@@ -124,6 +124,9 @@ __global__ void noise_actions_kernel(const float* __restrict__ action, const flo
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ engine
+constexpr int ROUTE_SLOTS = 65;   // routing-table slots: 0..63 = sampler steps of a schedule, 64 = plain evaluations
+constexpr int ROUTE_SLOT_EVAL = 64;
+
 struct WeightSpec {
   void* dst;
   size_t dst_row0;
@@ -166,6 +169,7 @@ struct mode_engine {
   unsigned long long *usage, *tokens;
   int dense_cap;  // tiles per dense table
   int cur_B = -1;
+  int last_slot = ROUTE_SLOT_EVAL;  // slot holding the routing of the most recent evaluation (mode_get_routing)
 
   CUtensorMap tm_hA, tm_attn, tm_perm, tm_h, tm_st, tm_goal;
   CUtensorMap tm_wqkv, tm_wproj, tm_wup, tm_wdown, tm_wtok, tm_wgoal;
@@ -495,16 +499,16 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(dev_alloc(e, &e->ybuf, (size_t)e->perm_rows * d));
   A_(dev_alloc(e, &e->st_bf16, (size_t)st_rows * e->obs));
   A_(dev_alloc(e, &e->goal_bf16, (size_t)goal_rows * e->gdim));
-  A_(dev_alloc(e, &e->topk_idx, (size_t)L * e->maxB * K));
-  A_(dev_alloc(e, &e->sel_idx, (size_t)L * e->maxB * K));
-  A_(dev_alloc(e, &e->pos_tab, (size_t)L * e->maxB * K));
-  A_(dev_alloc(e, &e->topk_w, (size_t)L * e->maxB * K));
-  A_(dev_alloc(e, &e->sel_w, (size_t)L * e->maxB * K));
-  A_(dev_alloc(e, &e->probs, (size_t)L * e->maxB * E));
-  A_(dev_alloc(e, &e->logits, (size_t)L * e->maxB * E));
-  A_(dev_alloc(e, &e->up_tiles, (size_t)L * e->max_tiles));
-  A_(dev_alloc(e, &e->down_tiles, (size_t)L * e->max_tiles));
-  A_(dev_alloc(e, &e->num_tiles, (size_t)L));
+  A_(dev_alloc(e, &e->topk_idx, ROUTE_SLOTS * (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->sel_idx, ROUTE_SLOTS * (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->pos_tab, ROUTE_SLOTS * (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->topk_w, ROUTE_SLOTS * (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->sel_w, ROUTE_SLOTS * (size_t)L * e->maxB * K));
+  A_(dev_alloc(e, &e->probs, ROUTE_SLOTS * (size_t)L * e->maxB * E));
+  A_(dev_alloc(e, &e->logits, ROUTE_SLOTS * (size_t)L * e->maxB * E));
+  A_(dev_alloc(e, &e->up_tiles, ROUTE_SLOTS * (size_t)L * e->max_tiles));
+  A_(dev_alloc(e, &e->down_tiles, ROUTE_SLOTS * (size_t)L * e->max_tiles));
+  A_(dev_alloc(e, &e->num_tiles, ROUTE_SLOTS * (size_t)L));
   e->dense_cap = maxM_pad / 128;  // enough for either tile size
   A_(dev_alloc(e, &e->dense_tiles, (size_t)3 * e->dense_cap));
   A_(dev_alloc(e, &e->dense_counts, 3));
@@ -719,8 +723,11 @@ static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* sta
   return MODE_OK;
 }
 
+// Routes `n_slots` evaluations at once: slot s uses sigma + s * sigma_slot_stride (a whole sampler schedule in one
+// launch), tables [slot][L][B][..].
 static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* z_explicit,
-                           int layer0, int n_layers) {
+                           int layer0, int n_layers, int slot0 = ROUTE_SLOT_EVAL, int n_slots = 1,
+                           int sigma_slot_stride = 0) {
   ProfScope ps(e, st, PC_ROUTE);
   RouterParams r;
   r.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
@@ -729,22 +736,25 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   r.topk_idx = e->topk_idx; r.topk_w = e->topk_w; r.sel_idx = e->sel_idx; r.sel_w = e->sel_w;
   r.probs = e->probs; r.logits = e->logits;
   r.L = n_layers; r.layer0 = layer0; r.B = B; r.E = e->E; r.K = e->K; r.Hd = e->Hd; r.normalize = e->cfg.router_normalize;
+  r.slot0 = slot0; r.Ltot = e->L; r.sigma_slot_stride = sigma_slot_stride;
   const int distinct_rows = (stride == 0 && !z_explicit) ? 1 : B;
-  CU_OK(launch_k(router_kernel, dim3(n_layers * distinct_rows), dim3(ROW_WARPS * 32), 0, st, r));
+  CU_OK(launch_k(router_kernel, dim3(n_slots * n_layers * distinct_rows), dim3(ROW_WARPS * 32), 0, st, r));
   PlanParams pl;
   pl.sel_idx = e->sel_idx; pl.pos = e->pos_tab; pl.up_tiles = e->up_tiles; pl.down_tiles = e->down_tiles;
   pl.num_tiles = e->num_tiles; pl.usage = e->usage; pl.tokens = e->tokens;
   pl.L = e->L; pl.B = B; pl.K = e->K; pl.E = e->E; pl.T = e->T; pl.max_tiles = e->max_tiles;
-  pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0; pl.tile_m = e->tile_m;
-  CU_OK(launch_k(plan_kernel, dim3(n_layers), dim3(256), 0, st, pl));
+  pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0; pl.tile_m = e->tile_m; pl.slot0 = slot0; pl.n_layers = n_layers;
+  CU_OK(launch_k(plan_kernel, dim3(n_slots * n_layers), dim3(256), 0, st, pl));
+  e->last_slot = slot0 + n_slots - 1;
   CU_OK(cudaGetLastError());
   e->launch_count += 2;
   return MODE_OK;
 }
 
 // One NoiseBlockMoE (modedit.py:530-595) given hA = bf16(ln_1(x)+c) and routing tables for layer l.
-static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode) {
+static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode, int slot = ROUTE_SLOT_EVAL) {
   const int d = e->d, M = B * e->T;
+  const size_t lt = (size_t)slot * e->L + l;  // layer index inside the routing tables
   GemmParams p = gemm_params(e->tm_hA, e->tm_wqkv, e->to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
   enable_stream_k(e, p);
@@ -766,21 +776,21 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
   Ln2Params n2;
-  n2.x = e->x; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + (size_t)l * B * e->K; n2.perm = e->perm;
+  n2.x = e->x; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + lt * B * e->K; n2.perm = e->perm;
   n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_LN2);
     LAUNCH_ROW_KERNEL(ln2_permute_kernel, d, row_blocks(M), st, n2);
   }
   CU_OK(cudaGetLastError());
-  p = gemm_params(e->tm_perm, e->tm_wup, e->to_h, e->up_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, 8 * d, d,
+  p = gemm_params(e->tm_perm, e->tm_wup, e->to_h, e->up_tiles + lt * e->max_tiles, e->num_tiles + lt, 8 * d, d,
                   e->b_up);
   enable_stream_k(e, p);
   {
     ProfScope ps(e, st, PC_UP);
     RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
   }
-  p = gemm_params(e->tm_h, e->tm_wdown, e->to_y, e->down_tiles + (size_t)l * e->max_tiles, e->num_tiles + l, d, e->F,
+  p = gemm_params(e->tm_h, e->tm_wdown, e->to_y, e->down_tiles + lt * e->max_tiles, e->num_tiles + lt, d, e->F,
                   nullptr);
   enable_stream_k(e, p);
   {
@@ -788,7 +798,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, p));
   }
   CombineParams c;
-  c.x = e->x; c.y = e->ybuf; c.pos = e->pos_tab + (size_t)l * B * e->K; c.w = e->sel_w + (size_t)l * B * e->K;
+  c.x = e->x; c.y = e->ybuf; c.pos = e->pos_tab + lt * B * e->K; c.w = e->sel_w + lt * B * e->K;
   c.g_next = (combine_mode == 0) ? e->ln1_g + (size_t)(l + 1) * d : e->lnf_g;
   c.cvec = e->cvec; c.hA = e->hA; c.xnorm = e->xnorm;
   c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
@@ -802,9 +812,13 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
 }
 
 // One network evaluation: router + plan + embed + L blocks + head. head_mode as HeadParams.mode.
+// `prerouted_slot` >= 0: the routing tables of that slot were filled ahead of time (sampler schedule); otherwise the
+// evaluation routes itself into ROUTE_SLOT_EVAL.
 static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* actions,
-                        int apply_c_in, int head_mode, float* out, const float* coefs, const float* clean) {
-  RET_IF(enqueue_routing(e, st, B, sigma, stride, nullptr, 0, e->L));
+                        int apply_c_in, int head_mode, float* out, const float* coefs, const float* clean,
+                        int prerouted_slot = -1) {
+  const int slot = prerouted_slot >= 0 ? prerouted_slot : ROUTE_SLOT_EVAL;
+  if (prerouted_slot < 0) RET_IF(enqueue_routing(e, st, B, sigma, stride, nullptr, 0, e->L));
   EmbedParams em;
   em.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   em.sig_u = e->sig_u; em.sig_v = e->sig_v; em.goal_tok = e->goal_tok; em.state_tok = e->state_tok; em.pos = e->pos;
@@ -816,7 +830,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
     LAUNCH_ROW_KERNEL(embed_kernel, e->d, row_blocks(B * e->T), st, em);
   }
   CU_OK(cudaGetLastError());
-  for (int l = 0; l < e->L; ++l) RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1));
+  for (int l = 0; l < e->L; ++l) RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1, slot));
   HeadParams h;
   h.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   h.xnorm = e->xnorm; h.w_out = e->w_out; h.b_out = e->b_out; h.x_act = actions; h.out = out; h.clean = clean;
@@ -918,7 +932,7 @@ static int get_ddim_graph(mode_engine* e, int B, int n, cudaGraphExec_t* exec) {
   CU_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   int rc = MODE_OK;
   for (int i = 0; i < n && rc == MODE_OK; ++i)
-    rc = enqueue_eval(e, e->cap_stream, B, e->sig_dev + i, 0, e->x_work, 1, 2, e->x_work, e->coefs_dev + 2 * i, nullptr);
+    rc = enqueue_eval(e, e->cap_stream, B, e->sig_dev + i, 0, e->x_work, 1, 2, e->x_work, e->coefs_dev + 2 * i, nullptr, i);
   cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
   if (rc != MODE_OK) {
     if (graph) cudaGraphDestroy(graph);
@@ -968,6 +982,8 @@ extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const 
   CU_OK(cudaGetLastError());
   const size_t xbytes = (size_t)B * e->A * e->adim * sizeof(float);
   CU_OK(cudaMemcpyAsync(e->x_work, x_inout_dev, xbytes, cudaMemcpyDeviceToDevice, st));
+  // route the whole sigma schedule (n steps x L layers) in one router + one plan launch, ahead of the captured loop
+  RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, nullptr, 0, e->L, 0, n, 1));
   RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
   CU_OK(cudaGraphLaunch(exec, st));
   CU_OK(cudaMemcpyAsync(x_inout_dev, e->x_work, xbytes, cudaMemcpyDeviceToDevice, st));
@@ -1021,11 +1037,12 @@ extern "C" int mode_get_routing(mode_engine_t* e, int layer, int B, int32_t* idx
   if (!e) return fail(MODE_ERR_INVALID, "null engine");
   if (layer < 0 || layer >= e->L || B < 1 || B > e->maxB) return fail(MODE_ERR_INVALID, "layer/B out of range");
   CU_OK(cudaDeviceSynchronize());
-  const size_t o = (size_t)layer * B * e->K;
+  const size_t lt = (size_t)e->last_slot * e->L + layer;
+  const size_t o = lt * B * e->K;
   if (idx_host) CU_OK(cudaMemcpy(idx_host, e->topk_idx + o, (size_t)B * e->K * sizeof(int), cudaMemcpyDeviceToHost));
   if (w_host) CU_OK(cudaMemcpy(w_host, e->topk_w + o, (size_t)B * e->K * sizeof(float), cudaMemcpyDeviceToHost));
   if (probs_host)
-    CU_OK(cudaMemcpy(probs_host, e->probs + (size_t)layer * B * e->E, (size_t)B * e->E * sizeof(float), cudaMemcpyDeviceToHost));
+    CU_OK(cudaMemcpy(probs_host, e->probs + lt * B * e->E, (size_t)B * e->E * sizeof(float), cudaMemcpyDeviceToHost));
   return MODE_OK;
 }
 

@@ -209,6 +209,10 @@ struct RouterParams {
   int L, B, E, K, Hd;
   int layer0;        // first layer handled (block-level entry routes a single layer)
   int normalize;
+  // Tables have a leading `slot` dimension [slot][L][B][...] so that a whole sigma schedule can be routed by ONE launch
+  // (slot = sampler step) ahead of the captured denoising loop; plain evaluations use a single slot.
+  int slot0, Ltot;   // first slot written; layers per slot in the table layout
+  int sigma_slot_stride;  // sigma of slot s starts at sc.sigma + s * sigma_slot_stride
 };
 
 // One CTA (8 warps) per (layer, distinct sigma row): each warp covers Hd/8 hidden units, partial logits are reduced
@@ -220,20 +224,39 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterPara
   __shared__ float part[ROW_WARPS][MAX_EXPERTS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = p.sc.sigma_stride == 0 && !p.z_explicit ? 1 : p.B;  // distinct rows
-  const int l = p.layer0 + blockIdx.x / R, b = blockIdx.x % R;
-  const float s = p.z_explicit ? 0.f : logf(load_sigma(p.sc, b)) / 4.0f;
+  const int per_slot = p.L * R;
+  const int slot_i = blockIdx.x / per_slot, rem = blockIdx.x % per_slot;
+  const int l = p.layer0 + rem / R, b = rem % R;
+  const int lt = (p.slot0 + slot_i) * p.Ltot + l;  // layer index inside the routing tables
+  const float s = p.z_explicit ? 0.f : logf(p.sc.sigma[slot_i * p.sigma_slot_stride + b * p.sc.sigma_stride]) / 4.0f;
   const float* ra = p.ra + static_cast<size_t>(l) * p.Hd;
   const float* rb = p.rb + static_cast<size_t>(l) * p.Hd;
   const float* w2 = p.w2 + static_cast<size_t>(l) * p.E * p.Hd;
   float acc[MAX_EXPERTS];
 #pragma unroll
   for (int e = 0; e < MAX_EXPERTS; ++e) acc[e] = 0.f;
-  for (int j = threadIdx.x; j < p.Hd; j += ROW_WARPS * 32) {
-    const float z = p.z_explicit ? p.z_explicit[static_cast<size_t>(b) * p.Hd + j] : fmaf(s, ra[j], rb[j]);
-    const float hdn = 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));  // nn.GELU() (erf form)
+  // each thread owns 4 consecutive hidden units per pass (Hd = 2d is a multiple of 512): 16-byte loads, all of a
+  // pass's loads (ra, rb, E rows of W2) are independent and issued together
+  for (int j = threadIdx.x * 4; j < p.Hd; j += ROW_WARPS * 32 * 4) {
+    float4 z4;
+    if (p.z_explicit) {
+      z4 = *reinterpret_cast<const float4*>(p.z_explicit + static_cast<size_t>(b) * p.Hd + j);
+    } else {
+      const float4 a4 = *reinterpret_cast<const float4*>(ra + j), b4 = *reinterpret_cast<const float4*>(rb + j);
+      z4 = make_float4(fmaf(s, a4.x, b4.x), fmaf(s, a4.y, b4.y), fmaf(s, a4.z, b4.z), fmaf(s, a4.w, b4.w));
+    }
+    constexpr float kInvSqrt2 = 0.70710678118654752440f;
+    float4 h4;  // nn.GELU() (erf form)
+    h4.x = 0.5f * z4.x * (1.0f + erff(z4.x * kInvSqrt2));
+    h4.y = 0.5f * z4.y * (1.0f + erff(z4.y * kInvSqrt2));
+    h4.z = 0.5f * z4.z * (1.0f + erff(z4.z * kInvSqrt2));
+    h4.w = 0.5f * z4.w * (1.0f + erff(z4.w * kInvSqrt2));
 #pragma unroll
     for (int e = 0; e < MAX_EXPERTS; ++e)
-      if (e < p.E) acc[e] = fmaf(hdn, w2[static_cast<size_t>(e) * p.Hd + j], acc[e]);
+      if (e < p.E) {
+        const float4 w = *reinterpret_cast<const float4*>(w2 + static_cast<size_t>(e) * p.Hd + j);
+        acc[e] = fmaf(h4.x, w.x, fmaf(h4.y, w.y, fmaf(h4.z, w.z, fmaf(h4.w, w.w, acc[e]))));
+      }
   }
 #pragma unroll
   for (int e = 0; e < MAX_EXPERTS; ++e) {
@@ -320,12 +343,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterPara
   __syncwarp();
   for (int i = lane; i < n_dst * p.E; i += 32) {
     const int bb = (R == 1) ? i / p.E : b, e = i % p.E;
-    const size_t o = (static_cast<size_t>(l) * p.B + bb) * p.E + e;
+    const size_t o = (static_cast<size_t>(lt) * p.B + bb) * p.E + e;
     p.probs[o] = part[0][e];
     p.logits[o] = part[1][e];
   }
   for (int bb = (R == 1 ? lane : (lane == 0 ? b : p.B)); bb < (R == 1 ? p.B : b + 1); bb += 32) {
-    const size_t pk = (static_cast<size_t>(l) * p.B + bb) * p.K;
+    const size_t pk = (static_cast<size_t>(lt) * p.B + bb) * p.K;
 #pragma unroll
     for (int k = 0; k < MAX_TOPK; ++k)
       if (k < p.K) {
@@ -356,19 +379,21 @@ struct PlanParams {
   int down_rows_per_expert;      // d
   int layer0;                    // first layer handled by blockIdx.x == 0 (block-level entry plans a single layer)
   int tile_m;                    // rows per GEMM M-tile (128 single-CTA, 256 CTA-pair): groups are padded to it
+  int slot0, n_layers;           // grid = n_slots * n_layers CTAs: slot = slot0 + blockIdx.x / n_layers
 };
 
 __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
   pdl_trigger();
   pdl_wait();
-  const int l = p.layer0 + blockIdx.x;
+  const int l = p.layer0 + blockIdx.x % p.n_layers;
+  const int lt = (p.slot0 + blockIdx.x / p.n_layers) * p.L + l;  // layer index inside the routing tables
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int warp_tot[8];
   __shared__ int cnt[MAX_EXPERTS];
   __shared__ int grp_row0[MAX_EXPERTS];
   __shared__ int grp_tile0[MAX_EXPERTS + 1];
-  const int* sel = p.sel_idx + static_cast<size_t>(l) * p.B * p.K;
-  int* pos = p.pos + static_cast<size_t>(l) * p.B * p.K;
+  const int* sel = p.sel_idx + static_cast<size_t>(lt) * p.B * p.K;
+  int* pos = p.pos + static_cast<size_t>(lt) * p.B * p.K;
   // pass 1: rank of every (sample, slot) inside its expert group; stored temporarily in pos
   for (int e = 0; e < p.E; ++e) {
     int running = 0;
@@ -404,7 +429,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
       tile += nt;
     }
     grp_tile0[p.E] = tile;
-    p.num_tiles[l] = tile;
+    p.num_tiles[lt] = tile;
     atomicAdd(p.tokens + l, static_cast<unsigned long long>(p.B) * p.T);
   }
   __syncthreads();
@@ -421,9 +446,9 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
       t.out_row0 = t.a_row0;
       t.rows_valid = min(p.tile_m, rows - i * p.tile_m);
       t.w_row_base = (l * p.E + e) * p.up_rows_per_expert;
-      p.up_tiles[static_cast<size_t>(l) * p.max_tiles + grp_tile0[e] + i] = t;
+      p.up_tiles[static_cast<size_t>(lt) * p.max_tiles + grp_tile0[e] + i] = t;
       t.w_row_base = (l * p.E + e) * p.down_rows_per_expert;
-      p.down_tiles[static_cast<size_t>(l) * p.max_tiles + grp_tile0[e] + i] = t;
+      p.down_tiles[static_cast<size_t>(lt) * p.max_tiles + grp_tile0[e] + i] = t;
     }
   }
 }
