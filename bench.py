@@ -227,11 +227,23 @@ def main():
         achieved = up_flops / (up_ms / up_n * 1e-3) / 1e12
         flops = {"qkv_gemm": 6.0 * M * d * d, "proj_gemm": 2.0 * M * d * d, "up_gemm_swiglu": up_flops,
                  "down_gemm": 2.0 * (k * M) * d * (4 * d)}
+        # algorithmic HBM bytes per launch of the HBM-bound row kernels
+        hbm_gbs = peaks.get("hbm_gbs", 6650.0)
+        T_ = cfg.seq_len
+        nbytes = {"attention": M * 3 * d * 2 + M * d * 2,                       # read qkv bf16, write out bf16
+                  "ln2_permute": M * d * 4 * 2 + k * M * d * 2,                 # r/w fp32 residual, write k bf16 copies
+                  "combine_ln1": M * d * 4 * 2 + k * M * d * 2 + M * d * 2,     # r/w fp32 residual, read k bf16 rows, write hA
+                  "embed": M * d * 4 + M * d * 2 + B * (1 + cfg.n_state_tokens) * d * 4}
         kernels = {}
         for name, (kms, n) in prof.items():
             kernels[name] = {"ms_per_denoising_step": round(kms, 4), "launches": n}
             if name in flops and kms > 0:
                 kernels[name]["tflops"] = round(flops[name] * n / (kms * 1e-3) / 1e12, 1)
+                kernels[name]["frac_of_bf16_peak"] = round(kernels[name]["tflops"] / peak_tf, 3)
+            if name in nbytes and kms > 0:
+                gbs = nbytes[name] * n / (kms * 1e-3) / 1e9
+                kernels[name]["hbm_gbs"] = round(gbs, 1)
+                kernels[name]["frac_of_hbm_peak"] = round(gbs / hbm_gbs, 3)
         step_flops = algorithmic_flops_per_denoising_step(cfg, B)
         traffic = None  # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture
         tr = ROOT / "profiles" / "ncu_traffic.json"
