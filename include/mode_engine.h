@@ -131,6 +131,11 @@ int mode_profile_eval(mode_engine_t* e, const float* state_dev, const float* goa
  * 3 plain->bf16, 4 plain->f32. M arbitrary, N % 256 == 0, K % 64 == 0. Returns after enqueueing. */
 int mode_debug_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* resid_dev,
                     void* out_dev, int M, int N, int K, int epilogue, void* stream);
+/* Unit-test entry for the weight-gradient GEMM: out[N_out, K_out] (fp32) = dY[rows, N_out]^T @ X[rows, K_out]
+ * (bf16 operands read MN-major straight from the row-major activations). rows % 64 == 0, N_out % 128 == 0,
+ * K_out % 256 == 0; swiglu_half > 0 un-interleaves packed SwiGLU rows on store. */
+int mode_debug_wgrad(const void* dy_dev, const void* x_dev, float* out_dev, int rows, int n_out, int k_out,
+                     int swiglu_half, void* stream);
 /* Unit-test entry for the attention kernel: qkv_dev bf16 (B*T, 3*H*Dh), out_dev bf16 (B*T, H*Dh). */
 int mode_debug_attention(const void* qkv_dev, const float* q_gain_dev, const float* k_gain_dev, void* out_dev,
                          int B, int T, int H, int Dh, float eps, void* stream);

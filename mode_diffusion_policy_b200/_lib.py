@@ -63,6 +63,7 @@ SYMBOLS = {
     "mode_reset_expert_usage": (C.c_int, [_P]),
     "mode_last_launch_count": (C.c_int64, [_P]),
     "mode_debug_gemm": (C.c_int, [_F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mode_debug_wgrad": (C.c_int, [_F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mode_debug_attention": (C.c_int, [_F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
 }
 

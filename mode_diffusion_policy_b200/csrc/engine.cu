@@ -17,6 +17,7 @@
 #include "../../include/mode_engine.h"
 #include "attention.cuh"
 #include "gemm.cuh"
+#include "gemm_wgrad.cuh"
 #include "rowwise.cuh"
 
 using namespace mode;
@@ -304,6 +305,7 @@ static int set_kernel_attrs() {
   RET_IF(gemm_set_attr<EPI_SWIGLU_BF16>());
   RET_IF(gemm_set_attr<EPI_PLAIN_BF16>());
   RET_IF(gemm_set_attr<EPI_PLAIN_F32>());
+  CU_OK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   g_attr_done = 1;
   return MODE_OK;
 }
@@ -1137,6 +1139,63 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
   cudaFree(d_n);
   if (rc != MODE_OK) return rc;
   if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "GEMM kernel failed: %s", cudaGetErrorString(ce));
+  return MODE_OK;
+}
+
+// Activation operand of the weight-gradient GEMM: row-major bf16 [rows, cols], box {64 columns, 64 rows}.
+static int make_mn_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+  return make_tmap_ex(m, base, rows, cols, 64, 2);
+}
+
+static int launch_wgrad(int num_sms, cudaStream_t st, const WgradParams& p) {
+  CU_OK(launch_k(gemm_wgrad_kernel, dim3(num_sms), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, st, p));
+  return MODE_OK;
+}
+
+extern "C" int mode_debug_wgrad(const void* dy_dev, const void* x_dev, float* out_dev, int rows, int n_out, int k_out,
+                                int swiglu_half, void* stream) {
+  if (!dy_dev || !x_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
+  if (rows < 64 || rows % 64 || n_out % 128 || k_out % 256) return fail(MODE_ERR_INVALID, "need rows %% 64 == 0, N_out %% 128 == 0, K_out %% 256 == 0");
+  RET_IF(set_kernel_attrs());
+  int dev = 0, sms = 0;
+  CU_OK(cudaGetDevice(&dev));
+  CU_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WgradParams p;
+  RET_IF(make_mn_tmap(&p.tmap_dy, dy_dev, rows, n_out));
+  RET_IF(make_mn_tmap(&p.tmap_x, x_dev, rows, k_out));
+  RET_IF(make_out_tmap(&p.tmap_out, out_dev, n_out, k_out, 4));
+  WgradProblem pr{0, rows / 64, 0, 0};
+  WgradProblem* d_pr = nullptr;
+  RET_IF(dev_alloc<WgradProblem>(nullptr, &d_pr, 1, false));
+  CU_OK(cudaMemcpy(d_pr, &pr, sizeof(pr), cudaMemcpyHostToDevice));
+  p.problems = d_pr;
+  p.n_problems = 1;
+  p.m_tiles = n_out / 128;
+  p.n_blocks = k_out / 256;
+  p.swiglu_half = swiglu_half;
+  int rc = launch_wgrad(sms, st, p);
+  if (rc == MODE_OK && getenv("MODE_GEMM_BENCH_REPS")) {
+    const int reps = atoi(getenv("MODE_GEMM_BENCH_REPS"));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && rc == MODE_OK; ++i) rc = launch_wgrad(sms, st, p);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("mode_debug_wgrad rows=%d N_out=%d K_out=%d: %.3f us/launch, %.1f TFLOP/s\n", rows, n_out, k_out,
+           1e3 * ms / reps, 2.0 * rows * (double)n_out * k_out * reps / (ms * 1e-3) / 1e12);
+    fflush(stdout);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(d_pr);
+  if (rc != MODE_OK) return rc;
+  if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "wgrad kernel failed: %s", cudaGetErrorString(ce));
   return MODE_OK;
 }
 

@@ -178,7 +178,7 @@ __device__ __forceinline__ void wait_flag(const int* flag) {
 }
 
 template <int EPI>
-__device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t taddr, uint32_t stage_smem, int lane,
+__device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, uint32_t taddr, uint32_t stage_smem, int lane,
                                                    int out_row0, const float* sbias, int nb, uint32_t& n_stores,
                                                    const SkParts sk = SkParts{nullptr, 0, 0}) {
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
@@ -195,9 +195,9 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, uint32_t
     __syncwarp();
     if (lane == 0) {
       if constexpr (EPI == EPI_RESID_F32)
-        tma_reduce_add_2d(&p.tmap_out, buf, col, out_row0);
+        tma_reduce_add_2d(tmap_out, buf, col, out_row0);
       else
-        tma_store_2d(&p.tmap_out, buf, col, out_row0);
+        tma_store_2d(tmap_out, buf, col, out_row0);
       bulk_commit_group();
     }
     ++n_stores;
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tc_fence_after();
       if (q * 32 < tile.rows_valid) {  // warp-uniform: this warp's 32 rows hold at least one real row
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
-        gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + q * 32, sbias, nb, n_stores);
+        gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, tile.out_row0 + q * 32, sbias, nb, n_stores);
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld): hand it back to the MMA warp
       tc_fence_before();
@@ -583,7 +583,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             sk.base = p.sk_partials + static_cast<size_t>(first) * kSlot;
             for (int i = 0; i < sk.n; ++i) wait_flag(p.sk_flags + (first + 2 * i) * 4 + q);
           }
-          gemm_epilogue_warp<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, sbias, nb, n_stores, sk);
+          gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, tile.out_row0 + row0, sbias, nb, n_stores, sk);
           if (sk.n > 0) {
             __syncwarp();
             if (lane == 0)

@@ -108,3 +108,34 @@ def test_attention_matches_reference(B, T, H, Dh):
     rel = (got - want).norm() / want.norm()
     assert rel.item() < 4e-3, rel.item()  # bf16 output rounding dominates (2^-9 rms)
     assert (got - want).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize("rows,n_out,k_out", [(64, 128, 256), (256, 128, 256), (1792, 1024, 1024), (3584, 3072, 1024),
+                                              (3584, 1024, 4096), (448, 256, 2048)])
+def test_wgrad_gemm_matches_fp32_reference(rows, n_out, k_out):
+    """dW = dY^T X with both operands consumed MN-major from the row-major activations (csrc/gemm_wgrad.cuh)."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(rows + n_out)
+    dy = (torch.randn(rows, n_out, generator=g) * 0.5).bfloat16().cuda()
+    x = (torch.randn(rows, k_out, generator=g) / math.sqrt(rows)).bfloat16().cuda()
+    out = torch.full((n_out, k_out), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(lib.mode_debug_wgrad(_ptr(dy), _ptr(x), _ptr(out), rows, n_out, k_out, 0, _stream()))
+    torch.cuda.synchronize()
+    want = dy.float().t() @ x.float()
+    assert torch.isfinite(out).all()
+    err = (out - want).abs().max().item()
+    assert err <= 2e-5 * (want.abs().max().item() + 1e-6) * math.sqrt(rows / 64), err
+
+
+def test_wgrad_gemm_unpacks_swiglu_rows():
+    lib = _lib.load()
+    rows, n_out, k_out, half = 256, 1024, 256, 512
+    g = torch.Generator(device="cpu").manual_seed(5)
+    dy = torch.randn(rows, n_out, generator=g).bfloat16().cuda()  # columns in the packed [128 proj | 128 gate] order
+    x = torch.randn(rows, k_out, generator=g).bfloat16().cuda()
+    out = torch.zeros(n_out, k_out, dtype=torch.float32, device="cuda")
+    _lib.check(lib.mode_debug_wgrad(_ptr(dy), _ptr(x), _ptr(out), rows, n_out, k_out, half, _stream()))
+    torch.cuda.synchronize()
+    packed = (dy.float().t() @ x.float()).view(n_out // 256, 2, 128, k_out)  # [block, proj/gate, 128, K]
+    want = torch.cat([packed[:, 0].reshape(half, k_out), packed[:, 1].reshape(half, k_out)])
+    assert (out - want).abs().max().item() <= 1e-3 * want.abs().max().item()
