@@ -87,6 +87,20 @@ int mode_denoise(mode_engine_t* e, const float* state_dev, const float* goal_dev
 int mode_loss(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* action_dev,
               const float* noise_dev, const float* sigma_dev, float* loss_dev, float* out_dev, int B, void* stream);
 
+/* One training step of GCDenoiser.loss (score_wrappers.py:45-63 as called by MoDEAgent.diffusion_loss,
+ * mode_agent.py:659-672) with the hand-written backward, deterministic mode (dropout 0, top-k routing):
+ * forward with saved activations, loss -> loss_dev[0], model output F -> out_dev (may be NULL), and the gradient of the
+ * mean loss w.r.t. every MoDeDiT parameter into the engine-owned flat fp32 gradient buffer. sigma_dev is per-sample
+ * (B,). Un-routed experts receive exact zeros. Enqueued on `stream`; the first call allocates the training state. */
+int mode_train_step(mode_engine_t* e, const float* state_dev, const float* goal_dev, const float* action_dev,
+                    const float* noise_dev, const float* sigma_dev, float* loss_dev, float* out_dev, int B,
+                    void* stream);
+/* The flat gradient buffer (device pointer, element count): ONE all-reduce over it synchronises data-parallel ranks. */
+int mode_grad_buffer(mode_engine_t* e, float** grads_dev, int64_t* numel);
+/* Element offset and size of the gradient of the reference parameter `name` inside the flat buffer (reference tensor
+ * layout, contiguous). */
+int mode_grad_offset(mode_engine_t* e, const char* name, int64_t* offset, int64_t* numel);
+
 /* sample_ddim (gc_sampling.py:922-951) over GCDenoiser: x_inout_dev (B, action_seq_len, action_dim) holds the initial
  * noise (randn * sigma_max, drawn by the caller as in mode_agent.py:756) and receives the denoised actions.
  * sigmas_host: n_plus_1 values, the last one normally 0 (get_sigmas_exponential, gc_sampling.py:35-38).

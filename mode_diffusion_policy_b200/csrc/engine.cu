@@ -19,6 +19,7 @@
 #include "gemm.cuh"
 #include "gemm_wgrad.cuh"
 #include "rowwise.cuh"
+#include "backward.cuh"
 
 using namespace mode;
 
@@ -139,6 +140,17 @@ struct WeightSpec {
   bool provided;
 };
 
+// Buffers and tensor maps of one NoiseBlockMoE evaluation. Inference uses ONE set for every layer with the residual
+// stream updated in place (x_in = x1 = xn = x_out); training uses one set per layer so that the backward pass finds every
+// activation it needs.
+struct LayerIO {
+  float *x_in, *x1, *xn, *x_out, *x_out_copy;
+  __nv_bfloat16 *hA, *qkv, *attn, *perm, *h, *y, *z, *hA_next;
+  CUtensorMap tm_hA, tm_attn, tm_perm, tm_h;          // GEMM A-operand loads
+  CUtensorMap to_qkv, to_x1, to_h, to_y, to_z;         // GEMM output stores
+};
+struct TrainState;
+
 struct mode_engine {
   mode_config_t cfg;
   int d, L, H, Dh, E, K, T, S, A, adim, maxB, maxM, Hd, F, obs, gdim;
@@ -166,7 +178,8 @@ struct mode_engine {
   __nv_bfloat16 *hA, *qkv, *attn, *perm, *hbuf, *ybuf, *st_bf16, *goal_bf16;
   int *topk_idx, *sel_idx, *pos_tab, *num_tiles, *dense_counts;
   float *topk_w, *sel_w, *probs, *logits;
-  GemmMTile *up_tiles, *down_tiles, *dense_tiles;
+  GemmMTile *up_tiles, *down_tiles, *downT_tiles, *dense_tiles;
+  WgradProblem *wg_up = nullptr, *wg_down = nullptr;  // training only
   unsigned long long *usage, *tokens;
   int dense_cap;  // tiles per dense table
   int cur_B = -1;
@@ -183,6 +196,9 @@ struct mode_engine {
   std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
   std::map<std::pair<int, int>, int64_t> graph_launches;
   int64_t launch_count = 0;
+  LayerIO io;                   // inference buffer set (rebuilt by ensure_batch)
+  bool train_weights_dirty = true;  // transposed weight copies of the training path are stale
+  TrainState* train = nullptr;  // lazily created by the first training call
 
   // optional per-kernel-class timing (mode_profile_eval): event pairs around every launch of one evaluation
   bool prof_on = false;
@@ -300,11 +316,13 @@ static int set_kernel_attrs() {
   RET_IF(gemm2_set_attr<EPI_SWIGLU_BF16>());
   RET_IF(gemm2_set_attr<EPI_PLAIN_BF16>());
   RET_IF(gemm2_set_attr<EPI_PLAIN_F32>());
+  RET_IF(gemm2_set_attr<EPI_SWIGLU_SAVE>());
   RET_IF(gemm_set_attr<EPI_BIAS_BF16>());
   RET_IF(gemm_set_attr<EPI_RESID_F32>());
   RET_IF(gemm_set_attr<EPI_SWIGLU_BF16>());
   RET_IF(gemm_set_attr<EPI_PLAIN_BF16>());
   RET_IF(gemm_set_attr<EPI_PLAIN_F32>());
+  RET_IF(gemm_set_attr<EPI_SWIGLU_SAVE>());
   CU_OK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   g_attr_done = 1;
   return MODE_OK;
@@ -320,6 +338,7 @@ static int launch_gemm(int epi, bool pair, int num_sms, cudaStream_t st, const G
       case EPI_SWIGLU_BF16: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_SWIGLU_BF16>, grid, block, G2_SMEM_BYTES, st, p)); break;
       case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_PLAIN_BF16>, grid, block, G2_SMEM_BYTES, st, p)); break;
       case EPI_PLAIN_F32: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_PLAIN_F32>, grid, block, G2_SMEM_BYTES, st, p)); break;
+      case EPI_SWIGLU_SAVE: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_SWIGLU_SAVE>, grid, block, G2_SMEM_BYTES, st, p)); break;
       default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
     }
   } else {
@@ -329,6 +348,7 @@ static int launch_gemm(int epi, bool pair, int num_sms, cudaStream_t st, const G
       case EPI_SWIGLU_BF16: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_SWIGLU_BF16>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
       case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_PLAIN_BF16>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
       case EPI_PLAIN_F32: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_PLAIN_F32>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
+      case EPI_SWIGLU_SAVE: CU_OK(launch_k(gemm_tcgen05_kernel<EPI_SWIGLU_SAVE>, grid, block, GEMM_SMEM_BYTES, st, p)); break;
       default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
     }
   }
@@ -388,8 +408,11 @@ static void add_spec(mode_engine* e, const std::string& name, void* dst, size_t 
   e->specs[name] = s;
 }
 
+static void destroy_train(TrainState* t);
+
 extern "C" void mode_destroy(mode_engine_t* e) {
   if (!e) return;
+  destroy_train(e->train);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (void* p : e->allocs) cudaFree(p);
@@ -510,6 +533,7 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(dev_alloc(e, &e->logits, ROUTE_SLOTS * (size_t)L * e->maxB * E));
   A_(dev_alloc(e, &e->up_tiles, ROUTE_SLOTS * (size_t)L * e->max_tiles));
   A_(dev_alloc(e, &e->down_tiles, ROUTE_SLOTS * (size_t)L * e->max_tiles));
+  A_(dev_alloc(e, &e->downT_tiles, ROUTE_SLOTS * (size_t)L * e->max_tiles));
   A_(dev_alloc(e, &e->num_tiles, ROUTE_SLOTS * (size_t)L));
   e->dense_cap = maxM_pad / 128;  // enough for either tile size
   A_(dev_alloc(e, &e->dense_tiles, (size_t)3 * e->dense_cap));
@@ -593,6 +617,7 @@ extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* d
     return fail(MODE_ERR_INVALID, "'%s': expected %zu elements, got %zu", name, (size_t)s.rows * s.cols, numel);
   s.provided = true;
   e->finalized = false;
+  e->train_weights_dirty = true;
   if (s.ignore) return MODE_OK;
   if (numel > e->stage_elems) return fail(MODE_ERR_INVALID, "'%s' larger than the staging buffer", name);
   CU_OK(cudaMemcpy(e->stage, data, numel * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
@@ -654,6 +679,15 @@ static int ensure_batch(mode_engine* e, int B) {
   RET_IF(make_out_tmap(&e->to_x, e->x, rows[0], e->d, 4));
   RET_IF(make_out_tmap(&e->to_state, e->state_tok, rows[1], e->d, 4));
   RET_IF(make_out_tmap(&e->to_goal, e->goal_tok, rows[2], e->d, 4));
+  {
+    LayerIO& io = e->io;
+    io.x_in = io.x1 = io.xn = io.x_out = e->x;
+    io.x_out_copy = nullptr;
+    io.hA = io.hA_next = e->hA; io.qkv = e->qkv; io.attn = e->attn; io.perm = e->perm; io.h = e->hbuf; io.y = e->ybuf;
+    io.z = nullptr;
+    io.tm_hA = e->tm_hA; io.tm_attn = e->tm_attn; io.tm_perm = e->tm_perm; io.tm_h = e->tm_h;
+    io.to_qkv = e->to_qkv; io.to_x1 = e->to_x; io.to_h = e->to_h; io.to_y = e->to_y;
+  }
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);  // captured kernels embed the old maps
   e->graphs.clear();
   e->graph_launches.clear();
@@ -743,6 +777,7 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   CU_OK(launch_k(router_kernel, dim3(n_slots * n_layers * distinct_rows), dim3(ROW_WARPS * 32), 0, st, r));
   PlanParams pl;
   pl.sel_idx = e->sel_idx; pl.pos = e->pos_tab; pl.up_tiles = e->up_tiles; pl.down_tiles = e->down_tiles;
+  pl.downT_tiles = e->downT_tiles; pl.wg_up = e->wg_up; pl.wg_down = e->wg_down;
   pl.num_tiles = e->num_tiles; pl.usage = e->usage; pl.tokens = e->tokens;
   pl.L = e->L; pl.B = B; pl.K = e->K; pl.E = e->E; pl.T = e->T; pl.max_tiles = e->max_tiles;
   pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0; pl.tile_m = e->tile_m; pl.slot0 = slot0; pl.n_layers = n_layers;
@@ -754,10 +789,10 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
 }
 
 // One NoiseBlockMoE (modedit.py:530-595) given hA = bf16(ln_1(x)+c) and routing tables for layer l.
-static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode, int slot = ROUTE_SLOT_EVAL) {
+static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode, int slot, const LayerIO& io) {
   const int d = e->d, M = B * e->T;
   const size_t lt = (size_t)slot * e->L + l;  // layer index inside the routing tables
-  GemmParams p = gemm_params(e->tm_hA, e->tm_wqkv, e->to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
+  GemmParams p = gemm_params(io.tm_hA, e->tm_wqkv, io.to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
   enable_stream_k(e, p);
   {
@@ -765,34 +800,39 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
   }
   AttnParams a;
-  a.qkv = e->qkv; a.out = e->attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
+  a.qkv = io.qkv; a.out = io.attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
   a.B = B; a.T = e->T; a.H = e->H; a.eps = e->cfg.rms_eps; a.inv_sqrt_dh = e->inv_sqrt_dh;
   {
     ProfScope ps(e, st, PC_ATTN);
     RET_IF(launch_attn(st, a, e->Dh));
   }
-  p = gemm_params(e->tm_attn, e->tm_wproj, e->to_x, e->dense_tiles, e->dense_counts, d, d, nullptr);  // x += acc
+  p = gemm_params(io.tm_attn, e->tm_wproj, io.to_x1, e->dense_tiles, e->dense_counts, d, d, nullptr);  // x1 += acc
   p.w_row_off = l * d;
   {
     ProfScope ps(e, st, PC_PROJ);
     RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
   Ln2Params n2;
-  n2.x = e->x; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + lt * B * e->K; n2.perm = e->perm;
+  n2.x = io.x1; n2.x_out = io.xn; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + lt * B * e->K; n2.perm = io.perm;
   n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_LN2);
     LAUNCH_ROW_KERNEL(ln2_permute_kernel, d, row_blocks(M), st, n2);
   }
   CU_OK(cudaGetLastError());
-  p = gemm_params(e->tm_perm, e->tm_wup, e->to_h, e->up_tiles + lt * e->max_tiles, e->num_tiles + lt, 8 * d, d,
+  p = gemm_params(io.tm_perm, e->tm_wup, io.to_h, e->up_tiles + lt * e->max_tiles, e->num_tiles + lt, 8 * d, d,
                   e->b_up);
   enable_stream_k(e, p);
   {
     ProfScope ps(e, st, PC_UP);
-    RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
+    if (io.z) {  // training: also keep the pre-activations for the SwiGLU backward
+      p.tmap_out2 = io.to_z;
+      RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
+    } else {
+      RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
+    }
   }
-  p = gemm_params(e->tm_h, e->tm_wdown, e->to_y, e->down_tiles + lt * e->max_tiles, e->num_tiles + lt, d, e->F,
+  p = gemm_params(io.tm_h, e->tm_wdown, io.to_y, e->down_tiles + lt * e->max_tiles, e->num_tiles + lt, d, e->F,
                   nullptr);
   enable_stream_k(e, p);
   {
@@ -800,9 +840,10 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, p));
   }
   CombineParams c;
-  c.x = e->x; c.y = e->ybuf; c.pos = e->pos_tab + lt * B * e->K; c.w = e->sel_w + lt * B * e->K;
+  c.x = io.xn; c.x_out = io.x_out; c.x_copy = io.x_out_copy; c.y = io.y;
+  c.pos = e->pos_tab + lt * B * e->K; c.w = e->sel_w + lt * B * e->K;
   c.g_next = (combine_mode == 0) ? e->ln1_g + (size_t)(l + 1) * d : e->lnf_g;
-  c.cvec = e->cvec; c.hA = e->hA; c.xnorm = e->xnorm;
+  c.cvec = e->cvec; c.hA = io.hA_next; c.xnorm = e->xnorm;
   c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_COMBINE);
@@ -818,13 +859,15 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
 // evaluation routes itself into ROUTE_SLOT_EVAL.
 static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* actions,
                         int apply_c_in, int head_mode, float* out, const float* coefs, const float* clean,
-                        int prerouted_slot = -1) {
+                        int prerouted_slot = -1, const LayerIO* layer_io = nullptr) {
+  // layer_io: per-layer buffer sets (training); nullptr = the shared in-place inference set
+  const LayerIO& io0 = layer_io ? layer_io[0] : e->io;
   const int slot = prerouted_slot >= 0 ? prerouted_slot : ROUTE_SLOT_EVAL;
   if (prerouted_slot < 0) RET_IF(enqueue_routing(e, st, B, sigma, stride, nullptr, 0, e->L));
   EmbedParams em;
   em.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   em.sig_u = e->sig_u; em.sig_v = e->sig_v; em.goal_tok = e->goal_tok; em.state_tok = e->state_tok; em.pos = e->pos;
-  em.w_act_t = e->w_act; em.actions = actions; em.ln1_g = e->ln1_g; em.x = e->x; em.cvec = e->cvec; em.hA = e->hA;
+  em.w_act_t = e->w_act; em.actions = actions; em.ln1_g = e->ln1_g; em.x = io0.x_in; em.x_copy = layer_io ? io0.x1 : nullptr; em.cvec = e->cvec; em.hA = io0.hA;
   em.B = B; em.T = e->T; em.S = e->S; em.A = e->A; em.action_dim = e->adim; em.d = e->d; em.apply_c_in = apply_c_in;
   em.eps = e->cfg.rms_eps; em.inv_sqrt_d = e->inv_sqrt_d;
   {
@@ -832,7 +875,12 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
     LAUNCH_ROW_KERNEL(embed_kernel, e->d, row_blocks(B * e->T), st, em);
   }
   CU_OK(cudaGetLastError());
-  for (int l = 0; l < e->L; ++l) RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1, slot));
+  for (int l = 0; l < e->L; ++l)
+    RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1, slot, layer_io ? layer_io[l] : e->io));
+  if (head_mode < 0) {  // training forward: the loss/head backward kernel consumes the final-ln output directly
+    e->launch_count += 1;
+    return MODE_OK;
+  }
   HeadParams h;
   h.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   h.xnorm = e->xnorm; h.w_out = e->w_out; h.b_out = e->b_out; h.x_act = actions; h.out = out; h.clean = clean;
@@ -1029,7 +1077,7 @@ extern "C" int mode_block_forward(mode_engine_t* e, int layer, const float* x_de
   l1.eps = e->cfg.rms_eps; l1.inv_sqrt_d = e->inv_sqrt_d;
   LAUNCH_ROW_KERNEL(ln1_kernel, d, row_blocks(M), st, l1);
   CU_OK(cudaGetLastError());
-  RET_IF(enqueue_block(e, st, B, layer, 2));
+  RET_IF(enqueue_block(e, st, B, layer, 2, ROUTE_SLOT_EVAL, e->io));
   CU_OK(cudaMemcpyAsync(out_dev, e->x, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
   e->launch_count += 2;
   return MODE_OK;
@@ -1209,3 +1257,5 @@ extern "C" int mode_debug_attention(const void* qkv_dev, const float* q_gain_dev
   a.inv_sqrt_dh = static_cast<float>(pow(static_cast<double>(Dh), -0.5));
   return launch_attn(reinterpret_cast<cudaStream_t>(stream), a, Dh);
 }
+
+#include "train.inc"

@@ -38,6 +38,7 @@ enum GemmEpilogue : int {
   EPI_SWIGLU_BF16 = 2,  // out_bf16[., nb*128+j] = (acc[j]+b[j]) * silu(acc[128+j]+b[128+j])   (expert up-projection)
   EPI_PLAIN_BF16 = 3,   // out_bf16 = acc                                      (expert down-projection)
   EPI_PLAIN_F32 = 4,    // out_f32  = acc                                      (obs/goal token embeddings)
+  EPI_SWIGLU_SAVE = 5,  // EPI_SWIGLU_BF16 + the pre-activations z = acc + bias -> tmap_out2 (training forward)
 };
 
 // One M-tile of work. For grouped GEMMs consecutive tiles may belong to different experts.
@@ -56,6 +57,7 @@ struct alignas(64) GemmParams {
   int n_blocks;                // N / 256
   int k_blocks;                // K / 64
   CUtensorMap tmap_out;        // output [rows, N_out] bf16 (box {64, 32}) or f32 (box {32, 32}), SWIZZLE_128B
+  CUtensorMap tmap_out2;       // EPI_SWIGLU_SAVE: pre-activation output [rows, N] bf16
   const float* bias;           // indexed by weight row (packed like the weights), may be null
   int w_row_off;               // added to every tile's w_row_base (layer offset of dense projections)
   // stream-K over the last, partial wave of tiles (CTA-pair kernel only; see SkIter)
@@ -280,10 +282,23 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
 // the global-load latency hides behind the tile's MMAs; named barrier 1 (epilogue warps only) publishes them.
 template <int EPI>
 __device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int w_row, int epi_tid) {
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_SWIGLU_BF16) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_SWIGLU_SAVE) {
     sbias[epi_tid] = __ldg(p.bias + w_row + epi_tid);
     sbias[128 + epi_tid] = __ldg(p.bias + w_row + 128 + epi_tid);
     asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+}
+
+// EPI_SWIGLU_SAVE = the bias->bf16 epilogue into tmap_out2 followed by the SwiGLU epilogue into tmap_out
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_dispatch(const GemmParams& p, uint32_t taddr, uint32_t stage_smem, int lane,
+                                                       int out_row0, const float* sbias, int nb, uint32_t& n_stores,
+                                                       const SkParts sk = SkParts{nullptr, 0, 0}) {
+  if constexpr (EPI == EPI_SWIGLU_SAVE) {
+    gemm_epilogue_warp<EPI_BIAS_BF16>(&p.tmap_out2, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
+    gemm_epilogue_warp<EPI_SWIGLU_BF16>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
+  } else {
+    gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
   }
 }
 
@@ -408,7 +423,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tc_fence_after();
       if (q * 32 < tile.rows_valid) {  // warp-uniform: this warp's 32 rows hold at least one real row
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
-        gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, tile.out_row0 + q * 32, sbias, nb, n_stores);
+        gemm_epilogue_dispatch<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + q * 32, sbias, nb, n_stores);
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld): hand it back to the MMA warp
       tc_fence_before();
@@ -463,6 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_w);
     tma_prefetch_desc(&p.tmap_out);
+    if constexpr (EPI == EPI_SWIGLU_SAVE) tma_prefetch_desc(&p.tmap_out2);
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(full_bar(s), 2);   // leader's: one arrival per CTA's producer (+ both CTAs' TMA bytes)
       mbar_init(empty_bar(s), 1);  // each CTA's own: the pair's MMA commit is multicast to both
@@ -583,7 +599,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             sk.base = p.sk_partials + static_cast<size_t>(first) * kSlot;
             for (int i = 0; i < sk.n; ++i) wait_flag(p.sk_flags + (first + 2 * i) * 4 + q);
           }
-          gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, tile.out_row0 + row0, sbias, nb, n_stores, sk);
+          gemm_epilogue_dispatch<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, sbias, nb, n_stores, sk);
           if (sk.n > 0) {
             __syncwarp();
             if (lane == 0)

@@ -153,22 +153,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_wgrad_kernel(const __gri
     int iter = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       const WgradProblem pr = p.problems[t / tiles_per_problem];
-      if (pr.k_blocks == 0) continue;
       const int r = t % tiles_per_problem, mt = r % p.m_tiles, nb = r / p.m_tiles;
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1;
-      ++iter;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
       int out_row = mt * 128;  // row inside the problem, packed index space
       if (p.swiglu_half > 0) {
         // packed blocks of 256 rows = 128 projected rows then their 128 gate rows -> reference row order
         const int blk = out_row / 256, in_blk = out_row % 256;
         out_row = (in_blk < 128 ? 0 : p.swiglu_half) + blk * 128;
       }
+      out_row += pr.out_row_base + q * 32;
+      if (pr.k_blocks == 0) {
+        // no token was routed to this expert: its gradient is exactly zero (the reference leaves .grad = None)
+        for (int c = 0; c < 8; ++c) {
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+          const uint32_t buf = stage_smem + (n_stores & 1u) * GEMM_EPI_BUF_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st_shared_v4(buf + lane * 128 + j * 16, 0u, 0u, 0u, 0u);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmap_out, buf, nb * GEMM_BLOCK_N + c * 32, out_row);
+            bulk_commit_group();
+          }
+          ++n_stores;
+        }
+        continue;
+      }
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      ++iter;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
-      gemm_epilogue_warp<EPI_PLAIN_F32>(&p.tmap_out, taddr, stage_smem, lane, pr.out_row_base + out_row + q * 32, nullptr, nb,
-                                        n_stores);
+      gemm_epilogue_warp<EPI_PLAIN_F32>(&p.tmap_out, taddr, stage_smem, lane, out_row, nullptr, nb, n_stores);
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
     }

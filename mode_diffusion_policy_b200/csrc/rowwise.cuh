@@ -3,7 +3,7 @@
 // expert combine, output head + EDM preconditioning + DDIM update.
 // One warp per token row (d floats), 16-byte vector accesses, fp32 math, warp-shuffle reductions.
 #pragma once
-#include "gemm.cuh"
+#include "gemm_wgrad.cuh"
 #include "ptx.cuh"
 
 namespace mode {
@@ -64,6 +64,7 @@ struct EmbedParams {
   const float* actions;    // [B, A, action_dim]
   const float* ln1_g;      // [d] layer-0 ln_1 gain
   float* x;                // [B*T, d]
+  float* x_copy;           // optional second copy (training: seeds the c_proj accumulation buffer x1)
   float* cvec;             // [B, d] conditioning vector c = emb_t (consumed by later kernels)
   __nv_bfloat16* hA;       // [B*T, d]
   int B, T, S, A, action_dim, d;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedPar
       const float4 c = make_float4(fmaf(s, u.x, v.x), fmaf(s, u.y, v.y), fmaf(s, u.z, v.z), fmaf(s, u.w, v.w));
       const float4 g = *reinterpret_cast<const float4*>(p.ln1_g + col);
       *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = x;
+      if (p.x_copy) *reinterpret_cast<float4*>(p.x_copy + static_cast<size_t>(row) * p.d + col) = x;
       if (t == 0) *reinterpret_cast<float4*>(p.cvec + static_cast<size_t>(b) * p.d + col) = c;
       const float h0 = (x.x * rn) * g.x + c.x, h1 = (x.y * rn) * g.y + c.y;
       const float h2 = (x.z * rn) * g.z + c.z, h3 = (x.w * rn) * g.w + c.w;
@@ -371,6 +373,9 @@ struct PlanParams {
   int* pos;                      // [L, B, K]
   GemmMTile* up_tiles;           // [L, max_tiles]
   GemmMTile* down_tiles;         // [L, max_tiles]
+  GemmMTile* downT_tiles;        // [L, max_tiles] transposed down weights (4d rows per expert): data gradient of `down`
+  WgradProblem* wg_up;           // [L, E] weight-gradient problems of the up projection (training; may be null)
+  WgradProblem* wg_down;         // [L, E]
   int* num_tiles;                // [L]
   unsigned long long* usage;     // [L, E]
   unsigned long long* tokens;    // [L]
@@ -436,6 +441,11 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
   if (tid < p.E) atomicAdd(p.usage + static_cast<size_t>(l) * p.E + tid, static_cast<unsigned long long>(cnt[tid]) * p.T);
   // pass 2: ranks -> row positions
   for (int i = tid; i < p.B * p.K; i += 256) pos[i] = grp_row0[sel[i]] + pos[i] * p.T;
+  if (p.wg_up && tid < p.E) {
+    const int nt = grp_tile0[tid + 1] - grp_tile0[tid];
+    p.wg_up[static_cast<size_t>(lt) * p.E + tid] = WgradProblem{grp_row0[tid], nt * p.tile_m / 64, (l * p.E + tid) * p.up_rows_per_expert, 0};
+    p.wg_down[static_cast<size_t>(lt) * p.E + tid] = WgradProblem{grp_row0[tid], nt * p.tile_m / 64, (l * p.E + tid) * p.down_rows_per_expert, 0};
+  }
   // pass 3: tile tables
   for (int e = 0; e < p.E; ++e) {
     const int nt = grp_tile0[e + 1] - grp_tile0[e];
@@ -449,6 +459,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
       p.up_tiles[static_cast<size_t>(lt) * p.max_tiles + grp_tile0[e] + i] = t;
       t.w_row_base = (l * p.E + e) * p.down_rows_per_expert;
       p.down_tiles[static_cast<size_t>(lt) * p.max_tiles + grp_tile0[e] + i] = t;
+      t.w_row_base = (l * p.E + e) * 4 * p.down_rows_per_expert;
+      p.downT_tiles[static_cast<size_t>(lt) * p.max_tiles + grp_tile0[e] + i] = t;
     }
   }
 }
@@ -458,7 +470,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
 // bf16 copy of each token row is written straight to its K expert groups (the gather of :563-566 done as a scatter
 // with 16-byte coalesced stores; no separate permute pass).
 struct Ln2Params {
-  float* x;               // [B*T, d] in/out
+  const float* x;         // [B*T, d] in (x1)
+  float* x_out;           // [B*T, d] out (xn); may alias x (inference: in place)
   const float* g;         // [d]
   const int* pos;         // [B, K] (this layer)
   __nv_bfloat16* perm;    // [rows_perm, d]
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln
       const float4 g = *reinterpret_cast<const float4*>(p.g + col);
       const float4 y = make_float4((x.x * rn) * g.x, (x.y * rn) * g.y, (x.z * rn) * g.z,
                                    (x.w * rn) * g.w);
-      *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = y;
+      *reinterpret_cast<float4*>(p.x_out + static_cast<size_t>(row) * p.d + col) = y;
       const uint2 pk = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
 #pragma unroll
       for (int k = 0; k < MAX_TOPK; ++k)
@@ -509,7 +522,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln
 // then hA = bf16(rms(x)*g_next + c) feeds the next block's QKV GEMM. For the last block g_next is the final `ln`
 // gain (modedit.py:818) and the normalised row is written back as fp32 for the head instead.
 struct CombineParams {
-  float* x;                    // [B*T, d] in: xn, out: block output
+  const float* x;              // [B*T, d] in: xn
+  float* x_out;                // [B*T, d] block output; may alias x (inference: in place)
+  float* x_copy;               // optional second copy of the block output (training: next layer's x1 seed)
   const __nv_bfloat16* y;      // [rows_perm, d] expert outputs (bf16)
   const int* pos;              // [B, K]
   const float* w;              // [B, K] (ascending expert order)
@@ -557,7 +572,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const Combin
         }
       float4 x = *reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row) * p.d + col);
       x = make_float4(x.x + acc.x, x.y + acc.y, x.z + acc.z, x.w + acc.w);
-      *reinterpret_cast<float4*>(p.x + static_cast<size_t>(row) * p.d + col) = x;
+      *reinterpret_cast<float4*>(p.x_out + static_cast<size_t>(row) * p.d + col) = x;
+      if (p.x_copy) *reinterpret_cast<float4*>(p.x_copy + static_cast<size_t>(row) * p.d + col) = x;
       xv[i] = x;
       ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
     }

@@ -150,6 +150,40 @@ class ModeEngine:
                                       sigma.data_ptr(), loss.data_ptr(), out.data_ptr(), B, self._stream()))
         return loss[0], out
 
+    # ---------------------------------------------------------------- training
+    def train_step(self, state, action, goal, noise, sigma):
+        """Forward + hand-written backward of GCDenoiser.loss (deterministic mode). Returns (loss, model output F); the
+        gradients are left in the engine's flat buffer (see `grad`, `flat_grads`)."""
+        state, goal, action, sigma, stride, B = self._prep(state, goal, action, sigma)
+        noise = _f32_cuda(noise, "noise")
+        if stride != 1 and B != 1:
+            sigma = sigma.expand(B).contiguous()
+        out = torch.empty_like(action)
+        loss = torch.empty(1, dtype=torch.float32, device=action.device)
+        _lib.check(self.lib.mode_train_step(self._h, state.data_ptr(), goal.data_ptr(), action.data_ptr(), noise.data_ptr(),
+                                            sigma.data_ptr(), loss.data_ptr(), out.data_ptr(), B, self._stream()))
+        return loss[0], out
+
+    def flat_grads(self) -> torch.Tensor:
+        """Zero-copy torch view of the engine-owned flat fp32 gradient buffer (one all-reduce synchronises DP ranks)."""
+        if getattr(self, "_flat", None) is None:
+            ptr, n = C.c_void_p(), C.c_int64()
+            _lib.check(self.lib.mode_grad_buffer(self._h, C.byref(ptr), C.byref(n)))
+
+            class _Dev:  # __cuda_array_interface__ holder
+                pass
+
+            holder = _Dev()
+            holder.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+            self._flat = torch.as_tensor(holder, device=self.device)
+        return self._flat
+
+    def grad(self, name: str, shape) -> torch.Tensor:
+        """View of the gradient of reference parameter `name` (reference layout)."""
+        off, n = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.mode_grad_offset(self._h, name.encode(), C.byref(off), C.byref(n)))
+        return self.flat_grads()[off.value: off.value + n.value].view(*shape)
+
     def sample_ddim(self, state, x, goal, sigmas) -> torch.Tensor:
         """sample_ddim over GCDenoiser (whole loop = one CUDA graph). `sigmas` includes the trailing 0. Returns actions."""
         state, goal, x, _, _, B = self._prep(state, goal, x, None)

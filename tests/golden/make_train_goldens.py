@@ -1,0 +1,68 @@
+"""Gradient goldens for the training path, from the reference's own autograd (build container only).
+
+Deterministic training-parity mode of SURVEY.md A.5: attn_pdrop = mlp_pdrop = goal_drop = 0, use_argmax=True,
+model.train(); loss = GCDenoiser.loss(state, actions, goal, noise, sigma)[0]; loss.backward() on CPU fp32.
+Full gradients of even the small models are tens of MB, so each tensor is stored as (L2 norm, sum, 256 sampled
+entries at indices drawn from a generator seeded by the tensor's position) — tests compare the engine's gradients at
+the same indices and the norms.
+
+    python tests/golden/make_train_goldens.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import make_goldens as MG  # noqa: E402  (stubs + reference imports)
+from make_goldens import O, MoDeDiT, GCDenoiser  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+N_SAMPLES = 256
+
+
+def sample_indices(numel, tensor_pos):
+    rng = np.random.default_rng(10_000 + tensor_pos)
+    return rng.integers(0, numel, size=min(N_SAMPLES, numel))
+
+
+def golden_train(tag, cfg, B, router_gain=30.0):
+    sd = O.make_weights(cfg, seed=1234, router_gain=router_gain)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cpu", goal_conditioned=True,
+                    action_dim=cfg.action_dim, embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=0.0,
+                    n_layers=cfg.n_layers, n_heads=cfg.n_heads, goal_seq_len=1, obs_seq_len=1,
+                    action_seq_len=cfg.action_seq_len, state_dim=7, mlp_pdrop=0.0, goal_drop=0.0,
+                    num_experts=cfg.num_experts, top_k=cfg.top_k, use_argmax=True, init_style="olmoe")
+    inner.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()})
+    model = GCDenoiser(inner, sigma_data=cfg.sigma_data).train()
+    g = np.load(OUT / f"{tag}.npz")
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    with torch.enable_grad():
+        loss, f_out = model.loss({"state_images": t(state)}, t(acts), t(goal), t(g["loss_noise"]), t(g["sigma_het"]))
+        loss.backward()
+    out = {"loss": np.float32(loss.item()), "F": f_out.detach().numpy()}
+    assert abs(float(loss) - float(g["loss_value"])) < 1e-5 * abs(float(loss)), "train-mode loss differs from eval-mode"
+    names = [n for n, _ in O.state_dict_spec(cfg)]
+    params = dict(inner.named_parameters())
+    for pos, name in enumerate(names):
+        p = params[name]
+        grad = np.zeros(p.shape, np.float32) if p.grad is None else p.grad.numpy()
+        flat = grad.reshape(-1)
+        idx = sample_indices(flat.size, pos)
+        out[f"norm/{name}"] = np.float32(np.linalg.norm(flat.astype(np.float64)))
+        out[f"sum/{name}"] = np.float32(flat.astype(np.float64).sum())
+        out[f"val/{name}"] = flat[idx].astype(np.float32)
+    np.savez_compressed(OUT / f"train_{tag}.npz", **out)
+    unused = [n for n in names if params[n].grad is None]
+    print(f"train_{tag}: loss {float(loss):.6f}; {len(names)} tensors; no-grad tensors: {len(unused)}")
+
+
+if __name__ == "__main__":
+    torch.set_grad_enabled(True)
+    golden_train("model_tiny_d256_l3_e4", MG.O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3,
+                                                          n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2), 5)
+    golden_train("model_wide_d512_l2_e8", MG.O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=512, n_layers=2,
+                                                          n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=8, top_k=2), 4)

@@ -1,0 +1,70 @@
+"""GPU tests of the training path (mode_train_step): loss and parameter gradients against the reference's own autograd
+(tests/golden/make_train_goldens.py, deterministic mode of SURVEY.md A.5). The engine's forward AND backward run on
+bf16 tensor-core operands, the goldens are fp32: gradients are compared at the sampled entries with a relative
+tolerance that reflects bf16 operands (a few 1e-2), norms within 5 %, and un-routed experts must be exact zeros."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mode_oracle as O
+from test_engine_gpu import MODELS, cu, engine_for
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def sample_indices(numel, tensor_pos):
+    """Same index generator as tests/golden/make_train_goldens.py."""
+    rng = np.random.default_rng(10_000 + tensor_pos)
+    return rng.integers(0, numel, size=min(256, numel))
+
+
+def grad_report(eng, cfg, gold):
+    rows = []
+    for pos, (name, shape) in enumerate(O.state_dict_spec(cfg)):
+        if name == "gripper_embed.weight":
+            continue
+        got = eng.grad(name, shape).reshape(-1).float().cpu().numpy()
+        idx = sample_indices(got.size, pos)
+        want = gold[f"val/{name}"]
+        wn = float(gold[f"norm/{name}"])
+        gn = float(np.linalg.norm(got.astype(np.float64)))
+        err = float(np.linalg.norm(got[idx] - want) / (np.linalg.norm(want) + 1e-30)) if wn > 0 else float(np.abs(got).max())
+        rows.append((name, wn, gn, err))
+    return rows
+
+
+@pytest.mark.parametrize("tag", list(MODELS))
+def test_loss_and_gradients_match_reference_autograd(tag):
+    cfg, B = MODELS[tag]
+    g = np.load(GOLD / f"{tag}.npz")
+    gt = np.load(GOLD / f"train_{tag}.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    eng = engine_for(cfg, sd, 8)
+    loss, F = eng.train_step(cu(state), cu(acts), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(gt["loss"])) <= 3e-2 * abs(float(gt["loss"])), (float(loss), float(gt["loss"]))
+    rows = grad_report(eng, cfg, gt)
+    bad = []
+    for name, wn, gn, err in rows:
+        if wn == 0.0:  # un-routed expert: the reference leaves .grad = None
+            ok = gn == 0.0
+        else:
+            ok = err < 6e-2 and abs(gn - wn) <= 0.06 * wn
+        if not ok:
+            bad.append((name, wn, gn, err))
+    worst = sorted(rows, key=lambda r: -r[3] if r[1] > 0 else 0)[:8]
+    print("worst sampled-entry relative errors:", [(n, round(e, 4)) for n, _, _, e in worst])
+    assert not bad, bad[:12]
+    # deterministic: a second step reproduces every gradient bit for bit
+    flat = eng.flat_grads().clone()
+    loss2, _ = eng.train_step(cu(state), cu(acts), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
+    assert torch.equal(flat, eng.flat_grads()) and float(loss2) == float(loss)
+    # inference after training still works on the same engine (shared weights, separate buffers)
+    D = eng.denoise(cu(state), cu(g["denoise_x"]), cu(goal), cu(g["sigma_het"])).cpu().numpy()
+    want = O.denoiser_forward(sd, cfg, state, g["denoise_x"], goal, g["sigma_het"], "bf16")
+    assert np.linalg.norm(D - want) / np.linalg.norm(want) < 1e-3
