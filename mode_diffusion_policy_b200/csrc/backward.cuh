@@ -474,8 +474,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const At
   float* vv = kh + T * DH;
   float* dO = vv + T * DH;
   float* P = dO + T * DH;
-  float* dS = P + ATTN_BWD_MAX_T * ATTN_BWD_MAX_T;
-  float* rq = dS + ATTN_BWD_MAX_T * ATTN_BWD_MAX_T;
+  float* dS = P + T * ATTN_BWD_MAX_T;
+  float* rq = dS + T * ATTN_BWD_MAX_T;
   float* rk = rq + ATTN_BWD_MAX_T;
   float gq[DPL], gk[DPL];
 #pragma unroll
