@@ -66,7 +66,8 @@ const char* mode_last_error(void);
  * "sigma_emb.bias", ...; the full list is in DESIGN.md), `data` is contiguous fp32 with the reference shape, on the
  * host (is_device = 0) or on the engine's device (1). The engine converts to its own layout (bf16, packed QKV,
  * interleaved SwiGLU rows); the caller keeps ownership. "gripper_embed.weight" is accepted and ignored (unused unless
- * use_proprio, modedit.py:684). Synchronous. */
+ * use_proprio, modedit.py:684). Host sources are copied synchronously; device sources are packed by a kernel on the
+ * default stream without synchronisation (mode_finalize_weights synchronises that stream). */
 int mode_set_weight(mode_engine_t* e, const char* name, const void* data, int is_device, const int64_t* shape,
                     int ndim);
 /* Verifies every tensor was provided, precomputes the sigma-embedding and router affine forms. Synchronous. */

@@ -619,10 +619,18 @@ extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* d
   e->finalized = false;
   e->train_weights_dirty = true;
   if (s.ignore) return MODE_OK;
-  if (numel > e->stage_elems) return fail(MODE_ERR_INVALID, "'%s' larger than the staging buffer", name);
-  CU_OK(cudaMemcpy(e->stage, data, numel * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
   const int threads = 256;
   const unsigned blocks = (unsigned)((numel + threads - 1) / threads);
+  if (is_device) {
+    // device source: pack straight from the caller's tensor, stream-ordered on the default stream, no synchronisation
+    // (a training loop re-packs all 686 M parameters after every optimiser step)
+    pack_rows_kernel<<<blocks, threads>>>(reinterpret_cast<const float*>(data), s.dst, s.rows, s.cols, s.dst_row0,
+                                          s.swiglu_half, s.to_bf16, s.transpose ? 1 : 0);
+    CU_OK(cudaGetLastError());
+    return MODE_OK;
+  }
+  if (numel > e->stage_elems) return fail(MODE_ERR_INVALID, "'%s' larger than the staging buffer", name);
+  CU_OK(cudaMemcpy(e->stage, data, numel * sizeof(float), cudaMemcpyHostToDevice));
   pack_rows_kernel<<<blocks, threads>>>(e->stage, s.dst, s.rows, s.cols, s.dst_row0, s.swiglu_half, s.to_bf16,
                                         s.transpose ? 1 : 0);
   CU_OK(cudaGetLastError());
@@ -645,7 +653,7 @@ extern "C" int mode_finalize_weights(mode_engine_t* e) {
     matvec_f64_kernel<<<(Hd + 7) / 8, 256>>>(W1, e->sig_v, e->r_b1 + (size_t)l * Hd, e->r_b + (size_t)l * Hd, Hd, d);
   }
   CU_OK(cudaGetLastError());
-  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaStreamSynchronize(nullptr));
   e->finalized = true;
   return MODE_OK;
 }

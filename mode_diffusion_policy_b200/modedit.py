@@ -182,6 +182,9 @@ class MoDeDiT(nn.Module):
         self.num_experts, self.top_k = num_experts, top_k
         self.use_proprio = use_proprio
         self.cond_mask_prob = goal_drop
+        self._train_cfg = dict(attn_pdrop=attn_pdrop, mlp_pdrop=mlp_pdrop, goal_drop=goal_drop, embed_pdrob=embed_pdrob,
+                               use_argmax=use_argmax)
+        self._warned_deterministic = False
         # parameters in the reference's registration order (modedit.py:680-722)
         self.sigma_emb = nn.Linear(1, embed_dim)
         self.sigma_linear = nn.Linear(embed_dim, embed_dim, bias=False)
@@ -228,6 +231,20 @@ class MoDeDiT(nn.Module):
             self._engine.load_state_dict({k: v for k, v in self.state_dict().items()})
             self._weights_key = key
         return self._engine
+
+    @property
+    def _param_names(self):
+        return [n for n, _ in self.named_parameters()]
+
+    def check_trainable(self) -> None:
+        """The engine trains in the deterministic mode of SURVEY.md A.5: no dropout, top-k (not multinomial) routing.
+        Configurations that ask for stochastic regularisation still train, with a one-time warning."""
+        c = self._train_cfg
+        stochastic = [k for k in ("attn_pdrop", "mlp_pdrop", "goal_drop", "embed_pdrob") if c[k]] + \
+            ([] if c["use_argmax"] else ["multinomial routing (use_argmax=False)"])
+        if stochastic and not self._warned_deterministic:
+            logger.warning("MoDE engine trains deterministically; ignored: %s", ", ".join(stochastic))
+            self._warned_deterministic = True
 
     def set_sigma_data(self, sigma_data: float) -> None:
         if float(sigma_data) != self._engine_cfg.sigma_data:

@@ -31,6 +31,33 @@ def _instantiate(inner_model):
         return MoDeDiT(**cfg)
 
 
+class _EngineLoss(torch.autograd.Function):
+    """GCDenoiser.loss through the engine's fused forward + hand-written backward (`mode_train_step`).
+
+    The engine computes the gradient of the (scalar, mean) loss w.r.t. every parameter during `forward`; `backward`
+    hands them to autograd scaled by the incoming gradient, so optimisers, Lightning and DDP hooks see ordinary
+    `.grad` tensors. Parameters are passed as inputs only to be registered in the graph."""
+
+    @staticmethod
+    def forward(ctx, inner, state_images, action, goal, noise, sigma, *params):
+        eng = inner._ensure_engine(action.shape[0])
+        loss, out = eng.train_step(state_images, action, goal, noise, sigma)
+        ctx.eng, ctx.names, ctx.shapes = eng, inner._param_names, [tuple(p.shape) for p in params]
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.mark_non_differentiable(out)
+        return loss, out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out):
+        grads = []
+        for name, shape, need in zip(ctx.names, ctx.shapes, ctx.needs):
+            if not need or name == "gripper_embed.weight":  # unused unless use_proprio (reference modedit.py:684)
+                grads.append(None)
+            else:
+                grads.append(ctx.eng.grad(name, shape) * g_loss)  # the product is a fresh tensor: the buffer is reused
+        return (None, None, None, None, None, None, *grads)
+
+
 class GCDenoiser(nn.Module):
     """Karras et al. preconditioner around the MoDE network; forward and loss run fused inside the CUDA engine
     (c_in scaling in the embedding kernel, c_out/c_skip combine in the head kernel)."""
@@ -61,10 +88,16 @@ class GCDenoiser(nn.Module):
         return self._engine(action.shape[0]).denoise(state["state_images"], action, goal, sigma).to(action.dtype)
 
     def loss(self, state, action, goal, noise, sigma, **kwargs):
-        """Forward value of the EDM loss (reference score_wrappers.py:45-63) with eval-mode routing. No autograd graph."""
+        """EDM loss (reference score_wrappers.py:45-63). In eval mode: the forward value. In train mode: forward and
+        the hand-written backward in one engine call, wired into autograd (deterministic mode of SURVEY.md A.5 — the
+        engine applies neither dropout nor multinomial routing; see MoDeDiT.check_trainable)."""
         m = self.inner_model
         goal = m._goals(goal, False)
-        loss, out = self._engine(action.shape[0]).loss(state["state_images"], action, goal, noise, sigma)
+        if m.training and torch.is_grad_enabled():
+            m.check_trainable()
+            params = [p for _, p in m.named_parameters()]
+            return _EngineLoss.apply(m, state["state_images"], action, goal, noise, sigma, *params)
+        loss, out = m._ensure_engine(action.shape[0]).loss(state["state_images"], action, goal, noise, sigma)
         return loss, out
 
     def sample_ddim(self, state, action, goal, sigmas):

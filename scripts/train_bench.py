@@ -1,0 +1,88 @@
+"""BASELINE.json configs[3]: training step, noised-action MSE, full MoDE (12 L, d=1024, 4 experts), per-GPU batch 128
+(global 1024 on 8 GPUs), bf16 tensor-core operands, ONE NCCL all-reduce of the flat gradient buffer per step, fused
+AdamW on the fp32 masters, weights re-packed for the next step. Prints one JSON line (rank 0).
+
+    python scripts/train_bench.py                                  # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/train_bench.py
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+from oracle import mode_oracle as O  # noqa: E402  (synthetic weights / inputs only)
+from mode_diffusion_policy_b200 import parallel  # noqa: E402
+from mode_diffusion_policy_b200.modedit import MoDeDiT  # noqa: E402
+from mode_diffusion_policy_b200.score_wrappers import GCDenoiser  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=128)
+ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--layers", type=int, default=12)
+a = ap.parse_args()
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+cfg = O.ModeConfig(n_layers=a.layers)
+B = a.batch
+inner = MoDeDiT(obs_dim=2048, goal_dim=512, device="cuda", goal_conditioned=True, action_dim=7, embed_dim=1024, embed_pdrob=0,
+                attn_pdrop=0.0, n_layers=a.layers, n_heads=8, goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7,
+                mlp_pdrop=0.0, goal_drop=0.0, num_experts=4, top_k=2, use_argmax=True, max_batch=B)
+inner.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_weights_fast(cfg, seed=1234).items()})
+model = GCDenoiser(inner, sigma_data=0.5).cuda().train()
+opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+state, goal, x0 = O.make_inputs(cfg, B, seed=4321 + rank)
+rng = np.random.default_rng(7 + rank)
+S, G = torch.from_numpy(state).cuda(), torch.from_numpy(goal).cuda()
+A_ = torch.from_numpy((x0 / np.float32(80.0)).astype(np.float32)).cuda()
+noise = torch.from_numpy(rng.standard_normal(x0.shape).astype(np.float32)).cuda()
+sigma = torch.from_numpy(np.exp(rng.uniform(np.log(1e-3), np.log(80.0), B)).astype(np.float32)).cuda()
+eng = None
+
+
+def step():
+    global eng
+    opt.zero_grad(set_to_none=True)
+    loss, _ = model.loss({"state_images": S}, A_, G, noise, sigma)
+    eng = inner._engine
+    if world > 1:  # ONE all-reduce over the engine's flat gradient buffer, before autograd hands out the views
+        flat = eng.flat_grads()
+        dist.all_reduce(flat)
+        flat.div_(world)
+    loss.backward()
+    opt.step()
+    return loss
+
+
+for _ in range(a.warmup):
+    step()
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
+    loss = step()
+e1.record()
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+(ms,) = parallel.max_over_ranks([e0.elapsed_time(e1)], "cuda")
+if rank == 0:
+    fwd_flops = 2.526888e12 * B / 256 * a.layers / 12
+    print(json.dumps({"metric": "training-samples/sec", "value": world * B * a.steps / (ms * 1e-3), "unit": "samples/s",
+                      "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+                      "global_batch": world * B, "dtype": "bf16", "data": "synthetic", "loss": float(loss),
+                      "approx_tflops": 3 * fwd_flops * a.steps / (ms * 1e-3) / 1e12,
+                      "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack",
+                                 "grad_allreduce": "one NCCL all-reduce over the flat fp32 gradient buffer"}}), flush=True)
+if world > 1:
+    dist.destroy_process_group()
