@@ -15,6 +15,8 @@ struct RmsBwd {
   float coef;     // mean_j(g_j dy_j xh_j) (0 when clamped)
 };
 
+constexpr int COLSUM_CHUNKS = 32;  // row chunks of the two-level deterministic column sums
+
 // ------------------------------------------------------------------------------------------------------------
 // Loss + head backward: F = out(ln(x)[-A:]); loss = mean((F - target)^2) (score_wrappers.py:58-62).
 // One warp per action token: recomputes F from the saved final-ln output, writes dF (for the head weight gradient),
@@ -136,24 +138,40 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) head_bwd_kernel(const HeadBwdP
   }
 }
 
-// g_wout[a, :] = sum_tok dF[tok, a] * xnorm[row(tok), :],  g_bout[a] = sum_tok dF[tok, a]   (fixed order over tok)
-__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ dF, const float* __restrict__ xnorm,
-                                                         float* __restrict__ g_wout, float* __restrict__ g_bout, int B,
-                                                         int T, int A, int adim, int d) {
+// partial[chunk, a, :] = sum over the chunk's action tokens of dF[tok, a] * xnorm[row(tok), :]  (+ column d: dF sums)
+// grid (ceil((d+1)/256), adim, COLSUM_CHUNKS); finished by colsum_f32_kernel over the chunks.
+__global__ void __launch_bounds__(256) head_wgrad_partial_kernel(const float* __restrict__ dF, const float* __restrict__ xnorm,
+                                                                 float* __restrict__ partial, int B, int T, int A, int adim,
+                                                                 int d) {
+  pdl_trigger();
+  pdl_wait();
+  const int col = blockIdx.x * 256 + threadIdx.x;  // col == d is the bias column
+  const int a = blockIdx.y;
+  if (col > d) return;
+  const int n = B * A, per = (n + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
+  const int t0 = blockIdx.z * per, t1 = min(n, t0 + per);
+  float acc = 0.f;
+  for (int tok = t0; tok < t1; ++tok) {
+    const int row = (tok / A) * T + (T - A) + tok % A;
+    const float g = dF[tok * 8 + a];
+    acc = col < d ? fmaf(g, xnorm[static_cast<size_t>(row) * d + col], acc) : acc + g;
+  }
+  partial[(static_cast<size_t>(blockIdx.z) * adim + a) * (d + 1) + col] = acc;
+}
+// scatter the finished [adim, d+1] sums into out.weight [adim, d] and out.bias [adim]
+__global__ void __launch_bounds__(256) head_wgrad_finish_kernel(const float* __restrict__ partial, float* __restrict__ g_wout,
+                                                                float* __restrict__ g_bout, int adim, int d) {
   pdl_trigger();
   pdl_wait();
   const int col = blockIdx.x * 256 + threadIdx.x;
   const int a = blockIdx.y;
-  if (col >= d) return;
-  float acc = 0.f, accb = 0.f;
-  for (int tok = 0; tok < B * A; ++tok) {
-    const int row = (tok / A) * T + (T - A) + tok % A;
-    const float g = dF[tok * 8 + a];
-    acc = fmaf(g, xnorm[static_cast<size_t>(row) * d + col], acc);
-    accb += g;
-  }
-  g_wout[static_cast<size_t>(a) * d + col] = acc;
-  if (col == 0) g_bout[a] = accb;
+  if (col > d) return;
+  float acc = 0.f;
+  for (int i = 0; i < COLSUM_CHUNKS; ++i) acc += partial[(static_cast<size_t>(i) * adim + a) * (d + 1) + col];
+  if (col < d)
+    g_wout[static_cast<size_t>(a) * d + col] = acc;
+  else
+    g_bout[a] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -401,37 +419,70 @@ __global__ void __launch_bounds__(256) dc_reduce_kernel(const __nv_bfloat16* __r
   *reinterpret_cast<float4*>(dc + static_cast<size_t>(b) * d + col) = acc;
 }
 
-// out[c] (+)= sum_{i < n} part[i, c]   — deterministic column sum of per-row gradient contributions (norm gains)
-__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ part, int n, int cols,
+// Deterministic column sums over many rows, two levels: COLSUM_CHUNKS partial sums over contiguous row chunks (one CTA
+// per (256 columns, chunk): coalesced reads, fixed order inside the chunk), then a fixed-order sum over the chunks.
+
+// partial[chunk, c] = sum over the chunk's rows of part[row, c]      (fp32 per-row contributions, e.g. norm gains)
+__global__ void __launch_bounds__(256) colsum_f32_partial_kernel(const float* __restrict__ part, int n, int cols,
+                                                                 float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int per = (n + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
+  const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
+  float acc = 0.f;
+  for (int i = r0; i < r1; ++i) acc += part[static_cast<size_t>(i) * cols + c];
+  partial[static_cast<size_t>(blockIdx.y) * cols + c] = acc;
+}
+// out[c] = sum_chunk partial[chunk, c]
+__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ partial, int n, int cols,
                                                          float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= cols) return;
   float acc = 0.f;
-  for (int i = 0; i < n; ++i) acc += part[static_cast<size_t>(i) * cols + c];
+  for (int i = 0; i < n; ++i) acc += partial[static_cast<size_t>(i) * cols + c];
   out[c] = acc;
 }
 
-// Bias gradients: out[remap(c)] = sum over the problem's rows of src[row, c] (bf16). Grid (col blocks, problems).
-// swiglu_half > 0 un-interleaves the packed SwiGLU column order.
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int ld,
-                                                          const WgradProblem* __restrict__ problems, int cols_per_problem,
-                                                          int swiglu_half, float* __restrict__ out) {
+// Bias gradients from bf16 activations-gradients: grid (col blocks, chunks, problems); a problem is a row range
+// (an expert's token group, or all rows).  partial[(problem, chunk), c]
+__global__ void __launch_bounds__(256) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ src, int ld,
+                                                                  const WgradProblem* __restrict__ problems,
+                                                                  int cols_per_problem, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols_per_problem) return;
+  const WgradProblem pr = problems[blockIdx.z];
+  const int n = pr.k_blocks * 64;
+  const int per = (n + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
+  const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += __bfloat162float(src[static_cast<size_t>(pr.row0 + r) * ld + c]);
+  partial[(static_cast<size_t>(blockIdx.z) * COLSUM_CHUNKS + blockIdx.y) * cols_per_problem + c] = acc;
+}
+// out[out_row_base + remap(c)] = sum_chunk partial[(problem, chunk), c]; swiglu_half > 0 un-interleaves packed columns
+__global__ void __launch_bounds__(256) colsum_bf16_finish_kernel(const float* __restrict__ partial,
+                                                                 const WgradProblem* __restrict__ problems,
+                                                                 int cols_per_problem, int swiglu_half,
+                                                                 float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= cols_per_problem) return;
   const WgradProblem pr = problems[blockIdx.y];
   float acc = 0.f;
-  for (int r = 0; r < pr.k_blocks * 64; ++r) acc += __bfloat162float(src[static_cast<size_t>(pr.row0 + r) * ld + c]);
+  for (int i = 0; i < COLSUM_CHUNKS; ++i)
+    acc += partial[(static_cast<size_t>(blockIdx.y) * COLSUM_CHUNKS + i) * cols_per_problem + c];
   int oc = c;
   if (swiglu_half > 0) {
     const int blk = c / 256, in_blk = c % 256;
     oc = (in_blk < 128 ? 0 : swiglu_half) + blk * 128 + (in_blk % 128);
   }
-  // out_row_base counts weight rows of the problem == bias entries of the problem
-  out[pr.out_row_base + oc] = acc;
+  out[pr.out_row_base + oc] = acc;  // out_row_base counts weight rows of the problem == bias entries of the problem
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -616,12 +667,12 @@ struct RouterBwdParams {
   int B, T, E, K, Hd;
   int normalize;
 };
+// One CTA per sample: every warp recomputes the (tiny) per-expert prelude, the 2d hidden units are split over the CTA.
 __global__ void __launch_bounds__(ROW_WARPS * 32) router_bwd_kernel(const RouterBwdParams p) {
   pdl_trigger();
   pdl_wait();
-  const int b = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int b = blockIdx.x;
   const int lane = threadIdx.x & 31;
-  if (b >= p.B) return;
   // lane e owns expert e
   const float pe = lane < p.E ? p.probs[b * p.E + lane] : 0.f;
   float dwk = 0.f;   // d w for the slot whose expert is this lane
@@ -649,10 +700,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_bwd_kernel(const Router
   // softmax backward: d logit_e = p_e (dp_e - sum_j dp_j p_j)
   const float sdp = warp_sum(lane < p.E ? dp * pe : 0.f);
   const float dlog = lane < p.E ? pe * (dp - sdp) : 0.f;
-  if (lane < p.E) p.dlogit[b * p.E + lane] = dlog;
+  if (lane < p.E && threadIdx.x < 32) p.dlogit[b * p.E + lane] = dlog;
   // d hid = W2^T dlogit ; d z = d hid * gelu'(z)
   const float s = logf(load_sigma(p.sc, b)) / 4.0f;
-  for (int j = lane; j < p.Hd; j += 32) {
+  for (int j = threadIdx.x; j < p.Hd; j += ROW_WARPS * 32) {  // Hd is a multiple of 256: uniform trip count
     const float z = fmaf(s, p.ra[j], p.rb[j]);
     const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
     const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
@@ -703,24 +754,31 @@ struct EmbedBwdParams {
   float* g_wact;             // [d, adim]
   int B, T, S, A, adim, d;
 };
-// grid: (d / 256, 1 + A + 1): blockIdx.y < 1 + A -> position row y; last -> action_emb weight (+ bf16 copies)
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) {
+// grid (d / 256, A + 2, EMBED_BWD_CHUNKS): blockIdx.y <= A -> position row y; A + 1 -> action_emb weight (8 values per
+// column); blockIdx.z = chunk of samples. Partial sums go to `partial[chunk][y][col(*8)]`, finished by
+// embed_bwd_finish_kernel in a fixed order.
+constexpr int EMBED_BWD_CHUNKS = 16;
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p, float* __restrict__ partial) {
   pdl_trigger();
   pdl_wait();
   const int col = blockIdx.x * 256 + threadIdx.x;
   if (col >= p.d) return;
   const int y = blockIdx.y;
+  const int per = (p.B + EMBED_BWD_CHUNKS - 1) / EMBED_BWD_CHUNKS;
+  const int b0 = blockIdx.z * per, b1 = min(p.B, b0 + per);
+  // partial layout: [chunk][(A + 1) rows of d | d * 8 action-weight values]
+  float* mine = partial + static_cast<size_t>(blockIdx.z) * ((p.A + 1) * p.d + p.d * 8);
   if (y == 0) {  // goal token (t = 1): pos row 0
     float acc = 0.f;
-    for (int b = 0; b < p.B; ++b) {
+    for (int b = b0; b < b1; ++b) {
       const float g = p.dX[(static_cast<size_t>(b) * p.T + 1) * p.d + col];
       acc += g;
       p.dgoal[static_cast<size_t>(b) * p.d + col] = __float2bfloat16_rn(g);
     }
-    p.g_pos[col] = acc;
+    mine[col] = acc;
   } else if (y <= p.A) {  // pos row y: action j = y - 1, plus the image tokens for y == 1
     float acc = 0.f;
-    for (int b = 0; b < p.B; ++b) {
+    for (int b = b0; b < b1; ++b) {
       acc += p.dX[(static_cast<size_t>(b) * p.T + 2 + p.S + (y - 1)) * p.d + col];
       if (y == 1)
         for (int s = 0; s < p.S; ++s) {
@@ -729,11 +787,11 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
           p.dstate[(static_cast<size_t>(b) * p.S + s) * p.d + col] = __float2bfloat16_rn(g);
         }
     }
-    p.g_pos[static_cast<size_t>(y) * p.d + col] = acc;
+    mine[static_cast<size_t>(y) * p.d + col] = acc;
   } else {  // action_emb.weight[col, a] = sum_{b, j} dX[b, 2+S+j, col] * (c_in * noised[b, j, a])
     float acc[8];
     for (int a = 0; a < 8; ++a) acc[a] = 0.f;
-    for (int b = 0; b < p.B; ++b) {
+    for (int b = b0; b < b1; ++b) {
       const float sigma = load_sigma(p.sc, b);
       const float c_in = 1.0f / sqrtf(sigma * sigma + p.sc.sigma_data * p.sc.sigma_data);
       for (int j = 0; j < p.A; ++j) {
@@ -742,7 +800,29 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const EmbedBwdParams p) 
         for (int a = 0; a < p.adim; ++a) acc[a] = fmaf(g, a_in[a], acc[a]);
       }
     }
-    for (int a = 0; a < p.adim; ++a) p.g_wact[static_cast<size_t>(col) * p.adim + a] = acc[a];
+    for (int a = 0; a < 8; ++a) mine[static_cast<size_t>(p.A + 1) * p.d + static_cast<size_t>(col) * 8 + a] = acc[a];
+  }
+}
+// grid (d / 256, A + 2): sums the chunks and writes pos_emb / action_emb.weight gradients
+__global__ void __launch_bounds__(256) embed_bwd_finish_kernel(const float* __restrict__ partial, float* __restrict__ g_pos,
+                                                               float* __restrict__ g_wact, int A, int adim, int d) {
+  pdl_trigger();
+  pdl_wait();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= d) return;
+  const int y = blockIdx.y;
+  const size_t stride = static_cast<size_t>(A + 1) * d + static_cast<size_t>(d) * 8;
+  if (y <= A) {
+    float acc = 0.f;
+    for (int c = 0; c < EMBED_BWD_CHUNKS; ++c) acc += partial[c * stride + static_cast<size_t>(y) * d + col];
+    g_pos[static_cast<size_t>(y) * d + col] = acc;
+  } else {
+    for (int a = 0; a < adim; ++a) {
+      float acc = 0.f;
+      for (int c = 0; c < EMBED_BWD_CHUNKS; ++c)
+        acc += partial[c * stride + static_cast<size_t>(A + 1) * d + static_cast<size_t>(col) * 8 + a];
+      g_wact[static_cast<size_t>(col) * adim + a] = acc;
+    }
   }
 }
 
@@ -761,20 +841,31 @@ struct SigmaBwdParams {
   __nv_bfloat16* e1_bf16;   // [B (padded), d]
   int B, d;
 };
-__global__ void __launch_bounds__(256) sigma_bwd_kernel(const SigmaBwdParams p) {
+// grid (d / 256, B): de1[b, i] = sum_o dc[b, o] * W2[o, i]  (+ the bf16 operands of the W2 weight gradient)
+__global__ void __launch_bounds__(256) sigma_bwd_kernel(const SigmaBwdParams p, float* __restrict__ de1) {
   pdl_trigger();
   pdl_wait();
   const int i = blockIdx.x * 256 + threadIdx.x;  // input feature of sigma_linear
+  const int b = blockIdx.y;
+  if (i >= p.d) return;
+  const float s = logf(load_sigma(p.sc, b)) / 4.0f;
+  float acc = 0.f;
+  for (int o = 0; o < p.d; ++o) acc = fmaf(p.dc[static_cast<size_t>(b) * p.d + o], p.w2[static_cast<size_t>(o) * p.d + i], acc);
+  de1[static_cast<size_t>(b) * p.d + i] = acc;
+  p.dc_bf16[static_cast<size_t>(b) * p.d + i] = __float2bfloat16_rn(p.dc[static_cast<size_t>(b) * p.d + i]);
+  p.e1_bf16[static_cast<size_t>(b) * p.d + i] = __float2bfloat16_rn(fmaf(s, p.w1[i], p.b1[i]));
+}
+// g_w1[i] = sum_b de1[b, i] * s_b ; g_b1[i] = sum_b de1[b, i]   (fixed order over b)
+__global__ void __launch_bounds__(256) sigma_bwd_finish_kernel(const SigmaBwdParams p, const float* __restrict__ de1) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= p.d) return;
   float gw = 0.f, gb = 0.f;
   for (int b = 0; b < p.B; ++b) {
-    const float s = logf(load_sigma(p.sc, b)) / 4.0f;
-    float de1 = 0.f;
-    for (int o = 0; o < p.d; ++o) de1 = fmaf(p.dc[static_cast<size_t>(b) * p.d + o], p.w2[static_cast<size_t>(o) * p.d + i], de1);
-    gw = fmaf(de1, s, gw);
-    gb += de1;
-    p.dc_bf16[static_cast<size_t>(b) * p.d + i] = __float2bfloat16_rn(p.dc[static_cast<size_t>(b) * p.d + i]);
-    p.e1_bf16[static_cast<size_t>(b) * p.d + i] = __float2bfloat16_rn(fmaf(s, p.w1[i], p.b1[i]));
+    const float v = de1[static_cast<size_t>(b) * p.d + i];
+    gw = fmaf(v, logf(load_sigma(p.sc, b)) / 4.0f, gw);
+    gb += v;
   }
   p.g_w1[i] = gw;
   p.g_b1[i] = gb;
