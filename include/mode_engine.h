@@ -101,6 +101,11 @@ int mode_grad_buffer(mode_engine_t* e, float** grads_dev, int64_t* numel);
 /* Element offset and size of the gradient of the reference parameter `name` inside the flat buffer (reference tensor
  * layout, contiguous). */
 int mode_grad_offset(mode_engine_t* e, const char* name, int64_t* offset, int64_t* numel);
+/* Makes `stream` wait (cudaStreamWaitEvent, no host sync) until the most recent mode_train_step has finished writing the
+ * gradients of block `layer` (its backward runs last-to-first), or all gradients when layer == -1. This is what lets a
+ * data-parallel caller all-reduce layer l's sections on a side stream while layers l-1..0 are still in backward — the
+ * role of DDP's bucketed reducer hooks in the reference (mode/training_calvin.py:97, DDPStrategy). */
+int mode_train_wait_grads(mode_engine_t* e, int layer, void* stream);
 
 /* sample_ddim (gc_sampling.py:922-951) over GCDenoiser: x_inout_dev (B, action_seq_len, action_dim) holds the initial
  * noise (randn * sigma_max, drawn by the caller as in mode_agent.py:756) and receives the denoised actions.

@@ -184,6 +184,16 @@ class ModeEngine:
         _lib.check(self.lib.mode_grad_offset(self._h, name.encode(), C.byref(off), C.byref(n)))
         return self.flat_grads()[off.value: off.value + n.value].view(*shape)
 
+    def grad_range(self, name: str) -> tuple[int, int]:
+        """(element offset, numel) of `name`'s gradient inside the flat buffer."""
+        off, n = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.mode_grad_offset(self._h, name.encode(), C.byref(off), C.byref(n)))
+        return off.value, n.value
+
+    def wait_grads(self, layer: int, stream: "torch.cuda.Stream") -> None:
+        """Make `stream` wait until the last train_step finished block `layer`'s gradients (-1: all gradients)."""
+        _lib.check(self.lib.mode_train_wait_grads(self._h, layer, C.c_void_p(stream.cuda_stream)))
+
     def sample_ddim(self, state, x, goal, sigmas) -> torch.Tensor:
         """sample_ddim over GCDenoiser (whole loop = one CUDA graph). `sigmas` includes the trailing 0. Returns actions."""
         state, goal, x, _, _, B = self._prep(state, goal, x, None)

@@ -14,6 +14,7 @@ from typing import Optional
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .engine import EngineConfig, ModeEngine
 
@@ -302,6 +303,49 @@ class MoDeDiT(nn.Module):
                                reset_expert_stats: bool = True):
         if freeze_routers:
             self.freeze_router()
+
+    # ---- auxiliary router losses (reference modedit.py:584-593, :898-969; weights are 0.0 in conf/model/mode_agent.yaml)
+    def _router_aux(self):
+        """Per-layer (shifted logits, clamped softmax) of the last `loss` call's sigma rows, recomputed with torch ops
+        from the fp32 masters so they carry autograd history to the router / sigma-embedding parameters. The router
+        sees only the sigma embedding (reference modedit.py:330-331), so this is B rows x a d->2d->E MLP per layer:
+        not hot-path work. The top-k mask itself comes from the engine (`routing`), so both agree on the selection."""
+        sigma = getattr(self, "_last_sigma", None)
+        if sigma is None:
+            raise RuntimeError("MoDE engine: auxiliary router losses need a preceding GCDenoiser.loss call")
+        s = (sigma.float().log() / 4).reshape(-1, 1)
+        c = F.linear(F.linear(s, self.sigma_emb.weight, self.sigma_emb.bias), self.sigma_linear.weight)
+        outs = []
+        for blk in self.blocks:
+            mlp = blk.router.router.mlp
+            logits = F.linear(F.gelu(F.linear(c, mlp[0].weight, mlp[0].bias)), mlp[3].weight, mlp[3].bias)
+            logits = logits - logits.max(dim=-1, keepdim=True).values  # / temperature (1.0), reference :345
+            probs = torch.clamp(torch.softmax(logits, dim=-1), min=1e-9, max=1 - 1e-9)
+            outs.append((logits, probs))
+        return outs
+
+    def load_balancing_loss(self):
+        """Mean over layers of E * sum_e mean(router_probs_e) * mean(mask_e) (reference modedit.py:584-593, :898-928).
+        All T tokens of a sample share one routing row, so token means equal sample means."""
+        total = 0.0
+        aux = self._router_aux()
+        B = aux[0][0].shape[0]
+        for layer, (_, probs) in enumerate(aux):
+            idx = torch.from_numpy(self._engine.routing(layer, B)[0]).long().to(probs.device)
+            mask = torch.zeros_like(probs).scatter_(1, idx, 1.0)
+            rp = probs * mask
+            if self.blocks[layer].router.normalize:
+                rp = rp / rp.sum(dim=-1, keepdim=True)
+            total = total + probs.shape[-1] * (rp.mean(dim=0) * mask.mean(dim=0)).sum()
+        return total / len(aux)
+
+    def compute_router_z_loss(self, eps=1e-6):
+        """Mean over layers and rows of log(sum_e exp(logit_e) + eps)^2 on the max-shifted logits (reference :930-969)."""
+        aux = self._router_aux()
+        total = 0.0
+        for logits, _ in aux:
+            total = total + torch.log(torch.exp(logits).sum(dim=-1) + eps).pow(2).mean()
+        return total / len(aux)
 
     def routing(self, layer: int, batch: int):
         """(top_k_indices, renormalised probs, clamped softmax) of the most recent call for `layer`."""

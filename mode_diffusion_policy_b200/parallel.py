@@ -1,6 +1,13 @@
-"""Data-parallel host logic for inference: trajectories are independent, so the batch is sharded
-across ranks with NO data-path collective; torch.distributed is only used for the timing barrier, the max-over-ranks
-reduction of device times and (optionally) gathering the (B, 10, 7) action chunks for a single caller."""
+"""Data-parallel host logic.
+
+Inference: trajectories are independent, so the batch is sharded across ranks with NO data-path collective;
+torch.distributed is only used for the timing barrier, the max-over-ranks reduction of device times and (optionally)
+gathering the (B, 10, 7) action chunks for a single caller.
+
+Training: the one exchange step is the all-reduce (mean) of the engine's flat gradient buffer. `GradAllReduce` issues it
+bucketed by layer on a side stream, gated by the engine's per-layer "gradients final" events, so NCCL moves layer l's
+weight gradients over NVLink while the backward of layers l-1..0 is still running (what DDP's reducer hooks do in the
+reference, mode/training_calvin.py:97)."""
 from __future__ import annotations
 
 import torch
@@ -45,3 +52,70 @@ def aggregate_throughput(units_per_rank: float, ms_local: float, device) -> tupl
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     (ms,) = max_over_ranks([ms_local], device)
     return world * units_per_rank / (ms * 1e-3), ms
+
+
+def plan_grad_buckets(ranges_per_layer: list[list[tuple[int, int]]], total: int, min_bucket: int = 1 << 20):
+    """Bucket plan for the overlapped gradient all-reduce.
+
+    ranges_per_layer[l] = (offset, numel) of every gradient tensor of block l inside a flat buffer of `total` elements.
+    Adjacent tensors are merged; merged spans of at least `min_bucket` elements become per-layer buckets (reduced as
+    soon as that layer's backward is done); everything else — small tensors and the non-block parameters — is covered
+    by `tail` spans reduced once at the end. Returns (layer_buckets, tail); together they tile [0, total) exactly once
+    (alignment gaps between sections ride along with the tail: they are never written and stay zero)."""
+    def merge(spans):
+        out = []
+        for off, n in sorted(spans):
+            if n == 0:
+                continue
+            if out and out[-1][0] + out[-1][1] == off:
+                out[-1] = (out[-1][0], out[-1][1] + n)
+            else:
+                out.append((off, n))
+        return out
+
+    layer_buckets = [[sp for sp in merge(r) if sp[1] >= min_bucket] for r in ranges_per_layer]
+    big = sorted(sp for lb in layer_buckets for sp in lb)
+    tail, cur = [], 0
+    for off, n in big:
+        if off < cur:
+            raise ValueError("overlapping gradient ranges")
+        if off > cur:
+            tail.append((cur, off - cur))
+        cur = off + n
+    if cur < total:
+        tail.append((cur, total - cur))
+    return layer_buckets, tail
+
+
+class GradAllReduce:
+    """Overlapped data-parallel gradient averaging for the engine's training step.
+
+        reducer = GradAllReduce(engine, [n for n, _ in inner.named_parameters()], n_layers)
+        loss, _ = model.loss(...)      # enqueues forward + backward (no host sync)
+        reducer.run()                  # per-layer buckets on the side stream, then the tail; main stream waits
+        loss.backward(); opt.step()
+    """
+
+    def __init__(self, engine, param_names, n_layers: int, group=None, min_bucket: int = 1 << 20):
+        self.engine, self.group, self.n_layers = engine, group, n_layers
+        per_layer = [[] for _ in range(n_layers)]
+        for name in param_names:
+            if name.startswith("blocks."):
+                per_layer[int(name.split(".")[1])].append(engine.grad_range(name))
+        self.flat = engine.flat_grads()
+        self.layer_buckets, self.tail = plan_grad_buckets(per_layer, self.flat.numel(), min_bucket)
+        self.stream = torch.cuda.Stream(device=self.flat.device)
+
+    def run(self) -> None:
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        main = torch.cuda.current_stream(self.flat.device)
+        with torch.cuda.stream(self.stream):
+            for layer in range(self.n_layers - 1, -1, -1):  # the backward finishes the last block first
+                self.engine.wait_grads(layer, self.stream)
+                for off, n in self.layer_buckets[layer]:
+                    dist.all_reduce(self.flat[off: off + n], op=dist.ReduceOp.AVG, group=self.group)
+            self.engine.wait_grads(-1, self.stream)
+            for off, n in self.tail:
+                dist.all_reduce(self.flat[off: off + n], op=dist.ReduceOp.AVG, group=self.group)
+        main.wait_stream(self.stream)

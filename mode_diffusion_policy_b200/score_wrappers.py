@@ -93,6 +93,7 @@ class GCDenoiser(nn.Module):
         engine applies neither dropout nor multinomial routing; see MoDeDiT.check_trainable)."""
         m = self.inner_model
         goal = m._goals(goal, False)
+        m._last_sigma = sigma.detach()  # for the auxiliary router losses (MoDeDiT.load_balancing_loss / z-loss)
         if m.training and torch.is_grad_enabled():
             m.check_trainable()
             params = [p for _, p in m.named_parameters()]

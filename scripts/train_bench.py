@@ -45,18 +45,22 @@ S, G = torch.from_numpy(state).cuda(), torch.from_numpy(goal).cuda()
 A_ = torch.from_numpy((x0 / np.float32(80.0)).astype(np.float32)).cuda()
 noise = torch.from_numpy(rng.standard_normal(x0.shape).astype(np.float32)).cuda()
 sigma = torch.from_numpy(np.exp(rng.uniform(np.log(1e-3), np.log(80.0), B)).astype(np.float32)).cuda()
-eng = None
+ap_overlap = os.environ.get("MODE_TRAIN_OVERLAP", "1") == "1"
+reducer = None
 
 
 def step():
-    global eng
+    global reducer
     opt.zero_grad(set_to_none=True)
     loss, _ = model.loss({"state_images": S}, A_, G, noise, sigma)
-    eng = inner._engine
-    if world > 1:  # ONE all-reduce over the engine's flat gradient buffer, before autograd hands out the views
-        flat = eng.flat_grads()
-        dist.all_reduce(flat)
-        flat.div_(world)
+    if world > 1:  # average the engine's flat gradient buffer before autograd hands out the views
+        if ap_overlap:  # per-layer buckets on a side stream, overlapped with the rest of the backward
+            if reducer is None:
+                reducer = parallel.GradAllReduce(inner._engine, [n for n, _ in inner.named_parameters()
+                                                                 if n != "gripper_embed.weight"], a.layers)
+            reducer.run()
+        else:  # one blocking all-reduce after the backward
+            dist.all_reduce(inner._engine.flat_grads(), op=dist.ReduceOp.AVG)
     loss.backward()
     opt.step()
     return loss
@@ -83,6 +87,6 @@ if rank == 0:
                       "global_batch": world * B, "dtype": "bf16", "data": "synthetic", "loss": float(loss),
                       "approx_tflops": 3 * fwd_flops * a.steps / (ms * 1e-3) / 1e12,
                       "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack",
-                                 "grad_allreduce": "one NCCL all-reduce over the flat fp32 gradient buffer"}}), flush=True)
+                                 "grad_allreduce": ("per-layer NCCL all-reduce buckets of the flat fp32 gradient buffer, overlapped with backward" if ap_overlap else "one NCCL all-reduce over the flat fp32 gradient buffer")}}), flush=True)
 if world > 1:
     dist.destroy_process_group()

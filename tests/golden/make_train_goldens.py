@@ -42,8 +42,16 @@ def golden_train(tag, cfg, B, router_gain=30.0):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
     with torch.enable_grad():
         loss, f_out = model.loss({"state_images": t(state)}, t(acts), t(goal), t(g["loss_noise"]), t(g["sigma_het"]))
+        # auxiliary router losses of the same forward (modedit.py:898-969) and their gradients
+        lb, zl = inner.load_balancing_loss(), inner.compute_router_z_loss()
+        aux_names = [n for n, _ in inner.named_parameters() if "router" in n or n.startswith("sigma_")]
+        aux_params = [dict(inner.named_parameters())[n] for n in aux_names]
+        aux_grads = torch.autograd.grad(lb + zl, aux_params, retain_graph=True, allow_unused=True)
         loss.backward()
-    out = {"loss": np.float32(loss.item()), "F": f_out.detach().numpy()}
+    out = {"loss": np.float32(loss.item()), "F": f_out.detach().numpy(), "aux_lb": np.float32(lb.item()),
+           "aux_z": np.float32(zl.item())}
+    for n, gr in zip(aux_names, aux_grads):
+        out[f"auxnorm/{n}"] = np.float32(0.0 if gr is None else np.linalg.norm(gr.numpy().astype(np.float64)))
     assert abs(float(loss) - float(g["loss_value"])) < 1e-5 * abs(float(loss)), "train-mode loss differs from eval-mode"
     names = [n for n, _ in O.state_dict_spec(cfg)]
     params = dict(inner.named_parameters())

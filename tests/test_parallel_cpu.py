@@ -53,3 +53,56 @@ def _worker(rank, world, port, total):
 def test_two_rank_sharding_and_timing_reduction(total):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, total), nprocs=2, join=True)
+
+
+def _layout(L=3, d=8):
+    """A flat buffer laid out by tensor kind (all layers of one kind contiguous), like the engine's gradient buffer."""
+    kinds = [("w_big", 40 * d), ("bias", d), ("w_mid", 10 * d), ("gain", d)]
+    off, per_layer = 0, [[] for _ in range(L)]
+    for _, n in kinds:
+        for l in range(L):
+            per_layer[l].append((off + l * n, n))
+        off += L * n
+        off = (off + 31) // 32 * 32  # sections are 128-byte aligned
+    top_level = off  # non-block parameters live after the block sections
+    return per_layer, off + 100, top_level
+
+
+def test_grad_bucket_plan_tiles_the_flat_buffer_exactly_once():
+    per_layer, total, _ = _layout()
+    buckets, tail = P.plan_grad_buckets(per_layer, total, min_bucket=64)
+    assert all(len(b) == 2 for b in buckets)  # w_big and w_mid of each layer; biases and gains ride in the tail
+    seen = torch.zeros(total, dtype=torch.int32)
+    for off, n in [sp for b in buckets for sp in b] + tail:
+        seen[off: off + n] += 1
+    assert bool((seen == 1).all())
+    # adjacent tensors of one layer merge into a single bucket (q, k, v weights are contiguous in the engine)
+    merged, _ = P.plan_grad_buckets([[(0, 50), (50, 50), (100, 28)]], 128, min_bucket=100)
+    assert merged == [[(0, 128)]]
+    with pytest.raises(ValueError):
+        P.plan_grad_buckets([[(0, 100)], [(50, 100)]], 200, min_bucket=10)
+
+
+def _bucket_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        per_layer, total, _ = _layout()
+        buckets, tail = P.plan_grad_buckets(per_layer, total, min_bucket=64)
+        grads = [torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+        flat = grads[rank].clone()
+        for layer in range(len(buckets) - 1, -1, -1):  # same order GradAllReduce issues them in
+            for off, n in buckets[layer]:
+                dist.all_reduce(flat[off: off + n])
+        for off, n in tail:
+            dist.all_reduce(flat[off: off + n])
+        flat /= world  # gloo has no AVG
+        want = torch.stack(grads).sum(0) / world
+        assert torch.allclose(flat, want, rtol=0, atol=1e-6)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_gradient_average_equals_mean():
+    mp.spawn(_bucket_worker, args=(2, _free_port()), nprocs=2, join=True)

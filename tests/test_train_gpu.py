@@ -113,3 +113,39 @@ def test_autograd_integration_and_optimizer_step():
         loss.backward()
         losses.append(float(loss))
     assert losses[-1] < 0.9 * losses[0], losses
+
+
+@pytest.mark.parametrize("tag", list(MODELS))
+def test_auxiliary_router_losses_match_reference(tag):
+    """load_balancing_loss / compute_router_z_loss (reference modedit.py:898-969) after a training-mode loss call:
+    values and gradient norms against the reference's autograd goldens. The routing mask comes from the engine, the
+    differentiable part is a B-row torch recompute of the router from the fp32 masters, so agreement is fp32-tight."""
+    from mode_diffusion_policy_b200.modedit import MoDeDiT
+    from mode_diffusion_policy_b200.score_wrappers import GCDenoiser
+
+    cfg, B = MODELS[tag]
+    g = np.load(GOLD / f"{tag}.npz")
+    gt = np.load(GOLD / f"train_{tag}.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cuda", goal_conditioned=True, action_dim=7,
+                    embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=0.0, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                    goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7, mlp_pdrop=0.0, goal_drop=0.0,
+                    num_experts=cfg.num_experts, top_k=cfg.top_k, use_argmax=True, max_batch=8)
+    inner.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = GCDenoiser(inner, sigma_data=0.5).cuda().train()
+    acts = cu((x0 / np.float32(80.0)).astype(np.float32))
+    loss, _ = model.loss({"state_images": cu(state)}, acts, cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
+    lb, zl = inner.load_balancing_loss(), inner.compute_router_z_loss()
+    assert abs(float(lb) - float(gt["aux_lb"])) <= 1e-4 * abs(float(gt["aux_lb"])), (float(lb), float(gt["aux_lb"]))
+    assert abs(float(zl) - float(gt["aux_z"])) <= 1e-3 * abs(float(gt["aux_z"])) + 1e-6, (float(zl), float(gt["aux_z"]))
+    names = [n for n, _ in inner.named_parameters() if "router" in n or n.startswith("sigma_")]
+    params = dict(inner.named_parameters())
+    grads = torch.autograd.grad(lb + zl, [params[n] for n in names], allow_unused=True, retain_graph=True)
+    for n, gr in zip(names, grads):
+        want = float(gt[f"auxnorm/{n}"])
+        got = 0.0 if gr is None else float(gr.double().norm())
+        assert abs(got - want) <= 2e-3 * want + 1e-7, (n, got, want)
+    # the total loss (action + weighted aux) back-propagates in one call, as training_step does (mode_agent.py:408-420)
+    (loss + 0.01 * lb + 0.001 * zl).backward()
+    assert params["blocks.0.router.router.mlp.3.weight"].grad is not None
