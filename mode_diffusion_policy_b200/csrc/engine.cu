@@ -18,6 +18,7 @@
 #include "attention.cuh"
 #include "gemm.cuh"
 #include "gemm_wgrad.cuh"
+#include "mlp_fused.cuh"
 #include "rowwise.cuh"
 #include "backward.cuh"
 
@@ -158,6 +159,8 @@ struct mode_engine {
   int perm_rows, max_tiles;
   float inv_sqrt_d, inv_sqrt_dh;
   bool pair;   // CTA-pair GEMM kernel (MODE_GEMM_CTA_PAIR, default on)
+  bool mlp_fused;  // expert up+down projections as one dynamically scheduled launch (MODE_MLP_FUSED=1, default off; needs pair)
+  int* mlp_sync;   // its tile queue head + per-M-tile dependency counters
   int tile_m;  // rows per M-tile: 256 with CTA pairs, 128 otherwise
   bool finalized = false;
   std::map<std::string, WeightSpec> specs;
@@ -324,6 +327,7 @@ static int set_kernel_attrs() {
   RET_IF(gemm_set_attr<EPI_PLAIN_F32>());
   RET_IF(gemm_set_attr<EPI_SWIGLU_SAVE>());
   CU_OK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CU_OK(cudaFuncSetAttribute(mlp_fused_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
   g_attr_done = 1;
   return MODE_OK;
 }
@@ -464,6 +468,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
     const char* env = getenv("MODE_GEMM_CTA_PAIR");
     e->pair = env ? atoi(env) != 0 : true;
     e->tile_m = e->pair ? 256 : 128;
+    env = getenv("MODE_MLP_FUSED");
+    e->mlp_fused = e->pair && (env ? atoi(env) != 0 : false);  // measured +1.5 % only: opt-in
   }
   e->max_tiles = (K * e->maxM + e->tile_m - 1) / e->tile_m + E;
   e->perm_rows = e->max_tiles * e->tile_m;
@@ -540,6 +546,7 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(dev_alloc(e, &e->dense_counts, 3));
   A_(dev_alloc(e, &e->sk_partials, (size_t)e->num_sms * 8 * 8 * 128, false));
   A_(dev_alloc(e, &e->sk_flags, (size_t)e->num_sms * 4));
+  A_(dev_alloc(e, &e->mlp_sync, (size_t)1 + e->max_tiles));
   A_(dev_alloc(e, &e->usage, (size_t)L * E));
   A_(dev_alloc(e, &e->tokens, (size_t)L));
   // tensor maps
@@ -823,6 +830,9 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   Ln2Params n2;
   n2.x = io.x1; n2.x_out = io.xn; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + lt * B * e->K; n2.perm = io.perm;
   n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
+  const bool fused_mlp = e->mlp_fused && !io.z;  // the training forward keeps the two-launch path (it saves z)
+  n2.zero = fused_mlp ? e->mlp_sync : nullptr;
+  n2.n_zero = 1 + e->max_tiles;
   {
     ProfScope ps(e, st, PC_LN2);
     LAUNCH_ROW_KERNEL(ln2_permute_kernel, d, row_blocks(M), st, n2);
@@ -830,22 +840,36 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   CU_OK(cudaGetLastError());
   p = gemm_params(io.tm_perm, e->tm_wup, io.to_h, e->up_tiles + lt * e->max_tiles, e->num_tiles + lt, 8 * d, d,
                   e->b_up);
-  enable_stream_k(e, p);
-  {
+  GemmParams pd = gemm_params(io.tm_h, e->tm_wdown, io.to_y, e->down_tiles + lt * e->max_tiles, e->num_tiles + lt, d, e->F,
+                              nullptr);
+  if (fused_mlp) {
+    // up-projection + SwiGLU and down-projection from one dynamic tile queue (mlp_fused.cuh); reported as PC_UP
     ProfScope ps(e, st, PC_UP);
-    if (io.z) {  // training: also keep the pre-activations for the SwiGLU backward
-      p.tmap_out2 = io.to_z;
-      RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
-    } else {
-      RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
+    MlpParams mp;
+    mp.up = p;
+    mp.down = pd;
+    mp.sync = e->mlp_sync;
+    {
+      const char* env = getenv("MODE_MLP_FLAGS");
+      mp.flags = env ? atoi(env) : (1 | (18 << 8));  // deferred signalling, down tiles queued 18 M-tiles behind
     }
-  }
-  p = gemm_params(io.tm_h, e->tm_wdown, io.to_y, e->down_tiles + lt * e->max_tiles, e->num_tiles + lt, d, e->F,
-                  nullptr);
-  enable_stream_k(e, p);
-  {
-    ProfScope ps(e, st, PC_DOWN);
-    RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, p));
+    CU_OK(launch_k(mlp_fused_2cta_kernel, dim3(e->num_sms & ~1), dim3(GEMM_THREADS), G2_SMEM_BYTES, st, mp));
+  } else {
+    enable_stream_k(e, p);
+    {
+      ProfScope ps(e, st, PC_UP);
+      if (io.z) {  // training: also keep the pre-activations for the SwiGLU backward
+        p.tmap_out2 = io.to_z;
+        RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
+      } else {
+        RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
+      }
+    }
+    enable_stream_k(e, pd);
+    {
+      ProfScope ps(e, st, PC_DOWN);
+      RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
+    }
   }
   CombineParams c;
   c.x = io.xn; c.x_out = io.x_out; c.x_copy = io.x_out_copy; c.y = io.y;
@@ -858,7 +882,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     LAUNCH_ROW_KERNEL(combine_kernel, d, row_blocks(M), st, c);
   }
   CU_OK(cudaGetLastError());
-  e->launch_count += 7;
+  e->launch_count += fused_mlp ? 6 : 7;
   return MODE_OK;
 }
 

@@ -478,11 +478,15 @@ struct Ln2Params {
   int B, T, K, d;
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
+  int* zero;         // tile queue + dependency counters of the fused expert-MLP kernel that follows (or null)
+  int n_zero;
 };
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln2Params p) {
   pdl_trigger();
   pdl_wait();
+  if (blockIdx.x == 0 && p.zero)
+    for (int i = threadIdx.x; i < p.n_zero; i += ROW_WARPS * 32) p.zero[i] = 0;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;

@@ -237,3 +237,22 @@ def test_module_surface_samplers_and_policy():
         inner.out.bias.add_(1.0)
     F2 = inner({"state_images": cu(state)}, cu(x0 / np.float32(80.0)), cu(goal), cu(g["sigma_het"]))
     np.testing.assert_allclose((F2 - F).cpu().numpy(), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["model_tiny_d256_l3_e4", "model_wide_d512_l2_e8"])
+def test_fused_expert_mlp_kernel_is_bit_identical(tag, monkeypatch):
+    """MODE_MLP_FUSED=1 (csrc/mlp_fused.cuh: up- and down-projection tiles from one dynamic queue with per-M-tile
+    dependency counters) must reproduce the two-launch path bit for bit: same tiles, same k order, other schedule."""
+    cfg, B = MODELS[tag]
+    g = np.load(GOLD / f"{tag}.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    outs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("MODE_MLP_FUSED", fused)
+        eng = engine_for(cfg, sd, 8)
+        den = eng.denoise(cu(state), cu(g["denoise_x"]), cu(goal), cu(g["sigma_het"]))  # per-sample sigma: ragged groups
+        smp = eng.sample_ddim(cu(state), cu(x0), cu(goal), O.get_sigmas_exponential(10, 1e-3, 80.0))
+        outs.append((den.clone(), smp.clone()))
+        del eng
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
