@@ -101,6 +101,10 @@ int mode_grad_buffer(mode_engine_t* e, float** grads_dev, int64_t* numel);
 /* Element offset and size of the gradient of the reference parameter `name` inside the flat buffer (reference tensor
  * layout, contiguous). */
 int mode_grad_offset(mode_engine_t* e, const char* name, int64_t* offset, int64_t* numel);
+/* Gradients of the last mode_train_step's loss w.r.t. its inputs: dstate_dev (B, n_state_tokens, obs_dim) and dgoal_dev
+ * (B, goal_dim), fp32, either may be NULL. In the reference these flow on into the FiLM-ResNet encoders that produce
+ * perceptual_emb (mode_agent.py:405-411, compute_input_embeddings :513-582); bf16 tensor-core operands like the rest. */
+int mode_train_input_grads(mode_engine_t* e, float* dstate_dev, float* dgoal_dev, int B, void* stream);
 /* Makes `stream` wait (cudaStreamWaitEvent, no host sync) until the most recent mode_train_step has finished writing the
  * gradients of block `layer` (its backward runs last-to-first), or all gradients when layer == -1. This is what lets a
  * data-parallel caller all-reduce layer l's sections on a side stream while layers l-1..0 are still in backward — the

@@ -901,4 +901,19 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const __nv_bfloat16* __
   out[idx] = acc;
 }
 
+// Generic data gradient dx[r, i] = sum_o dy[r, o] * w[o, i] (w = nn.Linear weight [d_out, n_in], bf16) for input widths
+// the tensor-core kernel does not tile (small test configurations).
+__global__ void __launch_bounds__(256) dgrad_simt_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ w,
+                                                         float* __restrict__ dx, int rows, int d_out, int n_in) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t idx = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
+  if (idx >= static_cast<size_t>(rows) * n_in) return;
+  const int r = static_cast<int>(idx / n_in), i = static_cast<int>(idx % n_in);
+  float acc = 0.f;
+  for (int o = 0; o < d_out; ++o)
+    acc = fmaf(__bfloat162float(dy[static_cast<size_t>(r) * d_out + o]), __bfloat162float(w[static_cast<size_t>(o) * n_in + i]), acc);
+  dx[idx] = acc;
+}
+
 }  // namespace mode

@@ -201,6 +201,8 @@ struct mode_engine {
   int64_t launch_count = 0;
   LayerIO io;                   // inference buffer set (rebuilt by ensure_batch)
   bool train_weights_dirty = true;  // transposed weight copies of the training path are stale
+  cudaEvent_t weights_ready = nullptr;  // recorded on the default stream after the last (re)pack
+  bool weights_wait_pending = false;
   TrainState* train = nullptr;  // lazily created by the first training call
 
   // optional per-kernel-class timing (mode_profile_eval): event pairs around every launch of one evaluation
@@ -419,6 +421,7 @@ extern "C" void mode_destroy(mode_engine_t* e) {
   destroy_train(e->train);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->weights_ready) cudaEventDestroy(e->weights_ready);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
 }
@@ -660,15 +663,24 @@ extern "C" int mode_finalize_weights(mode_engine_t* e) {
     matvec_f64_kernel<<<(Hd + 7) / 8, 256>>>(W1, e->sig_v, e->r_b1 + (size_t)l * Hd, e->r_b + (size_t)l * Hd, Hd, d);
   }
   CU_OK(cudaGetLastError());
-  CU_OK(cudaStreamSynchronize(nullptr));
+  // no host synchronisation: host-source weights were already synchronised in mode_set_weight, device-source packing is
+  // stream-ordered; the first call on another stream waits for this event (ensure_batch)
+  if (!e->weights_ready) CU_OK(cudaEventCreateWithFlags(&e->weights_ready, cudaEventDisableTiming));
+  CU_OK(cudaEventRecord(e->weights_ready, nullptr));
+  e->weights_wait_pending = true;
   e->finalized = true;
   return MODE_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ batch tables
-static int ensure_batch(mode_engine* e, int B) {
+static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
   if (B < 1 || B > e->maxB) return fail(MODE_ERR_INVALID, "batch %d outside [1, max_batch=%d]", B, e->maxB);
   if (!e->finalized) return fail(MODE_ERR_STATE, "mode_finalize_weights has not been called");
+  if (e->weights_wait_pending) {
+    // weights were (re)packed on the default stream without host synchronisation: order this stream after them
+    CU_OK(cudaStreamWaitEvent(st, e->weights_ready, 0));
+    e->weights_wait_pending = false;
+  }
   if (B == e->cur_B) return MODE_OK;
   std::vector<GemmMTile> tiles(3 * (size_t)e->dense_cap);
   int counts[3];
@@ -933,7 +945,7 @@ static int eval_common(mode_engine* e, const float* state_dev, const float* goal
                        int head_mode) {
   if (!e || !state_dev || !goal_dev || !actions_dev || !sigma_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
   if (sigma_stride != 0 && sigma_stride != 1) return fail(MODE_ERR_INVALID, "sigma_stride must be 0 or 1");
-  RET_IF(ensure_batch(e, B));
+  RET_IF(ensure_batch(e, B, reinterpret_cast<cudaStream_t>(stream)));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   e->launch_count = 0;
   RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
@@ -987,7 +999,7 @@ extern "C" int mode_loss(mode_engine_t* e, const float* state_dev, const float* 
                          void* stream) {
   if (!e || !state_dev || !goal_dev || !action_dev || !noise_dev || !sigma_dev || !loss_dev)
     return fail(MODE_ERR_INVALID, "null argument");
-  RET_IF(ensure_batch(e, B));
+  RET_IF(ensure_batch(e, B, reinterpret_cast<cudaStream_t>(stream)));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   e->launch_count = 0;
   const int per = e->A * e->adim, n = B * per;
@@ -1053,7 +1065,7 @@ extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const 
   if (n < 1 || n > 64) return fail(MODE_ERR_INVALID, "number of sampling steps must be in [1, 64]");
   for (int i = 0; i < n; ++i)
     if (!(sigmas_host[i] > 0.f)) return fail(MODE_ERR_INVALID, "sigmas[%d] must be > 0", i);
-  RET_IF(ensure_batch(e, B));
+  RET_IF(ensure_batch(e, B, reinterpret_cast<cudaStream_t>(stream)));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   e->launch_count = 0;
   cudaGraphExec_t exec = nullptr;
@@ -1076,7 +1088,7 @@ extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const 
 extern "C" int mode_sample_ddim_host(mode_engine_t* e, const float* state_host, const float* goal_host,
                                      float* x_inout_host, const float* sigmas_host, int n_plus_1, int B, void* stream) {
   if (!e || !state_host || !goal_host || !x_inout_host) return fail(MODE_ERR_INVALID, "null argument");
-  RET_IF(ensure_batch(e, B));
+  RET_IF(ensure_batch(e, B, reinterpret_cast<cudaStream_t>(stream)));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t n_state = (size_t)B * e->S * e->obs, n_goal = (size_t)B * e->gdim, n_x = (size_t)B * e->A * e->adim;
   CU_OK(cudaMemcpyAsync(e->in_state, state_host, n_state * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -1092,7 +1104,7 @@ extern "C" int mode_block_forward(mode_engine_t* e, int layer, const float* x_de
                                   int B, void* stream) {
   if (!e || !x_dev || !c_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
   if (layer < 0 || layer >= e->L) return fail(MODE_ERR_INVALID, "layer %d out of range", layer);
-  RET_IF(ensure_batch(e, B));
+  RET_IF(ensure_batch(e, B, reinterpret_cast<cudaStream_t>(stream)));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   e->launch_count = 0;
   const int d = e->d, M = B * e->T;

@@ -190,6 +190,14 @@ class ModeEngine:
         _lib.check(self.lib.mode_grad_offset(self._h, name.encode(), C.byref(off), C.byref(n)))
         return off.value, n.value
 
+    def input_grads(self, B: int, state_shape, goal_shape, want_state=True, want_goal=True):
+        """d loss / d state_images and d loss / d goal of the last train_step (fp32 tensors, or None if not wanted)."""
+        ds = torch.empty(state_shape, dtype=torch.float32, device=self.device) if want_state else None
+        dg = torch.empty(goal_shape, dtype=torch.float32, device=self.device) if want_goal else None
+        _lib.check(self.lib.mode_train_input_grads(self._h, ds.data_ptr() if want_state else None,
+                                                   dg.data_ptr() if want_goal else None, B, self._stream()))
+        return ds, dg
+
     def wait_grads(self, layer: int, stream: "torch.cuda.Stream") -> None:
         """Make `stream` wait until the last train_step finished block `layer`'s gradients (-1: all gradients)."""
         _lib.check(self.lib.mode_train_wait_grads(self._h, layer, C.c_void_p(stream.cuda_stream)))

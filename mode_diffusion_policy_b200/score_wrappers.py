@@ -44,6 +44,7 @@ class _EngineLoss(torch.autograd.Function):
         loss, out = eng.train_step(state_images, action, goal, noise, sigma)
         ctx.eng, ctx.names, ctx.shapes = eng, inner._param_names, [tuple(p.shape) for p in params]
         ctx.needs = [p.requires_grad for p in params]
+        ctx.in_shapes = (action.shape[0], tuple(state_images.shape), tuple(goal.shape), state_images.dtype, goal.dtype)
         ctx.mark_non_differentiable(out)
         return loss, out
 
@@ -55,7 +56,14 @@ class _EngineLoss(torch.autograd.Function):
                 grads.append(None)
             else:
                 grads.append(ctx.eng.grad(name, shape) * g_loss)  # the product is a fresh tensor: the buffer is reused
-        return (None, None, None, None, None, None, *grads)
+        # gradients w.r.t. the observation tokens and the goal flow on into the caller's encoders (mode_agent.py:405-411)
+        B, s_shape, g_shape, s_dtype, g_dtype = ctx.in_shapes
+        d_state = d_goal = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
+            d_state, d_goal = ctx.eng.input_grads(B, s_shape, g_shape, ctx.needs_input_grad[1], ctx.needs_input_grad[3])
+            d_state = None if d_state is None else (d_state * g_loss).to(s_dtype)
+            d_goal = None if d_goal is None else (d_goal * g_loss).to(g_dtype)
+        return (None, d_state, None, d_goal, None, None, *grads)
 
 
 class GCDenoiser(nn.Module):

@@ -40,8 +40,9 @@ def golden_train(tag, cfg, B, router_gain=30.0):
     g = np.load(OUT / f"{tag}.npz")
     acts = (x0 / np.float32(80.0)).astype(np.float32)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    st_in, goal_in = t(state).requires_grad_(True), t(goal).requires_grad_(True)  # the reference trains its encoders through these
     with torch.enable_grad():
-        loss, f_out = model.loss({"state_images": t(state)}, t(acts), t(goal), t(g["loss_noise"]), t(g["sigma_het"]))
+        loss, f_out = model.loss({"state_images": st_in}, t(acts), goal_in, t(g["loss_noise"]), t(g["sigma_het"]))
         # auxiliary router losses of the same forward (modedit.py:898-969) and their gradients
         lb, zl = inner.load_balancing_loss(), inner.compute_router_z_loss()
         aux_names = [n for n, _ in inner.named_parameters() if "router" in n or n.startswith("sigma_")]
@@ -50,6 +51,8 @@ def golden_train(tag, cfg, B, router_gain=30.0):
         loss.backward()
     out = {"loss": np.float32(loss.item()), "F": f_out.detach().numpy(), "aux_lb": np.float32(lb.item()),
            "aux_z": np.float32(zl.item())}
+    out["d_state"] = st_in.grad.numpy().copy()
+    out["d_goal"] = goal_in.grad.numpy().copy()
     for n, gr in zip(aux_names, aux_grads):
         out[f"auxnorm/{n}"] = np.float32(0.0 if gr is None else np.linalg.norm(gr.numpy().astype(np.float64)))
     assert abs(float(loss) - float(g["loss_value"])) < 1e-5 * abs(float(loss)), "train-mode loss differs from eval-mode"

@@ -90,8 +90,14 @@ def test_autograd_integration_and_optimizer_step():
     inner.freeze_router()  # the reference's default fine-tuning recipe (mode_agent.py:762-765)
     st = {"state_images": cu(state)}
     acts, noise, sig = cu((x0 / np.float32(80.0)).astype(np.float32)), cu(g["loss_noise"]), cu(g["sigma_het"])
-    loss, _ = model.loss(st, acts, cu(goal), noise, sig)
+    st["state_images"].requires_grad_(True)  # upstream encoders train through the loss (mode_agent.py:405-411)
+    goal_t = cu(goal).requires_grad_(True)
+    loss, _ = model.loss(st, acts, goal_t, noise, sig)
     loss.backward()
+    for got, want in ((st["state_images"].grad, gt["d_state"]), (goal_t.grad, gt["d_goal"])):
+        got = got.cpu().numpy().reshape(want.shape)
+        assert np.linalg.norm(got - want) <= 6e-2 * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
+    st = {"state_images": st["state_images"].detach()}
     params = dict(inner.named_parameters())
     assert params["blocks.0.router.router.mlp.0.weight"].grad is None and params["gripper_embed.weight"].grad is None
     for pos, (name, shape) in enumerate(O.state_dict_spec(cfg)):
@@ -149,3 +155,34 @@ def test_auxiliary_router_losses_match_reference(tag):
     # the total loss (action + weighted aux) back-propagates in one call, as training_step does (mode_agent.py:408-420)
     (loss + 0.01 * lb + 0.001 * zl).backward()
     assert params["blocks.0.router.router.mlp.3.weight"].grad is not None
+
+
+def test_input_gradients_tensor_core_path_matches_scalar_kernel(monkeypatch):
+    """At the CALVIN widths (obs 2048, goal 512) d loss / d state_images and d loss / d goal come from the tcgen05 GEMM
+    with transposed embedding weights; the scalar kernel (same bf16 operands, fp32 accumulation) is its reference.
+    Also checks <d_state, state> == <grad W_tok, W_tok> (both are sum dtok * W * state), likewise for the goal."""
+    cfg = O.ModeConfig(n_layers=2)
+    B = 6
+    sd = O.make_weights_fast(cfg, seed=1234)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    rng = np.random.default_rng(11)
+    noise = rng.standard_normal(x0.shape).astype(np.float32)
+    sigma = np.exp(rng.uniform(np.log(1e-3), np.log(80.0), B)).astype(np.float32)
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    got = {}
+    for simt in ("0", "1"):
+        monkeypatch.setenv("MODE_INPUT_GRAD_SIMT", simt)
+        eng = engine_for(cfg, sd, 8)
+        eng.train_step(cu(state), cu(acts), cu(goal), cu(noise), cu(sigma))
+        ds, dg = eng.input_grads(B, state.shape, goal.shape)
+        got[simt] = (ds.clone(), dg.clone(), eng.grad("tok_emb.weight", sd["tok_emb.weight"].shape).clone(),
+                     eng.grad("goal_emb.weight", sd["goal_emb.weight"].shape).clone())
+        del eng
+    for a, b in zip(got["0"][:2], got["1"][:2]):
+        assert float(b.abs().max()) > 0
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+    ds, dg, gw_tok, gw_goal = got["0"]
+    # the sums cancel heavily: the tolerance is relative to their absolute mass (bf16 rounding of state vs W operands)
+    for dx, x, gw, w in ((ds, cu(state), gw_tok, cu(sd["tok_emb.weight"])), (dg, cu(goal), gw_goal, cu(sd["goal_emb.weight"]))):
+        lhs, rhs, mass = float((dx * x).double().sum()), float((gw * w).double().sum()), float((dx * x).abs().double().sum())
+        assert abs(lhs - rhs) <= 2e-3 * mass, (lhs, rhs, mass)
