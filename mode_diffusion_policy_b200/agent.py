@@ -23,6 +23,13 @@ class DenoisingPolicy:
         self.sigma_sample_density_type = sigma_sample_density_type
         self.device = device
 
+    def load_pretrained_parameters(self, ckpt_path, strict: bool = False):
+        """Denoiser part of MoDEAgent.load_pretrained_parameters (reference mode_agent.py:134-265): reads
+        model_cleaned.safetensors / .pt, keeps the `model.inner_model.*` tensors. Returns a checkpoint.LoadReport."""
+        from . import checkpoint
+
+        return checkpoint.load_pretrained_parameters(self.model.inner_model, ckpt_path, strict=strict)
+
     def get_noise_schedule(self, n_sampling_steps, noise_schedule_type):
         t = noise_schedule_type
         if t == "karras":

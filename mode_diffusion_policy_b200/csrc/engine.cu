@@ -78,6 +78,31 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, void* __restrict
     reinterpret_cast<float*>(dst)[o] = src[i];
 }
 
+// Same mapping, four columns per thread (cols % 4 == 0, no transpose): 16-byte loads, 8- or 16-byte stores. A training loop
+// re-packs every parameter after each optimiser step, so this pass runs at HBM speed rather than one element per thread.
+__global__ void pack_rows_vec4_kernel(const float4* __restrict__ src, void* __restrict__ dst, int rows, int cols4,
+                                      size_t dst_row0, int swiglu_half, int to_bf16) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * cols4) return;
+  const int r = static_cast<int>(i / cols4), c4 = static_cast<int>(i % cols4);
+  int dr = r;
+  if (swiglu_half > 0) {
+    const int is_gate = r >= swiglu_half;
+    const int rr = is_gate ? r - swiglu_half : r;
+    dr = (rr / 128) * 256 + (is_gate ? 128 : 0) + (rr % 128);
+  }
+  const float4 v = src[i];
+  const size_t o = (dst_row0 + dr) * static_cast<size_t>(cols4) + c4;
+  if (to_bf16) {
+    uint2 pk;
+    pk.x = mode::pack_bf16x2(v.x, v.y);
+    pk.y = mode::pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[o] = pk;
+  } else {
+    reinterpret_cast<float4*>(dst)[o] = v;
+  }
+}
+
 // out[r] = sum_k W[r,k]*vec[k] (+ add[r]) accumulated in fp64; one warp per row. Used once at weight-load time.
 __global__ void matvec_f64_kernel(const float* __restrict__ W, const float* __restrict__ vec,
                                   const float* __restrict__ add, float* __restrict__ out, int rows, int cols) {
@@ -634,8 +659,14 @@ extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* d
   if (is_device) {
     // device source: pack straight from the caller's tensor, stream-ordered on the default stream, no synchronisation
     // (a training loop re-packs all 686 M parameters after every optimiser step)
-    pack_rows_kernel<<<blocks, threads>>>(reinterpret_cast<const float*>(data), s.dst, s.rows, s.cols, s.dst_row0,
-                                          s.swiglu_half, s.to_bf16, s.transpose ? 1 : 0);
+    if (!s.transpose && s.cols % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
+      const size_t n4 = numel / 4;
+      pack_rows_vec4_kernel<<<(unsigned)((n4 + threads - 1) / threads), threads>>>(
+          reinterpret_cast<const float4*>(data), s.dst, s.rows, s.cols / 4, s.dst_row0, s.swiglu_half, s.to_bf16);
+    } else {
+      pack_rows_kernel<<<blocks, threads>>>(reinterpret_cast<const float*>(data), s.dst, s.rows, s.cols, s.dst_row0,
+                                            s.swiglu_half, s.to_bf16, s.transpose ? 1 : 0);
+    }
     CU_OK(cudaGetLastError());
     return MODE_OK;
   }

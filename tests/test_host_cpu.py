@@ -123,3 +123,47 @@ def test_samplers_host_logic():
     assert calls == list(range(10))
     down, up = S.get_ancestral_step(2.0, 1.0)
     assert abs(down ** 2 + up ** 2 - 1.0) < 1e-6
+
+
+def test_checkpoint_loader_selects_and_remaps_denoiser_keys(tmp_path):
+    """model_cleaned.safetensors is keyed as MoDEAgent.state_dict() (reference mode_agent.py:134-265): denoiser tensors
+    under model.inner_model.*, encoders / CLIP beside them. Round trip through the writer, non-strict skip of a shape
+    mismatch, strict failure, and the directory form."""
+    from safetensors.torch import save_file
+    from mode_diffusion_policy_b200 import checkpoint as CK
+
+    def make(seed):
+        torch.manual_seed(seed)
+        return MoDeDiT(obs_dim=128, goal_dim=64, device="cpu", goal_conditioned=True, action_dim=7, embed_dim=256,
+                       embed_pdrob=0, attn_pdrop=0.0, n_layers=2, n_heads=4, goal_seq_len=1, obs_seq_len=1,
+                       action_seq_len=10, state_dim=7, num_experts=4, top_k=2, init_style="olmoe")
+
+    src, dst = make(1), make(2)
+    with torch.no_grad():
+        src.pos_emb.normal_()
+    agent_sd = {"model.inner_model." + k: v.detach().clone() for k, v in src.state_dict().items()}
+    agent_sd["static_resnet.resnet.conv1.weight"] = torch.zeros(4, 3, 7, 7)    # encoder: not ours
+    agent_sd["language_goal.clip_rn50.visual.proj"] = torch.zeros(8, 8)        # CLIP: skipped by the reference too
+    agent_sd["model.inner_model.out.bias"] = torch.zeros(9)                    # incompatible shape
+    agent_sd["model.inner_model.pos_emb"] = src.pos_emb.detach()[0].clone()    # same data, saved without the batch dim
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    save_file({k: v.contiguous() for k, v in agent_sd.items()}, str(d / "model_cleaned.safetensors"))
+    rep = CK.load_pretrained_parameters(dst, str(d))
+    assert rep.ignored == 2 and rep.missing == ["out.bias"]
+    assert rep.skipped_shape == [("out.bias", (9,), (7,))]
+    for k, v in src.state_dict().items():
+        if k != "out.bias":
+            assert torch.equal(dst.state_dict()[k], v), k
+    with pytest.raises(RuntimeError):
+        CK.load_pretrained_parameters(make(3), str(d), strict=True)
+    # writer -> loader round trip on a single file, strict
+    f = tmp_path / "model_cleaned.safetensors"
+    CK.save_denoiser(src, str(f))
+    again = make(4)
+    rep = CK.load_pretrained_parameters(again, str(f), strict=True)
+    assert not rep.missing and all(torch.equal(again.state_dict()[k], v) for k, v in src.state_dict().items())
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        CK.load_pretrained_parameters(make(5), str(empty))
