@@ -105,6 +105,22 @@ int mode_grad_offset(mode_engine_t* e, const char* name, int64_t* offset, int64_
  * (B, goal_dim), fp32, either may be NULL. In the reference these flow on into the FiLM-ResNet encoders that produce
  * perceptual_emb (mode_agent.py:405-411, compute_input_embeddings :513-582); bf16 tensor-core operands like the rest. */
 int mode_train_input_grads(mode_engine_t* e, float* dstate_dev, float* dgoal_dev, int B, void* stream);
+/* Fused optimizer: AdamW with torch.optim.AdamW's arithmetic over the flat gradient buffer, fused
+ * with the re-pack of the updated weights into the engine's GEMM layouts. The reference configures AdamW in
+ * MoDEAgent.configure_optimizers / get_optim_groups (mode_agent.py:267-301, :362-384): lr, betas, eps, and weight decay
+ * on every parameter whose name contains none of 'bias', 'LayerNorm', 'embedding'.
+ * mode_optimizer_bind: `param_dev` is the caller-owned fp32 master of reference parameter `name` (reference layout,
+ *   contiguous); it is updated in place by every step. weight_decay != 0 puts it in the decayed group. Parameters that
+ *   are never bound (frozen routers, mode_agent.py:762-765) are left untouched. Re-binding with a new pointer is allowed.
+ * mode_adamw_step: one launch over all bound tensors on `stream`, using the gradients of the last mode_train_step
+ *   (all-reduced by the caller in data-parallel runs); `step` counts from 1 (bias correction); grad_scale_dev is an
+ *   optional device scalar multiplied into every gradient (the loss tensor's incoming gradient). Moment buffers are
+ *   engine-owned (mode_optimizer_state exposes them for checkpointing; gradient-buffer layout). */
+int mode_optimizer_bind(mode_engine_t* e, const char* name, float* param_dev, int weight_decay);
+int mode_optimizer_unbind_all(mode_engine_t* e);
+int mode_adamw_step(mode_engine_t* e, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    const float* grad_scale_dev, void* stream);
+int mode_optimizer_state(mode_engine_t* e, float** exp_avg_dev, float** exp_avg_sq_dev, int64_t* numel);
 /* Makes `stream` wait (cudaStreamWaitEvent, no host sync) until the most recent mode_train_step has finished writing the
  * gradients of block `layer` (its backward runs last-to-first), or all gradients when layer == -1. This is what lets a
  * data-parallel caller all-reduce layer l's sections on a side stream while layers l-1..0 are still in backward — the

@@ -21,6 +21,7 @@
 #include "mlp_fused.cuh"
 #include "rowwise.cuh"
 #include "backward.cuh"
+#include "optimizer.cuh"
 
 using namespace mode;
 
@@ -679,21 +680,27 @@ extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* d
   return MODE_OK;
 }
 
+// Quantities derived from the packed weights (the sigma-affine collapse of DESIGN.md §5), recomputed whenever they change.
+static int refresh_derived(mode_engine* e, cudaStream_t st) {
+  const int d = e->d, Hd = e->Hd;
+  // emb_t(s) = sigma_linear(sigma_emb(s)) = s * (W2 w1) + (W2 b1)            (modedit.py:823-832)
+  matvec_f64_kernel<<<(d + 7) / 8, 256, 0, st>>>(e->sig_w2, e->sig_w1, nullptr, e->sig_u, d, d);
+  matvec_f64_kernel<<<(d + 7) / 8, 256, 0, st>>>(e->sig_w2, e->sig_b1, nullptr, e->sig_v, d, d);
+  // router first Linear on c = emb_t(s): s * (W1 u) + (W1 v + b1)            (modedit.py:304-310, :336)
+  for (int l = 0; l < e->L; ++l) {
+    const float* W1 = e->r_w1 + (size_t)l * Hd * d;
+    matvec_f64_kernel<<<(Hd + 7) / 8, 256, 0, st>>>(W1, e->sig_u, nullptr, e->r_a + (size_t)l * Hd, Hd, d);
+    matvec_f64_kernel<<<(Hd + 7) / 8, 256, 0, st>>>(W1, e->sig_v, e->r_b1 + (size_t)l * Hd, e->r_b + (size_t)l * Hd, Hd, d);
+  }
+  CU_OK(cudaGetLastError());
+  return MODE_OK;
+}
+
 extern "C" int mode_finalize_weights(mode_engine_t* e) {
   if (!e) return fail(MODE_ERR_INVALID, "null engine");
   for (auto& kv : e->specs)
     if (!kv.second.provided && !kv.second.ignore) return fail(MODE_ERR_STATE, "weight '%s' was never set", kv.first.c_str());
-  const int d = e->d, Hd = e->Hd;
-  // emb_t(s) = sigma_linear(sigma_emb(s)) = s * (W2 w1) + (W2 b1)            (modedit.py:823-832)
-  matvec_f64_kernel<<<(d + 7) / 8, 256>>>(e->sig_w2, e->sig_w1, nullptr, e->sig_u, d, d);
-  matvec_f64_kernel<<<(d + 7) / 8, 256>>>(e->sig_w2, e->sig_b1, nullptr, e->sig_v, d, d);
-  // router first Linear on c = emb_t(s): s * (W1 u) + (W1 v + b1)            (modedit.py:304-310, :336)
-  for (int l = 0; l < e->L; ++l) {
-    const float* W1 = e->r_w1 + (size_t)l * Hd * d;
-    matvec_f64_kernel<<<(Hd + 7) / 8, 256>>>(W1, e->sig_u, nullptr, e->r_a + (size_t)l * Hd, Hd, d);
-    matvec_f64_kernel<<<(Hd + 7) / 8, 256>>>(W1, e->sig_v, e->r_b1 + (size_t)l * Hd, e->r_b + (size_t)l * Hd, Hd, d);
-  }
-  CU_OK(cudaGetLastError());
+  RET_IF(refresh_derived(e, nullptr));
   // no host synchronisation: host-source weights were already synchronised in mode_set_weight, device-source packing is
   // stream-ordered; the first call on another stream waits for this event (ensure_batch)
   if (!e->weights_ready) CU_OK(cudaEventCreateWithFlags(&e->weights_ready, cudaEventDisableTiming));

@@ -1,0 +1,116 @@
+// AdamW over the engine's flat gradient buffer, fused with the weight re-pack.
+//
+// The reference trains with torch.optim.AdamW on parameter groups split by name (mode_agent.py:362-384: names containing
+// 'bias', 'LayerNorm' or 'embedding' get weight_decay 0). A step there costs three passes over 686 M parameters: the
+// optimizer (read p, g, m, v; write p, m, v), and for this engine a re-pack of the fp32 masters into the bf16 layouts the
+// GEMMs read, plus autograd handing out gradient copies. Here ONE launch walks every bound tensor: it reads the gradient
+// section, updates the moments (engine-owned flat buffers with the gradient layout) and the caller-owned fp32 master in
+// place, and writes the packed copy (bf16 or fp32, SwiGLU row interleave, transposed action embedding) in the same pass.
+// Arithmetic follows torch's single-tensor AdamW: p *= 1 - lr*wd; m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g;
+// p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+#pragma once
+#include "ptx.cuh"
+
+namespace mode {
+
+constexpr int OPT_BLOCK_ELEMS = 1024;  // 256 threads x 4 elements
+
+struct OptTensor {
+  float* p;                      // fp32 master (caller-owned, reference layout [rows, cols])
+  void* dst;                     // packed engine copy
+  unsigned long long g_off;      // element offset of this tensor in the flat gradient / moment buffers
+  unsigned long long dst_row0;
+  int rows, cols, swiglu_half, to_bf16, transpose, decay;
+  unsigned block0;               // first block of the launch that belongs to this tensor
+  unsigned pad;
+};
+
+struct AdamWParams {
+  const OptTensor* tab;
+  int n;
+  const float* grads;
+  float *m, *v;
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+  const float* grad_scale;  // device scalar multiplied into every gradient (the loss's incoming gradient), or null
+};
+
+__device__ __forceinline__ int opt_dst_row(int r, int swiglu_half) {
+  if (swiglu_half <= 0) return r;
+  const int is_gate = r >= swiglu_half;
+  const int rr = is_gate ? r - swiglu_half : r;
+  return (rr / 128) * 256 + (is_gate ? 128 : 0) + (rr % 128);
+}
+
+__device__ __forceinline__ float adamw_update(float p, float g, float& m, float& v, const AdamWParams& a, float decay_mul) {
+  p *= decay_mul;
+  m = m + (g - m) * (1.0f - a.beta1);
+  v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  return p - (a.lr / a.bc1) * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
+  // which tensor does this block belong to? (binary search over the first-block table; a few hundred entries)
+  int lo = 0, hi = a.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (a.tab[mid].block0 <= blockIdx.x)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const OptTensor t = a.tab[lo];
+  const size_t numel = static_cast<size_t>(t.rows) * t.cols;
+  const size_t base = static_cast<size_t>(blockIdx.x - t.block0) * OPT_BLOCK_ELEMS;
+  const float gs = a.grad_scale ? *a.grad_scale : 1.0f;
+  const float decay_mul = t.decay ? 1.0f - a.lr * a.wd : 1.0f;
+  if (!t.transpose && (t.cols & 3) == 0 && (t.g_off & 3) == 0 && (reinterpret_cast<uintptr_t>(t.p) & 15) == 0) {
+    const size_t i = base + threadIdx.x * 4;
+    if (i >= numel) return;
+    const size_t gi = t.g_off + i;  // sections are 128-byte aligned
+    float4 p = *reinterpret_cast<const float4*>(t.p + i);
+    const float4 g = *reinterpret_cast<const float4*>(a.grads + gi);
+    float4 m = *reinterpret_cast<const float4*>(a.m + gi);
+    float4 v = *reinterpret_cast<const float4*>(a.v + gi);
+    p.x = adamw_update(p.x, g.x * gs, m.x, v.x, a, decay_mul);
+    p.y = adamw_update(p.y, g.y * gs, m.y, v.y, a, decay_mul);
+    p.z = adamw_update(p.z, g.z * gs, m.z, v.z, a, decay_mul);
+    p.w = adamw_update(p.w, g.w * gs, m.w, v.w, a, decay_mul);
+    *reinterpret_cast<float4*>(t.p + i) = p;
+    *reinterpret_cast<float4*>(a.m + gi) = m;
+    *reinterpret_cast<float4*>(a.v + gi) = v;
+    const int r = static_cast<int>(i / t.cols), c = static_cast<int>(i % t.cols);
+    const size_t o = (t.dst_row0 + opt_dst_row(r, t.swiglu_half)) * static_cast<size_t>(t.cols) + c;
+    if (t.to_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(p.x, p.y);
+      pk.y = pack_bf16x2(p.z, p.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t.dst) + o) = pk;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(t.dst) + o) = p;
+    }
+    return;
+  }
+  for (int k = 0; k < 4; ++k) {  // small / oddly shaped tensors: one element at a time, coalesced across the block
+    const size_t i = base + k * 256 + threadIdx.x;
+    if (i >= numel) return;
+    const size_t gi = t.g_off + i;
+    float m = a.m[gi], v = a.v[gi];
+    const float p = adamw_update(t.p[i], a.grads[gi] * gs, m, v, a, decay_mul);
+    t.p[i] = p;
+    a.m[gi] = m;
+    a.v[gi] = v;
+    const int r = static_cast<int>(i / t.cols), c = static_cast<int>(i % t.cols);
+    if (t.transpose) {
+      reinterpret_cast<float*>(t.dst)[static_cast<size_t>(c) * t.rows + r] = p;
+    } else {
+      const size_t o = (t.dst_row0 + opt_dst_row(r, t.swiglu_half)) * static_cast<size_t>(t.cols) + c;
+      if (t.to_bf16)
+        reinterpret_cast<__nv_bfloat16*>(t.dst)[o] = __float2bfloat16_rn(p);
+      else
+        reinterpret_cast<float*>(t.dst)[o] = p;
+    }
+  }
+}
+
+}  // namespace mode

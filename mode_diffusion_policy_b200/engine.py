@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+from typing import Optional
 from dataclasses import dataclass, asdict
 
 import numpy as np
@@ -197,6 +198,39 @@ class ModeEngine:
         _lib.check(self.lib.mode_train_input_grads(self._h, ds.data_ptr() if want_state else None,
                                                    dg.data_ptr() if want_goal else None, B, self._stream()))
         return ds, dg
+
+    # ---------------------------------------------------------------- fused optimizer
+    def optimizer_bind(self, name: str, param: torch.Tensor, weight_decay: bool) -> None:
+        """Register the fp32 master of reference parameter `name`; mode_adamw_step updates it in place."""
+        if not (param.is_cuda and param.dtype == torch.float32 and param.is_contiguous()):
+            raise ValueError(f"{name}: the fused optimizer needs a contiguous fp32 CUDA parameter")
+        _lib.check(self.lib.mode_optimizer_bind(self._h, name.encode(), C.c_void_p(param.data_ptr()), int(bool(weight_decay))))
+
+    def optimizer_unbind_all(self) -> None:
+        _lib.check(self.lib.mode_optimizer_unbind_all(self._h))
+
+    def adamw_step(self, lr, beta1, beta2, eps, weight_decay, step: int, grad_scale: Optional[torch.Tensor] = None) -> None:
+        """AdamW over every bound parameter + re-pack of the engine's weight copies, one launch (csrc/optimizer.cuh)."""
+        gs = None
+        if grad_scale is not None:
+            gs = grad_scale.detach().to(device=self.device, dtype=torch.float32).reshape(1).contiguous()
+        _lib.check(self.lib.mode_adamw_step(self._h, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                            int(step), C.c_void_p(gs.data_ptr()) if gs is not None else None, self._stream()))
+
+    def optimizer_state(self):
+        """Zero-copy views (exp_avg, exp_avg_sq) of the engine-owned moment buffers (gradient-buffer layout)."""
+        m, v, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.mode_optimizer_state(self._h, C.byref(m), C.byref(v), C.byref(n)))
+
+        def view(ptr):
+            class _Dev:
+                pass
+
+            h = _Dev()
+            h.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+            return torch.as_tensor(h, device=self.device)
+
+        return view(m), view(v)
 
     def wait_grads(self, layer: int, stream: "torch.cuda.Stream") -> None:
         """Make `stream` wait until the last train_step finished block `layer`'s gradients (-1: all gradients)."""

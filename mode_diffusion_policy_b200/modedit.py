@@ -219,7 +219,10 @@ class MoDeDiT(nn.Module):
     def _weights_fingerprint(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def _ensure_engine(self, batch: int) -> ModeEngine:
+    def _ensure_engine(self, batch: int, force_repack: bool = False) -> ModeEngine:
+        """The engine for this module with its packed weights up to date. Changes are detected through the parameters'
+        (data_ptr, _version) pairs; `force_repack` is for callers that cannot rely on version counters (a training step
+        after a fused/foreach optimizer, which updates parameters without bumping them)."""
         cfg = self._engine_cfg
         if self._engine is None or batch > self._engine.cfg.max_batch:
             if self._engine is not None:
@@ -228,7 +231,7 @@ class MoDeDiT(nn.Module):
             self._engine = ModeEngine(cfg)
             self._weights_key = None
         key = self._weights_fingerprint()
-        if key != self._weights_key:
+        if key != self._weights_key or force_repack:
             self._engine.load_state_dict({k: v for k, v in self.state_dict().items()})
             self._weights_key = key
         return self._engine

@@ -1,0 +1,85 @@
+"""Fused optimizer for the engine's training path.
+
+`EngineAdamW` is a `torch.optim.Optimizer` (LR schedulers, Lightning's `configure_optimizers` and `state_dict()` see
+an ordinary optimizer with one param group), but `step()` is a single engine launch: AdamW with torch's arithmetic over
+the flat gradient buffer written by `GCDenoiser.loss`, updating the fp32 master parameters in place AND the engine's
+packed bf16 copies in the same pass (csrc/optimizer.cuh). It replaces three passes over 686 M parameters in the
+reference setup — autograd handing out gradient copies, `torch.optim.AdamW` (mode_agent.py:267-301) and this engine's
+weight re-pack.
+
+Weight-decay groups follow MoDEAgent.get_optim_groups (mode_agent.py:362-384): parameters whose name contains 'bias',
+'LayerNorm' or 'embedding' are not decayed.
+"""
+from __future__ import annotations
+
+import torch
+
+from .modedit import MoDeDiT
+
+NO_DECAY_SUBSTRINGS = ("bias", "LayerNorm", "embedding")  # reference mode_agent.py:365-366
+
+
+def use_weight_decay(name: str) -> bool:
+    return all(x not in name for x in NO_DECAY_SUBSTRINGS)
+
+
+class EngineAdamW(torch.optim.Optimizer):
+    def __init__(self, inner_model: MoDeDiT, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 materialize_grads: bool = False):
+        """materialize_grads=False: `loss.backward()` no longer copies the engine's gradients into `.grad` (nothing reads
+        them); set True to keep `.grad` populated for gradient logging (mode_agent.py:304-359)."""
+        self.inner = inner_model
+        named = [(n, p) for n, p in inner_model.named_parameters() if p.requires_grad and n != "gripper_embed.weight"]
+        super().__init__([p for _, p in named], dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._names = [n for n, _ in named]
+        self._step = 0
+        self._bound = {}
+        inner_model._skip_param_grads = not materialize_grads
+        inner_model._engine_keeps_sync = True  # step() re-packs what it updates: GCDenoiser.loss need not
+        inner_model._loss_grad_scale = None
+
+    def _bind(self, eng):
+        if self._bound.get("engine") is not eng:
+            eng.optimizer_unbind_all()
+            self._bound = {"engine": eng}
+        params = dict(self.inner.named_parameters())
+        for name in self._names:
+            p = params[name]
+            key = (p.data_ptr(), p.requires_grad)
+            if self._bound.get(name) != key and p.requires_grad:
+                eng.optimizer_bind(name, p.data, use_weight_decay(name))
+                self._bound[name] = key
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        eng = getattr(self.inner, "_engine", None)
+        if eng is None:
+            raise RuntimeError("EngineAdamW.step before any GCDenoiser.loss call")
+        self._bind(eng)
+        g = self.param_groups[0]
+        self._step += 1
+        eng.adamw_step(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._step,
+                       self.inner._loss_grad_scale)
+        return loss
+
+    def state_dict(self):
+        sd = {"step": self._step, "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+        eng = getattr(self.inner, "_engine", None)
+        if eng is not None and self._step > 0:
+            m, v = eng.optimizer_state()
+            sd["exp_avg"], sd["exp_avg_sq"] = m.clone(), v.clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        self._step = int(sd["step"])
+        for k, v in sd["param_groups"][0].items():
+            self.param_groups[0][k] = v
+        if "exp_avg" in sd:
+            eng = self.inner._ensure_engine(1)
+            m, v = eng.optimizer_state()
+            m.copy_(sd["exp_avg"])
+            v.copy_(sd["exp_avg_sq"])

@@ -40,9 +40,12 @@ class _EngineLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, inner, state_images, action, goal, noise, sigma, *params):
-        eng = inner._ensure_engine(action.shape[0])
+        # A torch optimizer may have updated the masters since the last step without touching their version counters
+        # (fused / foreach kernels do): re-pack unconditionally unless optim.EngineAdamW keeps the copies in sync itself.
+        eng = inner._ensure_engine(action.shape[0], force_repack=not getattr(inner, "_engine_keeps_sync", False))
         loss, out = eng.train_step(state_images, action, goal, noise, sigma)
         ctx.eng, ctx.names, ctx.shapes = eng, inner._param_names, [tuple(p.shape) for p in params]
+        ctx.inner = inner
         ctx.needs = [p.requires_grad for p in params]
         ctx.in_shapes = (action.shape[0], tuple(state_images.shape), tuple(goal.shape), state_images.dtype, goal.dtype)
         ctx.mark_non_differentiable(out)
@@ -51,7 +54,12 @@ class _EngineLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_out):
         grads = []
-        for name, shape, need in zip(ctx.names, ctx.shapes, ctx.needs):
+        inner = ctx.inner
+        if getattr(inner, "_skip_param_grads", False):
+            # optim.EngineAdamW reads the engine's flat gradient buffer directly: no per-parameter copies
+            inner._loss_grad_scale = g_loss.detach()
+            grads = [None] * len(ctx.names)
+        for name, shape, need in ([] if grads else zip(ctx.names, ctx.shapes, ctx.needs)):
             if not need or name == "gripper_embed.weight":  # unused unless use_proprio (reference modedit.py:684)
                 grads.append(None)
             else:

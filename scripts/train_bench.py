@@ -38,7 +38,13 @@ inner = MoDeDiT(obs_dim=2048, goal_dim=512, device="cuda", goal_conditioned=True
                 mlp_pdrop=0.0, goal_drop=0.0, num_experts=4, top_k=2, use_argmax=True, max_batch=B)
 inner.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_weights_fast(cfg, seed=1234).items()})
 model = GCDenoiser(inner, sigma_data=0.5).cuda().train()
-opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+if os.environ.get("MODE_TRAIN_FUSED_OPT", "1") == "1":  # one engine launch: AdamW over the flat gradient buffer + re-pack
+    from mode_diffusion_policy_b200.optim import EngineAdamW
+    opt = EngineAdamW(inner, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    opt_name = "engine fused AdamW+repack"
+else:
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+    opt_name = "torch fused AdamW + engine re-pack"
 state, goal, x0 = O.make_inputs(cfg, B, seed=4321 + rank)
 rng = np.random.default_rng(7 + rank)
 S, G = torch.from_numpy(state).cuda(), torch.from_numpy(goal).cuda()
@@ -86,7 +92,7 @@ if rank == 0:
                       "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                       "global_batch": world * B, "dtype": "bf16", "data": "synthetic", "loss": float(loss),
                       "approx_tflops": 3 * fwd_flops * a.steps / (ms * 1e-3) / 1e12,
-                      "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack",
+                      "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack", "optimizer": opt_name,
                                  "grad_allreduce": ("per-layer NCCL all-reduce buckets of the flat fp32 gradient buffer, overlapped with backward" if ap_overlap else "one NCCL all-reduce over the flat fp32 gradient buffer")}}), flush=True)
 if world > 1:
     dist.destroy_process_group()

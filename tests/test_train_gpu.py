@@ -186,3 +186,76 @@ def test_input_gradients_tensor_core_path_matches_scalar_kernel(monkeypatch):
     for dx, x, gw, w in ((ds, cu(state), gw_tok, cu(sd["tok_emb.weight"])), (dg, cu(goal), gw_goal, cu(sd["goal_emb.weight"]))):
         lhs, rhs, mass = float((dx * x).double().sum()), float((gw * w).double().sum()), float((dx * x).abs().double().sum())
         assert abs(lhs - rhs) <= 2e-3 * mass, (lhs, rhs, mass)
+
+
+def _tiny_denoiser(sd, cfg):
+    from mode_diffusion_policy_b200.modedit import MoDeDiT
+    from mode_diffusion_policy_b200.score_wrappers import GCDenoiser
+
+    inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cuda", goal_conditioned=True, action_dim=7,
+                    embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=0.0, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                    goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7, mlp_pdrop=0.0, goal_drop=0.0,
+                    num_experts=cfg.num_experts, top_k=cfg.top_k, use_argmax=True, max_batch=8)
+    inner.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return inner, GCDenoiser(inner, sigma_data=0.5).cuda().train()
+
+
+def test_fused_adamw_matches_torch_adamw_and_keeps_packed_weights_in_sync():
+    """optim.EngineAdamW (one launch: AdamW over the flat gradient buffer + re-pack, csrc/optimizer.cuh) against
+    torch.optim.AdamW with the reference's parameter groups (mode_agent.py:362-384) on the same gradients."""
+    from mode_diffusion_policy_b200.optim import EngineAdamW, use_weight_decay
+
+    cfg, B = MODELS["model_tiny_d256_l3_e4"]
+    g = np.load(GOLD / "model_tiny_d256_l3_e4.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    st = {"state_images": cu(state)}
+    acts, noise, sig, goal_t = cu((x0 / np.float32(80.0)).astype(np.float32)), cu(g["loss_noise"]), cu(g["sigma_het"]), cu(goal)
+    hp = dict(lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    inner_a, model_a = _tiny_denoiser(sd, cfg)
+    inner_b, model_b = _tiny_denoiser(sd, cfg)
+    named = [(n, p) for n, p in inner_a.named_parameters() if n != "gripper_embed.weight"]
+    opt_a = torch.optim.AdamW([{"params": [p for n, p in named if use_weight_decay(n)], "weight_decay": hp["weight_decay"]},
+                               {"params": [p for n, p in named if not use_weight_decay(n)], "weight_decay": 0.0}],
+                              lr=hp["lr"], betas=hp["betas"], eps=hp["eps"])
+    opt_b = EngineAdamW(inner_b, **hp)
+    losses = []
+    for _ in range(3):
+        opt_a.zero_grad(set_to_none=True)
+        la, _ = model_a.loss(st, acts, goal_t, noise, sig)
+        la.backward()
+        opt_a.step()
+        lb, _ = model_b.loss(st, acts, goal_t, noise, sig)
+        lb.backward()  # no .grad copies: the optimizer reads the engine's buffer
+        opt_b.step()
+        losses.append((float(la), float(lb)))
+    assert all(p.grad is None for p in inner_b.parameters())
+    assert losses[0][0] == losses[0][1] and losses[-1][0] < losses[0][0]
+    pa, pb = dict(inner_a.named_parameters()), dict(inner_b.named_parameters())
+    for n, _ in named:
+        a, b = pa[n].detach(), pb[n].detach()
+        # an Adam step moves every element by ~lr whatever the gradient's size, so rounding-level differences in tiny
+        # gradients (the two models' weights differ in the last bit after step 1) show up as fractions of lr: a handful
+        # of near-zero-gradient elements may flip sign (max), the bulk agrees to rounding (mean)
+        diff = (a - b).abs()
+        assert float(diff.max()) <= 2 * 3 * hp["lr"] and float(diff.mean()) <= 0.01 * hp["lr"], (n, float(diff.max()), float(diff.mean()))
+    assert not torch.equal(pb["out.weight"].detach().cpu(), torch.from_numpy(sd["out.weight"]))  # it did move
+    # the engine's packed copies follow the masters without a reload: a fresh model built from B's state_dict agrees
+    inner_b.eval()
+    with torch.no_grad():
+        l_inplace, _ = model_b.loss(st, acts, goal_t, noise, sig)
+    inner_c, model_c = _tiny_denoiser({k: v.detach().cpu().numpy() for k, v in inner_b.state_dict().items()}, cfg)
+    inner_c.eval()
+    with torch.no_grad():
+        l_fresh, _ = model_c.loss(st, acts, goal_t, noise, sig)
+    assert float(l_inplace) == float(l_fresh)
+    # scaled loss: the incoming gradient reaches the optimizer (grad accumulation style 0.5 * loss)
+    inner_b.train()
+    before = pb["out.weight"].detach().clone()
+    lb, _ = model_b.loss(st, acts, goal_t, noise, sig)
+    (0.5 * lb).backward()
+    assert float(inner_b._loss_grad_scale) == 0.5
+    opt_b.step()
+    assert not torch.equal(before, pb["out.weight"].detach())
+    sd_opt = opt_b.state_dict()
+    assert sd_opt["step"] == 4 and sd_opt["exp_avg"].abs().sum() > 0
