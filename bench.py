@@ -138,6 +138,9 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (default: the headline 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, what the driver runs): --batch trajectories per GPU; strong: --batch is the GLOBAL "
+                         "batch, split evenly over the ranks (SURVEY.md §8d asks for both, labelled)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,6 +164,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = O.ModeConfig()
     B = args.batch
+    if args.scaling == "strong":
+        from mode_diffusion_policy_b200.parallel import shard_bounds
+        b0, b1 = shard_bounds(args.batch, rank, world)
+        B = b1 - b0
+    # a "denoising step" is one evaluation of a FULL batch of args.batch trajectories: N ranks each evaluating their own
+    # full batch do N of them per step (weak), N ranks sharing one batch do one (strong)
+    units_per_step = world if args.scaling == "weak" else 1
     eng = ModeEngine(EngineConfig(max_batch=B))
     eng.load_state_dict(O.make_weights_fast(cfg, seed=1234))
     state, goal, x0 = O.make_inputs(cfg, B, seed=4321 + rank)
@@ -207,8 +217,8 @@ def main():
 
     # the job is as slow as its slowest rank: MAX over ranks of the device time, whole-job units / that time
     ms, e2e_ms = parallel.max_over_ranks([ms, e2e_s * 1e3], "cuda")
-    value = world * args.steps * N_SAMPLING_STEPS / (ms * 1e-3)
-    e2e_value = world * args.steps * N_SAMPLING_STEPS / (e2e_ms * 1e-3)
+    value = units_per_step * args.steps * N_SAMPLING_STEPS / (ms * 1e-3)
+    e2e_value = units_per_step * args.steps * N_SAMPLING_STEPS / (e2e_ms * 1e-3)
 
     if rank == 0:
         # ---------------- roofline of the dominant kernel: grouped expert up-projection GEMM (tcgen05, SwiGLU epilogue)
@@ -251,7 +261,7 @@ def main():
             traffic = json.loads(tr.read_text()).get("up_gemm_swiglu_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "denoising_steps_per_bench_step": N_SAMPLING_STEPS,
                        "parallelism": f"dp{world} (independent trajectory shards, no collective)",
@@ -266,9 +276,9 @@ def main():
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": traffic, "peak_source": peak_src,
                          "flops_per_launch": up_flops, "us_per_launch": 1e3 * up_ms / up_n},
-            "step_roofline": {"algorithmic_tflop_per_denoising_step": step_flops / 1e12,
-                              "achieved_tflops": step_flops * value / world / 1e12,
-                              "frac_of_peak": step_flops * value / world / 1e12 / peak_tf},
+            "step_roofline": {"algorithmic_tflop_per_denoising_step": step_flops / 1e12,  # this rank's batch
+                              "achieved_tflops": step_flops * args.steps * N_SAMPLING_STEPS / (ms * 1e-3) / 1e12,
+                              "frac_of_peak": step_flops * args.steps * N_SAMPLING_STEPS / (ms * 1e-3) / 1e12 / peak_tf},
             "kernels": kernels,
         }
         if not args.no_cpu_baseline:
