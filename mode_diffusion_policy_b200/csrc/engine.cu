@@ -857,25 +857,28 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
 static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode, int slot, const LayerIO& io) {
   const int d = e->d, M = B * e->T;
   const size_t lt = (size_t)slot * e->L + l;  // layer index inside the routing tables
+  // measurement aid (scripts/skip_diag.py): bit PC_x set = do not launch that kernel class; outputs are then garbage
+  const char* skip_env = getenv("MODE_DEBUG_SKIP");
+  const unsigned skip = skip_env ? (unsigned)strtoul(skip_env, nullptr, 0) : 0u;
   GemmParams p = gemm_params(io.tm_hA, e->tm_wqkv, io.to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
   enable_stream_k(e, p);
   {
     ProfScope ps(e, st, PC_QKV);
-    RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
+    if (!(skip >> PC_QKV & 1)) RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
   }
   AttnParams a;
   a.qkv = io.qkv; a.out = io.attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
   a.B = B; a.T = e->T; a.H = e->H; a.eps = e->cfg.rms_eps; a.inv_sqrt_dh = e->inv_sqrt_dh;
   {
     ProfScope ps(e, st, PC_ATTN);
-    RET_IF(launch_attn(st, a, e->Dh));
+    if (!(skip >> PC_ATTN & 1)) RET_IF(launch_attn(st, a, e->Dh));
   }
   p = gemm_params(io.tm_attn, e->tm_wproj, io.to_x1, e->dense_tiles, e->dense_counts, d, d, nullptr);  // x1 += acc
   p.w_row_off = l * d;
   {
     ProfScope ps(e, st, PC_PROJ);
-    RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
+    if (!(skip >> PC_PROJ & 1)) RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
   Ln2Params n2;
   n2.x = io.x1; n2.x_out = io.xn; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + lt * B * e->K; n2.perm = io.perm;
@@ -885,7 +888,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   n2.n_zero = 1 + e->max_tiles;
   {
     ProfScope ps(e, st, PC_LN2);
-    LAUNCH_ROW_KERNEL(ln2_permute_kernel, d, row_blocks(M), st, n2);
+    if (!(skip >> PC_LN2 & 1)) LAUNCH_ROW_KERNEL(ln2_permute_kernel, d, row_blocks(M), st, n2);
   }
   CU_OK(cudaGetLastError());
   p = gemm_params(io.tm_perm, e->tm_wup, io.to_h, e->up_tiles + lt * e->max_tiles, e->num_tiles + lt, 8 * d, d,
@@ -911,14 +914,14 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
       if (io.z) {  // training: also keep the pre-activations for the SwiGLU backward
         p.tmap_out2 = io.to_z;
         RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
-      } else {
+      } else if (!(skip >> PC_UP & 1)) {
         RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
       }
     }
     enable_stream_k(e, pd);
     {
       ProfScope ps(e, st, PC_DOWN);
-      RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
+      if (!(skip >> PC_DOWN & 1)) RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
     }
   }
   CombineParams c;
@@ -929,7 +932,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_COMBINE);
-    LAUNCH_ROW_KERNEL(combine_kernel, d, row_blocks(M), st, c);
+    if (!(skip >> PC_COMBINE & 1)) LAUNCH_ROW_KERNEL(combine_kernel, d, row_blocks(M), st, c);
   }
   CU_OK(cudaGetLastError());
   e->launch_count += fused_mlp ? 6 : 7;
