@@ -9,6 +9,7 @@
 // scores, P rounded to bf16 before PV, fp32 row sum, bf16 output.
 #pragma once
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace mode {
 
@@ -47,6 +48,9 @@ struct AttnParams {
   int B, T, H;
   float eps;                 // RMSNorm eps (1e-6)
   float inv_sqrt_dh;         // float(Dh ** -0.5): RMSNorm scale (modedit.py:75) and the SDPA softmax scale
+  // training only: dropout on the attention probabilities (SDPA dropout_p, modedit.py:149); thr == 0 disables it.
+  // Element (b, h, row, col) uses half (col & 1) of word ((b*H + h)*T + row) * ceil(T/2) + col/2 of stream RNG_ATTN.
+  DropoutSpec drop = DropoutSpec{0u, 0u, 1.0f};
 };
 
 // DH: head dim (32/64/128). MT: number of 16-row tiles covering T (T_pad = 16*MT).
@@ -182,6 +186,21 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
     sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
     sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
     sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+    if (p.drop.thr) {  // zero the dropped probabilities; the row sums above stay those of the full softmax
+      const uint32_t thalf = static_cast<uint32_t>(T + 1) >> 1;
+      const uint32_t w_lo = (static_cast<uint32_t>(item) * T + row_lo) * thalf, w_hi = (static_cast<uint32_t>(item) * T + row_hi) * thalf;
+#pragma unroll
+      for (int nj = 0; nj < 2 * MT; ++nj) {
+        if (nj <= 2 * mi + 1) {
+          const uint32_t cw = static_cast<uint32_t>(nj * 4 + tq);  // (nj*8 + 2*tq) / 2
+          const uint32_t b_lo = rng_bits(p.drop.key, w_lo + cw), b_hi = rng_bits(p.drop.key, w_hi + cw);
+          if ((b_lo & 0xffffu) < p.drop.thr) s[nj][0] = 0.f;
+          if ((b_lo >> 16) < p.drop.thr) s[nj][1] = 0.f;
+          if ((b_hi & 0xffffu) < p.drop.thr) s[nj][2] = 0.f;
+          if ((b_hi >> 16) < p.drop.thr) s[nj][3] = 0.f;
+        }
+      }
+    }
 
     // ---- O = P V (P rounded to bf16, unnormalised; divide by the fp32 row sum at the end)
     float o[DH / 8][4];
@@ -202,7 +221,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
         }
       }
     }
-    const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+    const float keep_scale = p.drop.thr ? p.drop.scale : 1.0f;
+    const float inv_lo = keep_scale / sum_lo, inv_hi = keep_scale / sum_hi;
     // ---- stage O through this tile's (now dead) Q rows so the global store is 16-byte coalesced
     __syncwarp();
 #pragma unroll

@@ -230,6 +230,9 @@ struct SwigluBwdParams {
   const GemmMTile* tiles;    // this layer's up-projection tile table (tile i covers rows [i*tile_m, (i+1)*tile_m))
   const int* num_tiles;
   int tile_m, F;             // F = 4d
+  DropoutSpec drop = DropoutSpec{0u, 0u, 1.0f};  // the forward's dropout on h (gemm.cuh SwiGLU epilogue): d swiglu = dH o keep / (1 - p)
+  const int* row_token = nullptr;  // [P] token of every permuted row
+  int E = 1, rows_per_expert = 1;    // expert of a tile = (w_row_base / rows_per_expert) % E
 };
 __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const SwigluBwdParams p) {
   pdl_trigger();
@@ -254,9 +257,21 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const SwigluBwdParams p
     const __nv_bfloat162* dh2 = reinterpret_cast<const __nv_bfloat162*>(&rdh);
     uint32_t* o1 = reinterpret_cast<uint32_t*>(&ozp);
     uint32_t* o2 = reinterpret_cast<uint32_t*>(&ozg);
+    uint32_t word0 = 0;
+    if (p.drop.thr) {
+      const uint32_t token = static_cast<uint32_t>(p.row_token[row]);
+      const uint32_t expert = static_cast<uint32_t>((tile.w_row_base / p.rows_per_expert) % p.E);
+      word0 = (token * p.E + expert) * static_cast<uint32_t>(p.F / 2) + static_cast<uint32_t>(c) / 2u;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 zp = __bfloat1622float2(zp2[j]), zg = __bfloat1622float2(zg2[j]), dh = __bfloat1622float2(dh2[j]);
+      const float2 zp = __bfloat1622float2(zp2[j]), zg = __bfloat1622float2(zg2[j]);
+      float2 dh = __bfloat1622float2(dh2[j]);
+      if (p.drop.thr) {
+        const uint32_t bits = rng_bits(p.drop.key, word0 + j);
+        dh.x = (bits & 0xffffu) < p.drop.thr ? 0.f : dh.x * p.drop.scale;
+        dh.y = (bits >> 16) < p.drop.thr ? 0.f : dh.y * p.drop.scale;
+      }
       const float s0 = 1.0f / (1.0f + __expf(-zg.x)), s1 = 1.0f / (1.0f + __expf(-zg.y));
       o1[j] = pack_bf16x2(dh.x * zg.x * s0, dh.y * zg.y * s1);
       o2[j] = pack_bf16x2(dh.x * zp.x * s0 * (1.0f + zg.x * (1.0f - s0)), dh.y * zp.y * s1 * (1.0f + zg.y * (1.0f - s1)));
@@ -499,6 +514,7 @@ struct AttnBwdParams {
   float* gk_part;
   int B, T, H;
   float eps, inv_sqrt_dh;
+  DropoutSpec drop = DropoutSpec{0u, 0u, 1.0f};  // the forward's attention-probability dropout (attention.cuh); thr == 0: none
 };
 constexpr int ATTN_BWD_MAX_T = 32;
 __host__ __device__ constexpr int attn_bwd_floats_per_warp(int T, int DH) {
@@ -590,10 +606,17 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const At
     const float e = on ? __expf(P[i * ATTN_BWD_MAX_T + lane] - mx) : 0.f;
     const float den = warp_sum(e);
     const float pij = e / den;
-    const float dpij = on ? dS[i * ATTN_BWD_MAX_T + lane] : 0.f;
+    // dropout: O = (P o m) V with m = keep / (1 - p)  ->  dP = (dO V^T) o m, and dV sees P o m
+    float m = 1.0f;
+    if (p.drop.thr) {
+      const uint32_t word = (static_cast<uint32_t>(item) * T + i) * (static_cast<uint32_t>(T + 1) >> 1) + (lane >> 1);
+      const uint32_t bits = rng_bits(p.drop.key, word);
+      m = (((lane & 1) ? (bits >> 16) : (bits & 0xffffu)) < p.drop.thr) ? 0.f : p.drop.scale;
+    }
+    const float dpij = on ? dS[i * ATTN_BWD_MAX_T + lane] * m : 0.f;
     const float rowdot = warp_sum(pij * dpij);
     if (lane < T) {
-      P[i * ATTN_BWD_MAX_T + lane] = pij;
+      P[i * ATTN_BWD_MAX_T + lane] = pij * m;
       dS[i * ATTN_BWD_MAX_T + lane] = pij * (dpij - rowdot) * p.inv_sqrt_dh;
     }
     __syncwarp();
@@ -666,6 +689,7 @@ struct RouterBwdParams {
   float* hid;             // [B, Hd] fp32 (for the W2 gradient)
   int B, T, E, K, Hd;
   int normalize;
+  int per_token = 0;      // 1: sel_idx is [B*T, K] (multinomial routing draws per token); 0: [B, K] shared by the sample
 };
 // One CTA per sample: every warp recomputes the (tiny) per-expert prelude, the 2d hidden units are split over the CTA.
 __global__ void __launch_bounds__(ROW_WARPS * 32) router_bwd_kernel(const RouterBwdParams p) {
@@ -675,25 +699,32 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_bwd_kernel(const Router
   const int lane = threadIdx.x & 31;
   // lane e owns expert e
   const float pe = lane < p.E ? p.probs[b * p.E + lane] : 0.f;
-  float dwk = 0.f;   // d w for the slot whose expert is this lane
-  bool selected = false;
-  for (int k = 0; k < p.K; ++k) {
-    const int e = p.sel_idx[b * p.K + k];
-    float s = 0.f;
-    for (int t = 0; t < p.T; ++t) s += p.dw_row[(b * p.T + t) * p.K + k];
-    if (lane == e) {
-      dwk = s;
-      selected = true;
-    }
-  }
-  // w_e = p_e / S over selected (normalize) -> d p_e = (dw_e - sum_sel(dw w)) / S
   float dp = 0.f;
-  if (p.normalize) {
-    const float S = warp_sum(selected ? pe : 0.f);
-    const float dot = warp_sum(selected ? dwk * pe / S : 0.f);
-    dp = selected ? (dwk - dot) / S : 0.f;
-  } else {
-    dp = selected ? dwk : 0.f;
+  // per_token: every token has its own selection; d p accumulates over the sample's tokens (the probabilities are shared)
+  for (int tt = 0; tt < (p.per_token ? p.T : 1); ++tt) {
+    float dwk = 0.f;   // d w for the slot whose expert is this lane
+    bool selected = false;
+    for (int k = 0; k < p.K; ++k) {
+      const int e = p.per_token ? p.sel_idx[(b * p.T + tt) * p.K + k] : p.sel_idx[b * p.K + k];
+      float s = 0.f;
+      if (p.per_token) {
+        s = p.dw_row[(b * p.T + tt) * p.K + k];
+      } else {
+        for (int t = 0; t < p.T; ++t) s += p.dw_row[(b * p.T + t) * p.K + k];
+      }
+      if (lane == e) {
+        dwk = s;
+        selected = true;
+      }
+    }
+    // w_e = p_e / S over selected (normalize) -> d p_e = (dw_e - sum_sel(dw w)) / S
+    if (p.normalize) {
+      const float S = warp_sum(selected ? pe : 0.f);
+      const float dot = warp_sum(selected ? dwk * pe / S : 0.f);
+      dp += selected ? (dwk - dot) / S : 0.f;
+    } else {
+      dp += selected ? dwk : 0.f;
+    }
   }
   // clamp(p, 1e-9, 1-1e-9): gradient passes only strictly inside the interval
   if (!(pe > 1e-9f && pe < 1.0f - 1e-9f)) dp = 0.f;

@@ -143,6 +143,17 @@ __global__ void set_schedule_kernel(const ScheduleArg a, float* __restrict__ sig
   }
 }
 
+// Training-mode goal masking (MoDeDiT.mask_cond, modedit.py:882-893): every goal feature is zeroed independently with
+// probability cond_mask_prob, no rescaling. Element i uses half (i & 1) of word i/2 of stream RNG_GOAL. With `grad` set
+// the same mask is applied in place to the gradient w.r.t. the goal instead.
+__global__ void goal_mask_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, uint32_t key, uint32_t thr) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t bits = rng_bits(key, static_cast<uint32_t>(i >> 1));
+  const bool dropped = ((i & 1) ? (bits >> 16) : (bits & 0xffffu)) < thr;
+  out[i] = dropped ? 0.f : in[i];
+}
+
 // noised = action + noise * sigma  (GCDenoiser.loss, score_wrappers.py:59)
 __global__ void noise_actions_kernel(const float* __restrict__ action, const float* __restrict__ noise,
                                      const float* __restrict__ sigma, float* __restrict__ out, int per_sample, int n) {
@@ -230,6 +241,18 @@ struct mode_engine {
   cudaEvent_t weights_ready = nullptr;  // recorded on the default stream after the last (re)pack
   bool weights_wait_pending = false;
   TrainState* train = nullptr;  // lazily created by the first training call
+
+  // stochastic training mode (mode_train_set_stochastic): dropout probabilities, multinomial routing, RNG position
+  struct {
+    float p_attn = 0.f, p_mlp = 0.f, p_goal = 0.f;
+    int multinomial = 0;
+    unsigned long long seed = 0;
+    uint32_t step = 0;
+  } stoch;
+  bool stoch_active = false;  // true only while mode_train_step enqueues its forward/backward
+  // token-level routing tables [L][maxB*T][K] (multinomial routing draws per token), permuted-row -> token map
+  int *tok_topk_idx = nullptr, *tok_sel_idx = nullptr, *tok_pos = nullptr, *row_token = nullptr;
+  float *tok_topk_w = nullptr, *tok_sel_w = nullptr, *goal_masked = nullptr;
 
   // optional per-kernel-class timing (mode_profile_eval): event pairs around every launch of one evaluation
   bool prof_on = false;
@@ -775,6 +798,11 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.sk_enable = 0;
   p.sk_partials = nullptr;
   p.sk_flags = nullptr;
+  p.drop = DropoutSpec{0u, 0u, 1.0f};
+  p.row_token = nullptr;
+  p.drop_rows_per_expert = 1;
+  p.drop_E = 1;
+  p.drop_half_F = 0;
   return p;
 }
 // Stream-K over the last partial wave (QKV, expert up/down). Correct (tests/test_kernels_gpu.py) but OFF by default:
@@ -824,6 +852,28 @@ static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* sta
   return MODE_OK;
 }
 
+// Routing tables of layer l as the routed kernels see them: `units` routing units of `rt` token rows each.
+struct RouteView {
+  const int* sel_idx;
+  const float* sel_w;
+  int* pos;
+  int units, rt;
+  bool per_token;
+};
+static inline bool token_routing(const mode_engine* e) { return e->stoch_active && e->stoch.multinomial; }
+static RouteView route_view(mode_engine* e, int B, size_t lt, int l) {
+  if (token_routing(e)) {
+    const size_t o = (size_t)l * B * e->T * e->K;
+    return RouteView{e->tok_sel_idx + o, e->tok_sel_w + o, e->tok_pos + o, B * e->T, 1, true};
+  }
+  const size_t o = lt * B * e->K;
+  return RouteView{e->sel_idx + o, e->sel_w + o, e->pos_tab + o, B, e->T, false};
+}
+static DropoutSpec dropout_spec(const mode_engine* e, float p, uint32_t stream, int layer) {
+  if (!e->stoch_active || p <= 0.f) return DropoutSpec{0u, 0u, 1.0f};
+  return DropoutSpec{rng_key(e->stoch.seed, e->stoch.step, stream, (uint32_t)layer), drop_threshold(p), 1.0f / (1.0f - p)};
+}
+
 // Routes `n_slots` evaluations at once: slot s uses sigma + s * sigma_slot_stride (a whole sampler schedule in one
 // launch), tables [slot][L][B][..].
 static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* z_explicit,
@@ -838,6 +888,11 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   r.probs = e->probs; r.logits = e->logits;
   r.L = n_layers; r.layer0 = layer0; r.B = B; r.E = e->E; r.K = e->K; r.Hd = e->Hd; r.normalize = e->cfg.router_normalize;
   r.slot0 = slot0; r.Ltot = e->L; r.sigma_slot_stride = sigma_slot_stride;
+  const bool tok = token_routing(e);
+  if (tok && (stride != 1 || n_slots != 1 || layer0 != 0 || n_layers != e->L))
+    return fail(MODE_ERR_STATE, "per-token multinomial routing needs per-sample sigma and a full-network evaluation");
+  r.multinomial = tok ? 1 : 0; r.T = e->T; r.seed = e->stoch.seed; r.step = e->stoch.step;
+  r.tok_topk_idx = e->tok_topk_idx; r.tok_topk_w = e->tok_topk_w; r.tok_sel_idx = e->tok_sel_idx; r.tok_sel_w = e->tok_sel_w;
   const int distinct_rows = (stride == 0 && !z_explicit) ? 1 : B;
   CU_OK(launch_k(router_kernel, dim3(n_slots * n_layers * distinct_rows), dim3(ROW_WARPS * 32), 0, st, r));
   PlanParams pl;
@@ -846,6 +901,10 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   pl.num_tiles = e->num_tiles; pl.usage = e->usage; pl.tokens = e->tokens;
   pl.L = e->L; pl.B = B; pl.K = e->K; pl.E = e->E; pl.T = e->T; pl.max_tiles = e->max_tiles;
   pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0; pl.tile_m = e->tile_m; pl.slot0 = slot0; pl.n_layers = n_layers;
+  pl.route_lt_sub = 0;
+  if (tok) {  // token-level tables have no slot dimension; the tile tables stay in the evaluation slot
+    pl.sel_idx = e->tok_sel_idx; pl.pos = e->tok_pos; pl.B = B * e->T; pl.T = 1; pl.route_lt_sub = slot0 * e->L;
+  }
   CU_OK(launch_k(plan_kernel, dim3(n_slots * n_layers), dim3(256), 0, st, pl));
   e->last_slot = slot0 + n_slots - 1;
   CU_OK(cudaGetLastError());
@@ -870,6 +929,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   AttnParams a;
   a.qkv = io.qkv; a.out = io.attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
   a.B = B; a.T = e->T; a.H = e->H; a.eps = e->cfg.rms_eps; a.inv_sqrt_dh = e->inv_sqrt_dh;
+  a.drop = dropout_spec(e, e->stoch.p_attn, RNG_ATTN, l);
   {
     ProfScope ps(e, st, PC_ATTN);
     if (!(skip >> PC_ATTN & 1)) RET_IF(launch_attn(st, a, e->Dh));
@@ -881,8 +941,12 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     if (!(skip >> PC_PROJ & 1)) RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
   Ln2Params n2;
-  n2.x = io.x1; n2.x_out = io.xn; n2.g = e->ln2_g + (size_t)l * d; n2.pos = e->pos_tab + lt * B * e->K; n2.perm = io.perm;
-  n2.B = B; n2.T = e->T; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
+  const RouteView rv = route_view(e, B, lt, l);
+  const DropoutSpec mlp_drop = dropout_spec(e, e->stoch.p_mlp, RNG_MLP, l);
+  n2.x = io.x1; n2.x_out = io.xn; n2.g = e->ln2_g + (size_t)l * d; n2.pos = rv.pos; n2.perm = io.perm;
+  int* row_token = mlp_drop.thr ? e->row_token + (size_t)l * e->perm_rows : nullptr;  // [L][perm_rows], training only
+  n2.row_token = row_token;
+  n2.B = rv.units; n2.T = rv.rt; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
   const bool fused_mlp = e->mlp_fused && !io.z;  // the training forward keeps the two-launch path (it saves z)
   n2.zero = fused_mlp ? e->mlp_sync : nullptr;
   n2.n_zero = 1 + e->max_tiles;
@@ -913,6 +977,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
       ProfScope ps(e, st, PC_UP);
       if (io.z) {  // training: also keep the pre-activations for the SwiGLU backward
         p.tmap_out2 = io.to_z;
+        p.drop = mlp_drop; p.row_token = row_token; p.drop_rows_per_expert = 8 * d; p.drop_E = e->E; p.drop_half_F = e->F / 2;
         RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
       } else if (!(skip >> PC_UP & 1)) {
         RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
@@ -926,10 +991,10 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   }
   CombineParams c;
   c.x = io.xn; c.x_out = io.x_out; c.x_copy = io.x_out_copy; c.y = io.y;
-  c.pos = e->pos_tab + lt * B * e->K; c.w = e->sel_w + lt * B * e->K;
+  c.pos = rv.pos; c.w = rv.sel_w;
   c.g_next = (combine_mode == 0) ? e->ln1_g + (size_t)(l + 1) * d : e->lnf_g;
   c.cvec = e->cvec; c.hA = io.hA_next; c.xnorm = e->xnorm;
-  c.B = B; c.T = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
+  c.B = rv.units; c.T = rv.rt; c.Tc = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_COMBINE);
     if (!(skip >> PC_COMBINE & 1)) LAUNCH_ROW_KERNEL(combine_kernel, d, row_blocks(M), st, c);

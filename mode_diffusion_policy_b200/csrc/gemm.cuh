@@ -12,6 +12,7 @@
 // (TMA <-> MMA), two TMEM accumulators of 128x256 fp32 with full/empty mbarriers (MMA <-> epilogue).
 #pragma once
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace mode {
 
@@ -64,6 +65,14 @@ struct alignas(64) GemmParams {
   int sk_enable;
   float4* sk_partials;         // [grid CTAs][8 chunks][8 vec][128 rows] fp32 partial accumulators (128 KB per CTA)
   int* sk_flags;               // [grid CTAs][4 epilogue warps], 0 between kernels
+  // EPI_SWIGLU_SAVE only (training): nn.Dropout between SwishGLU and the down projection (modedit.py:254) applied to h
+  // in the epilogue. Hidden unit j of token m in expert e uses half (j & 1) of word (m*E + e)*(F/2) + j/2 of stream
+  // RNG_MLP; row_token maps a permuted row to its token (written by ln2_permute_kernel). drop.thr == 0: no dropout.
+  DropoutSpec drop;
+  const int* row_token;
+  int drop_rows_per_expert;    // weight rows per expert (8d): expert = (w_row_base / this) % drop_E
+  int drop_E;
+  int drop_half_F;             // F / 2 = 2d
 };
 
 // Work decomposition of the CTA-pair kernel. Tiles of full waves are data-parallel (tile = worker + i * P). The last,
@@ -179,10 +188,16 @@ __device__ __forceinline__ void wait_flag(const int* flag) {
   } while (!v);
 }
 
-template <int EPI>
+// per-lane dropout state of the SwiGLU epilogue: word index of this row's hidden unit 0
+struct EpiDrop {
+  uint32_t key, thr, base;
+  float scale;
+};
+template <int EPI, bool DROP = false>
 __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, uint32_t taddr, uint32_t stage_smem, int lane,
                                                    int out_row0, const float* sbias, int nb, uint32_t& n_stores,
-                                                   const SkParts sk = SkParts{nullptr, 0, 0}) {
+                                                   const SkParts sk = SkParts{nullptr, 0, 0},
+                                                   const EpiDrop dr = EpiDrop{0, 0, 0, 1.0f}) {
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
   auto chunk_addr = [&](uint32_t buf, uint32_t j) { return buf + row_off + ((j ^ sw) << 4); };
@@ -224,10 +239,18 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
           for (int u = 0; u < 2; ++u) {
             const float4 b0 = bp[2 * j + u], b1 = bg[2 * j + u];
             const int o = 8 * j + 4 * u;
-            const float h0 = (__uint_as_float(rp[o + 0]) + b0.x) * silu_f(__uint_as_float(rg[o + 0]) + b1.x);
-            const float h1 = (__uint_as_float(rp[o + 1]) + b0.y) * silu_f(__uint_as_float(rg[o + 1]) + b1.y);
-            const float h2 = (__uint_as_float(rp[o + 2]) + b0.z) * silu_f(__uint_as_float(rg[o + 2]) + b1.z);
-            const float h3 = (__uint_as_float(rp[o + 3]) + b0.w) * silu_f(__uint_as_float(rg[o + 3]) + b1.w);
+            float h0 = (__uint_as_float(rp[o + 0]) + b0.x) * silu_f(__uint_as_float(rg[o + 0]) + b1.x);
+            float h1 = (__uint_as_float(rp[o + 1]) + b0.y) * silu_f(__uint_as_float(rg[o + 1]) + b1.y);
+            float h2 = (__uint_as_float(rp[o + 2]) + b0.z) * silu_f(__uint_as_float(rg[o + 2]) + b1.z);
+            float h3 = (__uint_as_float(rp[o + 3]) + b0.w) * silu_f(__uint_as_float(rg[o + 3]) + b1.w);
+            if constexpr (DROP) {
+              const uint32_t w = dr.base + static_cast<uint32_t>(nb * 128 + c32 + o) / 2u;
+              const uint32_t r0 = rng_bits(dr.key, w), r1 = rng_bits(dr.key, w + 1u);
+              h0 = (r0 & 0xffffu) < dr.thr ? 0.f : h0 * dr.scale;
+              h1 = (r0 >> 16) < dr.thr ? 0.f : h1 * dr.scale;
+              h2 = (r1 & 0xffffu) < dr.thr ? 0.f : h2 * dr.scale;
+              h3 = (r1 >> 16) < dr.thr ? 0.f : h3 * dr.scale;
+            }
             pk[2 * u] = pack_bf16x2(h0, h1);
             pk[2 * u + 1] = pack_bf16x2(h2, h3);
           }
@@ -293,10 +316,17 @@ __device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, in
 template <int EPI>
 __device__ __forceinline__ void gemm_epilogue_dispatch(const GemmParams& p, uint32_t taddr, uint32_t stage_smem, int lane,
                                                        int out_row0, const float* sbias, int nb, uint32_t& n_stores,
-                                                       const SkParts sk = SkParts{nullptr, 0, 0}) {
+                                                       int w_row_base, const SkParts sk = SkParts{nullptr, 0, 0}) {
   if constexpr (EPI == EPI_SWIGLU_SAVE) {
     gemm_epilogue_warp<EPI_BIAS_BF16>(&p.tmap_out2, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
-    gemm_epilogue_warp<EPI_SWIGLU_BF16>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
+    if (p.drop.thr) {
+      const uint32_t token = static_cast<uint32_t>(p.row_token[out_row0 + lane]);
+      const uint32_t expert = static_cast<uint32_t>((w_row_base / p.drop_rows_per_expert) % p.drop_E);
+      const EpiDrop dr{p.drop.key, p.drop.thr, (token * p.drop_E + expert) * static_cast<uint32_t>(p.drop_half_F), p.drop.scale};
+      gemm_epilogue_warp<EPI_SWIGLU_BF16, true>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk, dr);
+    } else {
+      gemm_epilogue_warp<EPI_SWIGLU_BF16>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
+    }
   } else {
     gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
   }
@@ -423,7 +453,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tc_fence_after();
       if (q * 32 < tile.rows_valid) {  // warp-uniform: this warp's 32 rows hold at least one real row
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * GEMM_BLOCK_N;
-        gemm_epilogue_dispatch<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + q * 32, sbias, nb, n_stores);
+        gemm_epilogue_dispatch<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + q * 32, sbias, nb, n_stores, tile.w_row_base);
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld): hand it back to the MMA warp
       tc_fence_before();
@@ -599,7 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             sk.base = p.sk_partials + static_cast<size_t>(first) * kSlot;
             for (int i = 0; i < sk.n; ++i) wait_flag(p.sk_flags + (first + 2 * i) * 4 + q);
           }
-          gemm_epilogue_dispatch<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, sbias, nb, n_stores, sk);
+          gemm_epilogue_dispatch<EPI>(p, taddr, stage_smem, lane, tile.out_row0 + row0, sbias, nb, n_stores, tile.w_row_base, sk);
           if (sk.n > 0) {
             __syncwarp();
             if (lane == 0)

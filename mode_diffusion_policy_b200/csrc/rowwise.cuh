@@ -5,6 +5,7 @@
 #pragma once
 #include "gemm_wgrad.cuh"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace mode {
 
@@ -215,6 +216,17 @@ struct RouterParams {
   // (slot = sampler step) ahead of the captured denoising loop; plain evaluations use a single slot.
   int slot0, Ltot;   // first slot written; layers per slot in the table layout
   int sigma_slot_stride;  // sigma of slot s starts at sc.sigma + s * sigma_slot_stride
+  // Training with use_argmax=False (modedit.py:389-390): every TOKEN draws its K experts with torch.multinomial(probs, K,
+  // replacement=False) semantics, i.e. K sequential draws proportional to the remaining clamped probabilities. Draw k
+  // of token m inverts the CDF over the remaining experts (ascending index) at u * S, u = rng_uniform(bits(m*K + k)) of
+  // stream RNG_ROUTE, S = fp32 sum of the remaining probabilities in ascending order. Tables [L][B*T][K], layer-major.
+  int multinomial = 0, T = 1;
+  unsigned long long seed = 0;
+  uint32_t step = 0;
+  int* tok_topk_idx = nullptr;   // draw order (what torch.multinomial returns)
+  float* tok_topk_w = nullptr;
+  int* tok_sel_idx = nullptr;    // ascending expert order
+  float* tok_sel_w = nullptr;
 };
 
 // One CTA (8 warps) per (layer, distinct sigma row): each warp covers Hd/8 hidden units, partial logits are reduced
@@ -360,6 +372,55 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_kernel(const RouterPara
         p.sel_w[pk + k] = srtp[k];
       }
   }
+  if (!p.multinomial) return;
+  // ---- per-token multinomial draws (lane t handles token t of this sample); part[0][e] holds the clamped probabilities
+  const uint32_t key = rng_key(p.seed, p.step, RNG_ROUTE, static_cast<uint32_t>(l));
+  for (int t = lane; t < p.T; t += 32) {
+    const uint32_t m = static_cast<uint32_t>(b) * p.T + t;
+    uint32_t avail = p.E >= 32 ? 0xffffffffu : ((1u << p.E) - 1u);
+    int dr[MAX_TOPK];
+    float dw[MAX_TOPK];
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAX_TOPK; ++k) {
+      dr[k] = 0;
+      dw[k] = 0.f;
+      if (k < p.K) {
+        float S = 0.f;
+        for (int e = 0; e < p.E; ++e)
+          if (avail >> e & 1u) S = __fadd_rn(S, part[0][e]);
+        const float target = __fmul_rn(rng_uniform(rng_bits(key, m * p.K + k)), S);
+        float cum = 0.f;
+        int chosen = -1, last = 0;
+        for (int e = 0; e < p.E; ++e)
+          if (avail >> e & 1u) {
+            last = e;
+            cum = __fadd_rn(cum, part[0][e]);
+            if (chosen < 0 && target < cum) chosen = e;
+          }
+        if (chosen < 0) chosen = last;
+        avail &= ~(1u << chosen);
+        dr[k] = chosen;
+        dw[k] = part[0][chosen];
+        tot = __fadd_rn(tot, dw[k]);
+      }
+    }
+    const size_t o = (static_cast<size_t>(l) * p.B * p.T + m) * p.K;
+#pragma unroll
+    for (int k = 0; k < MAX_TOPK; ++k) {
+      if (k < p.K) {
+        const float w = p.normalize ? dw[k] / tot : dw[k];
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < MAX_TOPK; ++j)
+          if (j < p.K && dr[j] < dr[k]) ++rank;
+        p.tok_topk_idx[o + k] = dr[k];
+        p.tok_topk_w[o + k] = w;
+        p.tok_sel_idx[o + rank] = dr[k];
+        p.tok_sel_w[o + rank] = w;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -385,6 +446,7 @@ struct PlanParams {
   int layer0;                    // first layer handled by blockIdx.x == 0 (block-level entry plans a single layer)
   int tile_m;                    // rows per GEMM M-tile (128 single-CTA, 256 CTA-pair): groups are padded to it
   int slot0, n_layers;           // grid = n_slots * n_layers CTAs: slot = slot0 + blockIdx.x / n_layers
+  int route_lt_sub = 0;              // subtracted from the table-layer index for sel_idx / pos (token-level tables: no slots)
 };
 
 __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
@@ -397,8 +459,8 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
   __shared__ int cnt[MAX_EXPERTS];
   __shared__ int grp_row0[MAX_EXPERTS];
   __shared__ int grp_tile0[MAX_EXPERTS + 1];
-  const int* sel = p.sel_idx + static_cast<size_t>(lt) * p.B * p.K;
-  int* pos = p.pos + static_cast<size_t>(lt) * p.B * p.K;
+  const int* sel = p.sel_idx + static_cast<size_t>(lt - p.route_lt_sub) * p.B * p.K;
+  int* pos = p.pos + static_cast<size_t>(lt - p.route_lt_sub) * p.B * p.K;
   // pass 1: rank of every (sample, slot) inside its expert group; stored temporarily in pos
   for (int e = 0; e < p.E; ++e) {
     int running = 0;
@@ -480,7 +542,10 @@ struct Ln2Params {
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
   int* zero;         // tile queue + dependency counters of the fused expert-MLP kernel that follows (or null)
   int n_zero;
+  int* row_token = nullptr;  // optional [rows_perm]: token row of every permuted row (MLP dropout of the training path)
 };
+// (B, T) of the routed kernels are ROUTING units x rows per unit: (samples, tokens per sample) when all tokens of a
+// sample share their experts (eval / arg-max routing), (B*T tokens, 1) under per-token multinomial routing.
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln2Params p) {
   pdl_trigger();
@@ -518,6 +583,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln
       for (int k = 0; k < MAX_TOPK; ++k)
         if (k < p.K) *reinterpret_cast<uint2*>(p.perm + static_cast<size_t>(dst_row[k]) * p.d + col) = pk;
     }
+  if (p.row_token && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < MAX_TOPK; ++k)
+      if (k < p.K) p.row_token[dst_row[k]] = row;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -538,6 +608,7 @@ struct CombineParams {
   float* xnorm;                // [B*T, d] (mode 1: final ln output, fp32)
   int B, T, K, d;
   int mode;                    // 0: next block's ln_1 + c -> hA ; 1: final ln -> xnorm ; 2: none (block-level entry)
+  int Tc;                      // token rows per cvec row (tokens per sample; differs from T under per-token routing)
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
@@ -592,7 +663,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const Combin
       const float4 y = make_float4((x.x * rn) * g.x, (x.y * rn) * g.y, (x.z * rn) * g.z,
                                    (x.w * rn) * g.w);
       if (p.mode == 0) {
-        const float4 c = *reinterpret_cast<const float4*>(p.cvec + static_cast<size_t>(b) * p.d + col);
+        const float4 c = *reinterpret_cast<const float4*>(p.cvec + static_cast<size_t>(row / p.Tc) * p.d + col);
         *reinterpret_cast<uint2*>(p.hA + static_cast<size_t>(row) * p.d + col) =
             make_uint2(pack_bf16x2(y.x + c.x, y.y + c.y), pack_bf16x2(y.z + c.z, y.w + c.w));
       } else {

@@ -165,6 +165,22 @@ class ModeEngine:
                                             sigma.data_ptr(), loss.data_ptr(), out.data_ptr(), B, self._stream()))
         return loss[0], out
 
+    def set_stochastic(self, attn_pdrop=0.0, mlp_pdrop=0.0, goal_drop=0.0, multinomial=False, seed=0, step=0):
+        """Stochastic regularisation of the reference's train mode for the following `train_step` calls (attention /
+        expert-MLP dropout, goal masking, per-token multinomial routing; reference modedit.py:149, :254, :882-893,
+        :389-390). The masks are a pure function of (seed, step, ...): `step` advances by one per stochastic step."""
+        _lib.check(self.lib.mode_train_set_stochastic(self._h, float(attn_pdrop), float(mlp_pdrop), float(goal_drop),
+                                                      int(bool(multinomial)), int(seed) & (2 ** 64 - 1), int(step)))
+
+    def token_routing(self, layer: int, batch: int):
+        """(expert indices in draw order, renormalised probabilities), each [batch*T, top_k], of the last multinomial
+        training step."""
+        n = batch * self.cfg.seq_len
+        idx = np.zeros((n, self.cfg.top_k), dtype=np.int32)
+        w = np.zeros((n, self.cfg.top_k), dtype=np.float32)
+        _lib.check(self.lib.mode_train_get_token_routing(self._h, layer, batch, idx.ctypes.data, w.ctypes.data))
+        return idx, w
+
     def flat_grads(self) -> torch.Tensor:
         """Zero-copy torch view of the engine-owned flat fp32 gradient buffer (one all-reduce synchronises DP ranks)."""
         if getattr(self, "_flat", None) is None:

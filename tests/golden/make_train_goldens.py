@@ -77,3 +77,119 @@ if __name__ == "__main__":
                                                           n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2), 5)
     golden_train("model_wide_d512_l2_e8", MG.O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=512, n_layers=2,
                                                           n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=8, top_k=2), 4)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Stochastic training mode (the reference's default: attn_pdrop 0.3, mlp_pdrop 0.1, goal_drop 0.1, use_argmax=False).
+# torch's generator cannot be reproduced by the engine, so the REFERENCE is run with the engine's masks instead: the
+# four random sources are patched to read oracle/mode_rng.py (the numpy restatement of csrc/rng.cuh) —
+#   torch.bernoulli (MoDeDiT.mask_cond, modedit.py:888), F.scaled_dot_product_attention's dropout_p (:149),
+#   nn.Dropout inside every expert Mlp (:254), torch.multinomial (RouterCond, :389-390)
+# — everything else (modules, autograd) is the reference's own code.
+def golden_train_stochastic(tag, cfg, B, seed, step, p_attn=0.3, p_mlp=0.1, p_goal=0.1, router_gain=4.0):
+    import math
+
+    from oracle import mode_rng as R
+
+    sd = O.make_weights(cfg, seed=1234, router_gain=router_gain)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cpu", goal_conditioned=True,
+                    action_dim=cfg.action_dim, embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=p_attn,
+                    n_layers=cfg.n_layers, n_heads=cfg.n_heads, goal_seq_len=1, obs_seq_len=1,
+                    action_seq_len=cfg.action_seq_len, state_dim=7, mlp_pdrop=p_mlp, goal_drop=p_goal,
+                    num_experts=cfg.num_experts, top_k=cfg.top_k, use_argmax=False, init_style="olmoe")
+    inner.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()})
+    model = GCDenoiser(inner, sigma_data=cfg.sigma_data).train()
+    T, E, K, H, F = cfg.seq_len, cfg.num_experts, cfg.top_k, cfg.n_heads, 4 * cfg.embed_dim
+    ctx = {"attn_calls": 0, "route_calls": 0, "masks": {}, "routing": {}}
+
+    def fake_bernoulli(pt, *a, **k):
+        bs, t, dd = pt.shape
+        keep = R.goal_keep_mask(seed, step, bs, dd, p_goal).reshape(bs, t, dd)
+        return torch.from_numpy((~keep).astype(np.float32))
+
+    def fake_sdpa(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False, **kw):
+        layer = ctx["attn_calls"] % cfg.n_layers
+        ctx["attn_calls"] += 1
+        assert is_causal and attn_mask is None
+        Bq, Hq, Tq, Dq = q.shape
+        att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(Dq))
+        causal = torch.tril(torch.ones(Tq, Tq)).view(1, 1, Tq, Tq)
+        att = torch.softmax(att.masked_fill(causal == 0, float("-inf")), dim=-1)
+        if dropout_p > 0:
+            keep = torch.from_numpy(R.attn_keep_mask(seed, step, layer, Bq, Hq, Tq, dropout_p).astype(np.float32))
+            att = att * keep / (1.0 - dropout_p)
+        return att @ v
+
+    def fake_multinomial(probs, k, replacement=False):
+        layer = ctx["route_calls"] % cfg.n_layers
+        ctx["route_calls"] += 1
+        assert not replacement and probs.shape[0] == B * T
+        idx = R.multinomial_draws(seed, step, layer, probs.detach().numpy()[::T], T, k)
+        ctx["routing"][layer] = idx
+        return torch.from_numpy(idx)
+
+    class MaskedDropout(torch.nn.Module):
+        def __init__(self, layer, expert, p):
+            super().__init__()
+            self.layer, self.expert, self.p = layer, expert, p
+
+        def forward(self, h):
+            tokens = ctx["masks"][self.layer][:, self.expert].nonzero()[0]
+            assert len(tokens) == h.shape[0]
+            keep = R.mlp_keep_mask(seed, step, self.layer, tokens, self.expert, E, F, self.p)
+            return h * torch.from_numpy(keep.astype(np.float32)) / (1.0 - self.p)
+
+    def router_hook(layer):
+        def hook(mod, args, out):
+            ctx["masks"][layer] = out[0].detach().reshape(B * T, E).numpy() > 0
+        return hook
+
+    for li, blk in enumerate(inner.blocks):
+        blk.router.register_forward_hook(router_hook(li))
+        for e in range(E):
+            mlp = blk.experts[f"expert_{e}"].mlp
+            assert isinstance(mlp[1], torch.nn.Dropout)
+            mlp[1] = MaskedDropout(li, e, p_mlp)
+
+    g = np.load(OUT / f"{tag}.npz")
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    st_in, goal_in = t(state).requires_grad_(True), t(goal).requires_grad_(True)
+    saved = (torch.bernoulli, torch.nn.functional.scaled_dot_product_attention, torch.multinomial)
+    torch.bernoulli, torch.nn.functional.scaled_dot_product_attention, torch.multinomial = fake_bernoulli, fake_sdpa, fake_multinomial
+    try:
+        with torch.enable_grad():
+            loss, f_out = model.loss({"state_images": st_in}, t(acts), goal_in, t(g["loss_noise"]), t(g["sigma_het"]))
+            loss.backward()
+    finally:
+        torch.bernoulli, torch.nn.functional.scaled_dot_product_attention, torch.multinomial = saved
+    assert ctx["attn_calls"] == cfg.n_layers and ctx["route_calls"] == cfg.n_layers
+    out = {"loss": np.float32(loss.item()), "F": f_out.detach().numpy(), "seed": np.int64(seed), "step": np.int64(step),
+           "p": np.array([p_attn, p_mlp, p_goal], np.float32), "router_gain": np.float32(router_gain)}
+    out["d_state"] = st_in.grad.numpy().copy()
+    out["d_goal"] = goal_in.grad.numpy().copy()
+    for li in range(cfg.n_layers):
+        out[f"routing/{li}"] = ctx["routing"][li].astype(np.int32)
+    names = [n for n, _ in O.state_dict_spec(cfg)]
+    params = dict(inner.named_parameters())
+    for pos, name in enumerate(names):
+        p = params[name]
+        grad = np.zeros(p.shape, np.float32) if p.grad is None else p.grad.numpy()
+        flat = grad.reshape(-1)
+        idx = sample_indices(flat.size, pos)
+        out[f"norm/{name}"] = np.float32(np.linalg.norm(flat.astype(np.float64)))
+        out[f"sum/{name}"] = np.float32(flat.astype(np.float64).sum())
+        out[f"val/{name}"] = flat[idx].astype(np.float32)
+    np.savez_compressed(OUT / f"train_stoch_{tag}.npz", **out)
+    usage = [np.bincount(ctx["routing"][li].reshape(-1), minlength=E).tolist() for li in range(cfg.n_layers)]
+    print(f"train_stoch_{tag}: loss {float(loss):.6f} (deterministic {float(g['loss_value']):.6f}); expert usage per layer {usage}")
+
+
+if __name__ == "__main__":
+    golden_train_stochastic("model_tiny_d256_l3_e4", MG.O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3,
+                                                                     n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2),
+                            5, seed=20261017, step=3)
+    golden_train_stochastic("model_wide_d512_l2_e8", MG.O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=512, n_layers=2,
+                                                                     n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=8, top_k=2),
+                            4, seed=77, step=0)

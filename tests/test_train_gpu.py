@@ -259,3 +259,93 @@ def test_fused_adamw_matches_torch_adamw_and_keeps_packed_weights_in_sync():
     assert not torch.equal(before, pb["out.weight"].detach())
     sd_opt = opt_b.state_dict()
     assert sd_opt["step"] == 4 and sd_opt["exp_avg"].abs().sum() > 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Stochastic training mode: the reference's default recipe (attn_pdrop 0.3, mlp_pdrop 0.1, goal_drop 0.1, per-token
+# multinomial routing). The goldens were produced by the REFERENCE's own modules and autograd with its four random
+# sources patched to the engine's counter-based bits (tests/golden/make_train_goldens.py::golden_train_stochastic), so
+# engine and reference see identical masks and identical expert draws.
+@pytest.mark.parametrize("tag", list(MODELS))
+def test_stochastic_training_matches_reference_with_the_same_masks(tag):
+    cfg, B = MODELS[tag]
+    g = np.load(GOLD / f"{tag}.npz")
+    gs = np.load(GOLD / f"train_stoch_{tag}.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=float(gs["router_gain"]))
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    eng = engine_for(cfg, sd, 8)
+    p_attn, p_mlp, p_goal = (float(v) for v in gs["p"])
+    seed, step = int(gs["seed"]), int(gs["step"])
+    args = (cu(state), cu(acts), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
+    eng.set_stochastic(p_attn, p_mlp, p_goal, True, seed, step)
+    loss, F = eng.train_step(*args)
+    torch.cuda.synchronize()
+    # per-token expert draws: bit-exact against torch.multinomial-semantics draws made by the reference run
+    for layer in range(cfg.n_layers):
+        idx, w = eng.token_routing(layer, B)
+        assert np.array_equal(idx, gs[f"routing/{layer}"]), f"layer {layer}: expert draws differ"
+        assert np.allclose(w.sum(axis=1), 1.0, atol=1e-6)
+    assert abs(float(loss) - float(gs["loss"])) <= 3e-2 * abs(float(gs["loss"])), (float(loss), float(gs["loss"]))
+    Fg = F.cpu().numpy()
+    assert np.linalg.norm(Fg - gs["F"]) <= 2e-2 * np.linalg.norm(gs["F"]), np.linalg.norm(Fg - gs["F"]) / np.linalg.norm(gs["F"])
+    rows = grad_report(eng, cfg, gs)
+    bad = []
+    for name, wn, gn, err in rows:
+        ok = (gn == 0.0) if wn == 0.0 else (err < 6e-2 and abs(gn - wn) <= 0.06 * wn)
+        if not ok:
+            bad.append((name, wn, gn, err))
+    worst = sorted(rows, key=lambda r: -r[3] if r[1] > 0 else 0)[:8]
+    print("worst sampled-entry relative errors (stochastic):", [(n, round(e, 4)) for n, _, _, e in worst])
+    assert not bad, bad[:12]
+    ds, dg = eng.input_grads(B, state.shape, goal.shape)
+    for got, want in ((ds, gs["d_state"]), (dg, gs["d_goal"])):
+        got = got.cpu().numpy().reshape(want.shape)
+        assert np.linalg.norm(got - want) <= 6e-2 * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
+    # the goal gradient is exactly zero where the goal feature was masked
+    from oracle import mode_rng as R
+    keep = R.goal_keep_mask(seed, step, B, cfg.goal_dim, p_goal)
+    assert not dg.cpu().numpy().reshape(B, -1)[~keep].any() and (~keep).any()
+    # reproducible from (seed, step): bit-identical replay; the step counter advanced, so a plain second call differs
+    flat = eng.flat_grads().clone()
+    loss_next, _ = eng.train_step(*args)  # step + 1: fresh masks
+    assert float(loss_next) != float(loss)
+    eng.set_stochastic(p_attn, p_mlp, p_goal, True, seed, step)
+    loss_again, _ = eng.train_step(*args)
+    assert float(loss_again) == float(loss) and torch.equal(flat, eng.flat_grads())
+    # switching the regularisation off restores the deterministic mode exactly
+    eng.set_stochastic()
+    loss_det, _ = eng.train_step(*args)
+    eng2 = engine_for(cfg, sd, 8)
+    loss_det2, _ = eng2.train_step(*args)
+    assert float(loss_det) == float(loss_det2) and torch.equal(eng.flat_grads(), eng2.flat_grads())
+
+
+def test_stochastic_pieces_one_at_a_time():
+    """Each regulariser alone changes the loss, and dropout masks hit the configured rate (expert-usage counters see
+    per-token draws: every token still selects exactly top_k experts)."""
+    cfg, B = MODELS["model_tiny_d256_l3_e4"]
+    g = np.load(GOLD / "model_tiny_d256_l3_e4.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=4.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    eng = engine_for(cfg, sd, 8)
+    args = (cu(state), cu(acts), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
+    base = float(eng.train_step(*args)[0])
+    seen = set()
+    for kw in ({"attn_pdrop": 0.3}, {"mlp_pdrop": 0.1}, {"goal_drop": 0.5}, {"multinomial": True}):
+        eng.set_stochastic(seed=5, step=1, **kw)
+        v = float(eng.train_step(*args)[0])
+        assert np.isfinite(v) and v != base, kw
+        assert torch.isfinite(eng.flat_grads()).all()
+        seen.add(v)
+    assert len(seen) == 4
+    eng.set_stochastic(multinomial=True, seed=9, step=0)
+    eng.reset_expert_usage()
+    eng.train_step(*args)
+    for layer in range(cfg.n_layers):
+        usage, tokens = eng.expert_usage(layer)
+        assert int(np.sum(usage)) == cfg.top_k * B * cfg.seq_len and tokens == B * cfg.seq_len
+        idx, _ = eng.token_routing(layer, B)
+        assert (idx[:, 0] != idx[:, 1]).all()  # without replacement
+        assert np.array_equal(np.bincount(idx.reshape(-1), minlength=cfg.num_experts), np.asarray(usage))
