@@ -241,14 +241,36 @@ class MoDeDiT(nn.Module):
         return [n for n, _ in self.named_parameters()]
 
     def check_trainable(self) -> None:
-        """The engine trains in the deterministic mode of SURVEY.md A.5: no dropout, top-k (not multinomial) routing.
-        Configurations that ask for stochastic regularisation still train, with a one-time warning."""
-        c = self._train_cfg
-        stochastic = [k for k in ("attn_pdrop", "mlp_pdrop", "goal_drop", "embed_pdrob") if c[k]] + \
-            ([] if c["use_argmax"] else ["multinomial routing (use_argmax=False)"])
-        if stochastic and not self._warned_deterministic:
-            logger.warning("MoDE engine trains deterministically; ignored: %s", ", ".join(stochastic))
+        """Everything the reference's train mode does is built (attention / expert dropout, goal masking, per-token
+        multinomial routing) except dropout on the embeddings (`embed_pdrob`, 0 in conf/model/mode_agent.yaml)."""
+        if self._train_cfg["embed_pdrob"] and not self._warned_deterministic:
+            logger.warning("MoDE engine: embed_pdrob=%s is not applied (the reference config uses 0)", self._train_cfg["embed_pdrob"])
             self._warned_deterministic = True
+
+    # ---- stochastic regularisation of the reference's train mode (modedit.py:149, :254, :389-390, :882-893)
+    def set_train_rng(self, seed: int, step: int = 0) -> None:
+        """Position of the engine's counter-based random stream: the masks and expert draws of training step n are a
+        pure function of (seed, step + n). Default seed: torch.initial_seed() mixed with the data-parallel rank."""
+        self._train_seed, self._train_step = int(seed), int(step)
+
+    def _train_rng(self):
+        if getattr(self, "_train_seed", None) is None:
+            rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+            self.set_train_rng((torch.initial_seed() * 1000003 + rank) & (2 ** 64 - 1), 0)
+        return self._train_seed, self._train_step
+
+    def _stochastic_args(self):
+        """Arguments of ModeEngine.set_stochastic for the next training step (all off when `deterministic_training`)."""
+        c = self._train_cfg
+        if getattr(self, "deterministic_training", False):
+            return dict(attn_pdrop=0.0, mlp_pdrop=0.0, goal_drop=0.0, multinomial=False, seed=0, step=0)
+        seed, step = self._train_rng()
+        return dict(attn_pdrop=c["attn_pdrop"], mlp_pdrop=c["mlp_pdrop"], goal_drop=c["goal_drop"],
+                    multinomial=not c["use_argmax"], seed=seed, step=step)
+
+    def _advance_train_rng(self):
+        if getattr(self, "_train_seed", None) is not None:
+            self._train_step += 1
 
     def set_sigma_data(self, sigma_data: float) -> None:
         if float(sigma_data) != self._engine_cfg.sigma_data:
@@ -328,13 +350,20 @@ class MoDeDiT(nn.Module):
         return outs
 
     def load_balancing_loss(self):
-        """Mean over layers of E * sum_e mean(router_probs_e) * mean(mask_e) (reference modedit.py:584-593, :898-928).
-        All T tokens of a sample share one routing row, so token means equal sample means."""
+        """Mean over layers of E * sum_e mean(router_probs_e) * mean(mask_e) over all tokens (reference modedit.py:584-593,
+        :898-928). With arg-max routing all T tokens of a sample share one routing row; under multinomial routing every
+        token has its own draws (the engine's token-level table of the last training step)."""
         total = 0.0
         aux = self._router_aux()
         B = aux[0][0].shape[0]
+        per_token = bool(getattr(self, "_last_step_multinomial", False))
         for layer, (_, probs) in enumerate(aux):
-            idx = torch.from_numpy(self._engine.routing(layer, B)[0]).long().to(probs.device)
+            if per_token:
+                T = self._engine.cfg.seq_len
+                idx = torch.from_numpy(self._engine.token_routing(layer, B)[0]).long().to(probs.device)
+                probs = probs.repeat_interleave(T, dim=0)  # cond is repeated to every token (reference :328-330)
+            else:
+                idx = torch.from_numpy(self._engine.routing(layer, B)[0]).long().to(probs.device)
             mask = torch.zeros_like(probs).scatter_(1, idx, 1.0)
             rp = probs * mask
             if self.blocks[layer].router.normalize:

@@ -43,7 +43,11 @@ class _EngineLoss(torch.autograd.Function):
         # A torch optimizer may have updated the masters since the last step without touching their version counters
         # (fused / foreach kernels do): re-pack unconditionally unless optim.EngineAdamW keeps the copies in sync itself.
         eng = inner._ensure_engine(action.shape[0], force_repack=not getattr(inner, "_engine_keeps_sync", False))
+        stoch = inner._stochastic_args()
+        eng.set_stochastic(**stoch)
+        inner._last_step_multinomial = stoch["multinomial"]
         loss, out = eng.train_step(state_images, action, goal, noise, sigma)
+        inner._advance_train_rng()
         ctx.eng, ctx.names, ctx.shapes = eng, inner._param_names, [tuple(p.shape) for p in params]
         ctx.inner = inner
         ctx.needs = [p.requires_grad for p in params]
@@ -105,8 +109,9 @@ class GCDenoiser(nn.Module):
 
     def loss(self, state, action, goal, noise, sigma, **kwargs):
         """EDM loss (reference score_wrappers.py:45-63). In eval mode: the forward value. In train mode: forward and
-        the hand-written backward in one engine call, wired into autograd (deterministic mode of SURVEY.md A.5 — the
-        engine applies neither dropout nor multinomial routing; see MoDeDiT.check_trainable)."""
+        the hand-written backward in one engine call, wired into autograd, with the reference's train-mode
+        regularisation (attention / expert dropout, goal masking, per-token multinomial routing) drawn from the
+        engine's counter-based stream (MoDeDiT.set_train_rng); `inner_model.deterministic_training = True` turns it off."""
         m = self.inner_model
         goal = m._goals(goal, False)
         m._last_sigma = sigma.detach()  # for the auxiliary router losses (MoDeDiT.load_balancing_loss / z-loss)

@@ -349,3 +349,76 @@ def test_stochastic_pieces_one_at_a_time():
         idx, _ = eng.token_routing(layer, B)
         assert (idx[:, 0] != idx[:, 1]).all()  # without replacement
         assert np.array_equal(np.bincount(idx.reshape(-1), minlength=cfg.num_experts), np.asarray(usage))
+
+
+def test_module_surface_trains_with_the_reference_default_regularisation():
+    """MoDeDiT/GCDenoiser constructed with the reference's conf values (attn_pdrop 0.3, mlp_pdrop 0.1, goal_drop 0.1,
+    use_argmax False) train through the stochastic engine path: fresh masks every step, reproducible from
+    set_train_rng, per-token load-balancing term, and the loss still goes down."""
+    from mode_diffusion_policy_b200.modedit import MoDeDiT
+    from mode_diffusion_policy_b200.score_wrappers import GCDenoiser
+
+    cfg, B = MODELS["model_tiny_d256_l3_e4"]
+    g = np.load(GOLD / "model_tiny_d256_l3_e4.npz")
+    gs = np.load(GOLD / "train_stoch_model_tiny_d256_l3_e4.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=float(gs["router_gain"]))
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cuda", goal_conditioned=True, action_dim=7,
+                    embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=0.3, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                    goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7, mlp_pdrop=0.1, goal_drop=0.1,
+                    num_experts=4, top_k=2, use_argmax=False, max_batch=8)
+    inner.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = GCDenoiser(inner, sigma_data=0.5).cuda().train()
+    st = {"state_images": cu(state)}
+    acts, noise, sig, goal_t = cu((x0 / np.float32(80.0)).astype(np.float32)), cu(g["loss_noise"]), cu(g["sigma_het"]), cu(goal)
+    inner.set_train_rng(int(gs["seed"]), int(gs["step"]))
+    loss0, _ = model.loss(st, acts, goal_t, noise, sig)
+    loss0.backward()
+    # the same (seed, step) as the reference-generated golden: same loss, same gradients
+    assert abs(float(loss0) - float(gs["loss"])) <= 3e-2 * abs(float(gs["loss"]))
+    params = dict(inner.named_parameters())
+    for pos, (name, shape) in enumerate(O.state_dict_spec(cfg)):
+        if name == "gripper_embed.weight" or float(gs[f"norm/{name}"]) == 0.0:
+            continue
+        got = params[name].grad.reshape(-1).cpu().numpy()
+        idx = sample_indices(got.size, pos)
+        want = gs[f"val/{name}"]
+        assert np.linalg.norm(got[idx] - want) <= 6e-2 * np.linalg.norm(want), name
+    # per-token load-balancing term (reference modedit.py:584-593) from the engine's token-level draws
+    lb = float(inner.load_balancing_loss())
+    T, E = cfg.seq_len, cfg.num_experts
+    want_lb = 0.0
+    for layer in range(cfg.n_layers):
+        idx, w = inner._engine.token_routing(layer, B)
+        mask = np.zeros((B * T, E), np.float64)
+        np.put_along_axis(mask, idx.astype(np.int64), 1.0, axis=1)
+        rp = np.zeros((B * T, E), np.float64)
+        np.put_along_axis(rp, idx.astype(np.int64), w.astype(np.float64), axis=1)
+        want_lb += E * float((rp.mean(0) * mask.mean(0)).sum())
+    assert abs(lb - want_lb / cfg.n_layers) < 1e-4 * abs(lb), (lb, want_lb / cfg.n_layers)
+    inner.zero_grad(set_to_none=True)
+    loss1, _ = model.loss(st, acts, goal_t, noise, sig)  # next step: fresh masks
+    assert float(loss1) != float(loss0)
+    inner.set_train_rng(int(gs["seed"]), int(gs["step"]))
+    loss0b, _ = model.loss(st, acts, goal_t, noise, sig)
+    assert float(loss0b) == float(loss0)
+    # eval mode and deterministic_training bypass the regularisation
+    model.eval()
+    with torch.no_grad():
+        le, _ = model.loss(st, acts, goal_t, noise, sig)
+    model.train()
+    inner.deterministic_training = True
+    ld, _ = model.loss(st, acts, goal_t, noise, sig)
+    assert abs(float(ld) - float(le)) <= 1e-5 * abs(float(le))
+    inner.deterministic_training = False
+    # optimisation under dropout + multinomial routing: the evaluation loss on the fixed batch goes down
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
+    for _ in range(8):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = model.loss(st, acts, goal_t, noise, sig)
+        loss.backward()
+        opt.step()
+    model.eval()
+    with torch.no_grad():
+        le2, _ = model.loss(st, acts, goal_t, noise, sig)
+    assert float(le2) < 0.9 * float(le), (float(le), float(le2))
