@@ -26,6 +26,9 @@ ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--layers", type=int, default=12)
+ap.add_argument("--stochastic", action="store_true",
+                help="the reference's default train-mode regularisation (conf/model/mode_agent.yaml: attn_pdrop 0.3, "
+                     "mlp_pdrop 0.1, goal_drop 0.1, use_argmax False = per-token multinomial routing)")
 a = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
@@ -34,8 +37,9 @@ if world > 1:
 cfg = O.ModeConfig(n_layers=a.layers)
 B = a.batch
 inner = MoDeDiT(obs_dim=2048, goal_dim=512, device="cuda", goal_conditioned=True, action_dim=7, embed_dim=1024, embed_pdrob=0,
-                attn_pdrop=0.0, n_layers=a.layers, n_heads=8, goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7,
-                mlp_pdrop=0.0, goal_drop=0.0, num_experts=4, top_k=2, use_argmax=True, max_batch=B)
+                attn_pdrop=0.3 if a.stochastic else 0.0, n_layers=a.layers, n_heads=8, goal_seq_len=1, obs_seq_len=1,
+                action_seq_len=10, state_dim=7, mlp_pdrop=0.1 if a.stochastic else 0.0, goal_drop=0.1 if a.stochastic else 0.0,
+                num_experts=4, top_k=2, use_argmax=not a.stochastic, max_batch=B)
 inner.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_weights_fast(cfg, seed=1234).items()})
 model = GCDenoiser(inner, sigma_data=0.5).cuda().train()
 if os.environ.get("MODE_TRAIN_FUSED_OPT", "1") == "1":  # one engine launch: AdamW over the flat gradient buffer + re-pack
@@ -92,7 +96,8 @@ if rank == 0:
                       "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                       "global_batch": world * B, "dtype": "bf16", "data": "synthetic", "loss": float(loss),
                       "approx_tflops": 3 * fwd_flops * a.steps / (ms * 1e-3) / 1e12,
-                      "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack", "optimizer": opt_name,
+                      "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack",
+                                 "regularisation": ("attn_pdrop 0.3, mlp_pdrop 0.1, goal_drop 0.1, per-token multinomial routing" if a.stochastic else "none (deterministic mode)"), "optimizer": opt_name,
                                  "grad_allreduce": ("per-layer NCCL all-reduce buckets of the flat fp32 gradient buffer, overlapped with backward" if ap_overlap else "one NCCL all-reduce over the flat fp32 gradient buffer")}}), flush=True)
 if world > 1:
     dist.destroy_process_group()
