@@ -517,8 +517,10 @@ struct AttnBwdParams {
   DropoutSpec drop = DropoutSpec{0u, 0u, 1.0f};  // the forward's attention-probability dropout (attention.cuh); thr == 0: none
 };
 constexpr int ATTN_BWD_MAX_T = 32;
-__host__ __device__ constexpr int attn_bwd_floats_per_warp(int T, int DH) {
-  return 6 * T * DH + 2 * T * ATTN_BWD_MAX_T + 2 * ATTN_BWD_MAX_T;
+// per-warp shared memory: q^, k^, v, dO as bf16 [T][DH] (all four ARE bf16 values: rounded operands / bf16 tensors),
+// P and dS fp32 [T][32], the two reciprocal-norm vectors. 18 KB at T=14, Dh=128 -> 12 warps per SM.
+__host__ __device__ constexpr int attn_bwd_bytes_per_warp(int T, int DH) {
+  return 4 * T * DH * 2 + (2 * T * ATTN_BWD_MAX_T + 2 * ATTN_BWD_MAX_T) * 4;
 }
 template <int DH>
 __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const AttnBwdParams p) {
@@ -531,16 +533,15 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const At
   if (item >= p.B * p.H) return;
   const int b = item / p.H, h = item % p.H;
   const int T = p.T, d = p.H * DH;
-  // per-warp shared memory: qn, kn (normalised, no gain), qh, kh (bf16-rounded with gain), v, dO : [T][DH] fp32;
-  // P, dS : [T][T] fp32; rq, rk : [T]
-  float* base = reinterpret_cast<float*>(attn_bwd_smem) + static_cast<size_t>(warp) * attn_bwd_floats_per_warp(T, DH);
-  float* qn = base;
-  float* kn = qn + T * DH;
-  float* qh = kn + T * DH;
-  float* kh = qh + T * DH;
-  float* vv = kh + T * DH;
-  float* dO = vv + T * DH;
-  float* P = dO + T * DH;
+  // per-warp shared memory: qh, kh (bf16-rounded normalised q, k with gain), v, dO : [T][DH] bf16;
+  // P, dS : [T][32] fp32; rq, rk : [T]. The gain-free normalised q, k of the RMSNorm backward are recomputed from the
+  // (L2-resident) qkv rows at the end instead of being kept.
+  uint8_t* wbase = attn_bwd_smem + static_cast<size_t>(warp) * attn_bwd_bytes_per_warp(T, DH);
+  __nv_bfloat16* qh = reinterpret_cast<__nv_bfloat16*>(wbase);
+  __nv_bfloat16* kh = qh + T * DH;
+  __nv_bfloat16* vv = kh + T * DH;
+  __nv_bfloat16* dO = vv + T * DH;
+  float* P = reinterpret_cast<float*>(dO + T * DH);
   float* dS = P + T * ATTN_BWD_MAX_T;
   float* rq = dS + T * ATTN_BWD_MAX_T;
   float* rk = rq + ATTN_BWD_MAX_T;
@@ -559,8 +560,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const At
       const int c = lane + 32 * u;
       q[u] = __bfloat162float(src[c]);
       k[u] = __bfloat162float(src[d + c]);
-      vv[t * DH + c] = __bfloat162float(src[2 * d + c]);
-      dO[t * DH + c] = __bfloat162float(p.dO[(static_cast<size_t>(b) * T + t) * d + h * DH + c]);
+      vv[t * DH + c] = src[2 * d + c];
+      dO[t * DH + c] = p.dO[(static_cast<size_t>(b) * T + t) * d + h * DH + c];
       sq += q[u] * q[u];
       sk += k[u] * k[u];
     }
@@ -574,10 +575,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const At
 #pragma unroll
     for (int u = 0; u < DPL; ++u) {
       const int c = lane + 32 * u;
-      qn[t * DH + c] = q[u] * r_q;
-      kn[t * DH + c] = k[u] * r_k;
-      qh[t * DH + c] = bf16_round(q[u] * r_q * gq[u]);
-      kh[t * DH + c] = bf16_round(k[u] * r_k * gk[u]);
+      qh[t * DH + c] = __float2bfloat16_rn(q[u] * r_q * gq[u]);
+      kh[t * DH + c] = __float2bfloat16_rn(k[u] * r_k * gk[u]);
     }
   }
   __syncwarp();
@@ -589,8 +588,8 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const At
 #pragma unroll
       for (int u = 0; u < DPL; ++u) {
         const int c = lane + 32 * u;
-        s = fmaf(qh[i * DH + c], kh[j * DH + c], s);
-        dp = fmaf(dO[i * DH + c], vv[j * DH + c], dp);
+        s = fmaf(__bfloat162float(qh[i * DH + c]), __bfloat162float(kh[j * DH + c]), s);
+        dp = fmaf(__bfloat162float(dO[i * DH + c]), __bfloat162float(vv[j * DH + c]), dp);
       }
       s = warp_sum(s) * p.inv_sqrt_dh;
       dp = warp_sum(dp);
@@ -632,35 +631,39 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_bwd_kernel(const At
     for (int j = 0; j <= t; ++j) {  // row t as a query: keys j <= t
       const float ds = dS[t * ATTN_BWD_MAX_T + j];
 #pragma unroll
-      for (int u = 0; u < DPL; ++u) dq[u] = fmaf(ds, kh[j * DH + lane + 32 * u], dq[u]);
+      for (int u = 0; u < DPL; ++u) dq[u] = fmaf(ds, __bfloat162float(kh[j * DH + lane + 32 * u]), dq[u]);
     }
     for (int i = t; i < T; ++i) {  // row t as a key/value: queries i >= t
       const float pp = P[i * ATTN_BWD_MAX_T + t], ds = dS[i * ATTN_BWD_MAX_T + t];
 #pragma unroll
       for (int u = 0; u < DPL; ++u) {
-        dv[u] = fmaf(pp, dO[i * DH + lane + 32 * u], dv[u]);
-        dk[u] = fmaf(ds, qh[i * DH + lane + 32 * u], dk[u]);
+        dv[u] = fmaf(pp, __bfloat162float(dO[i * DH + lane + 32 * u]), dv[u]);
+        dk[u] = fmaf(ds, __bfloat162float(qh[i * DH + lane + 32 * u]), dk[u]);
       }
     }
-    // per-head RMSNorm backward: q^ = qn * g, qn = q * r
+    // per-head RMSNorm backward: q^ = qn * g, qn = q * r (recomputed from the saved row)
+    const float r_q = fabsf(rq[t]), r_k = fabsf(rk[t]);
+    const __nv_bfloat16* srow = p.qkv + (static_cast<size_t>(b) * T + t) * 3 * d + h * DH;
+    float qn[DPL], kn[DPL];
     float dotq = 0.f, dotk = 0.f;
 #pragma unroll
     for (int u = 0; u < DPL; ++u) {
       const int c = lane + 32 * u;
-      dotq += gq[u] * dq[u] * qn[t * DH + c];
-      dotk += gk[u] * dk[u] * kn[t * DH + c];
-      gq_acc[u] += dq[u] * qn[t * DH + c];
-      gk_acc[u] += dk[u] * kn[t * DH + c];
+      qn[u] = __bfloat162float(srow[c]) * r_q;
+      kn[u] = __bfloat162float(srow[d + c]) * r_k;
+      dotq += gq[u] * dq[u] * qn[u];
+      dotk += gk[u] * dk[u] * kn[u];
+      gq_acc[u] += dq[u] * qn[u];
+      gk_acc[u] += dk[u] * kn[u];
     }
-    const float r_q = fabsf(rq[t]), r_k = fabsf(rk[t]);
     dotq = rq[t] < 0.f ? 0.f : warp_sum(dotq) / static_cast<float>(DH);
     dotk = rk[t] < 0.f ? 0.f : warp_sum(dotk) / static_cast<float>(DH);
     __nv_bfloat16* dst = p.dqkv + (static_cast<size_t>(b) * T + t) * 3 * d + h * DH;
 #pragma unroll
     for (int u = 0; u < DPL; ++u) {
       const int c = lane + 32 * u;
-      dst[c] = __float2bfloat16_rn(r_q * (gq[u] * dq[u] - qn[t * DH + c] * dotq));
-      dst[d + c] = __float2bfloat16_rn(r_k * (gk[u] * dk[u] - kn[t * DH + c] * dotk));
+      dst[c] = __float2bfloat16_rn(r_q * (gq[u] * dq[u] - qn[u] * dotq));
+      dst[d + c] = __float2bfloat16_rn(r_k * (gk[u] * dk[u] - kn[u] * dotk));
       dst[2 * d + c] = __float2bfloat16_rn(dv[u]);
     }
   }
@@ -745,7 +748,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) router_bwd_kernel(const Router
   }
 }
 
-// g_w2[e, j] = sum_b dlogit[b, e] hid[b, j];  g_b2[e] = sum_b dlogit[b, e];  g_b1[j] = sum_b dz[b, j]  (fixed order)
+// g_w2[e, j] = sum_b dlogit[b, e] hid[b, j];  g_b2[e] = sum_b dlogit[b, e];  g_b1[j] = sum_b dz[b, j]  (fixed order).
+// grid (Hd/256, E + 1): blockIdx.y < E handles expert y's row of W2 (and its bias), blockIdx.y == E the b1 sums, so the
+// E + 1 serial loops over the batch run side by side instead of one after the other in each thread.
 __global__ void __launch_bounds__(256) router_wgrad_small_kernel(const float* __restrict__ dlogit, const float* __restrict__ hid,
                                                                  const __nv_bfloat16* __restrict__ dz, float* __restrict__ g_w2,
                                                                  float* __restrict__ g_b2, float* __restrict__ g_b1, int B,
@@ -754,19 +759,23 @@ __global__ void __launch_bounds__(256) router_wgrad_small_kernel(const float* __
   pdl_wait();
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= Hd) return;
-  float b1 = 0.f;
-  for (int b = 0; b < B; ++b) b1 += __bfloat162float(dz[static_cast<size_t>(b) * Hd + j]);
-  g_b1[j] = b1;
-  for (int e = 0; e < E; ++e) {
-    float acc = 0.f, accb = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float g = dlogit[b * E + e];
-      acc = fmaf(g, hid[static_cast<size_t>(b) * Hd + j], acc);
-      accb += g;
-    }
-    g_w2[static_cast<size_t>(e) * Hd + j] = acc;
-    if (j == 0) g_b2[e] = accb;
+  const int e = blockIdx.y;
+  if (e == E) {
+    float b1 = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) b1 += __bfloat162float(dz[static_cast<size_t>(b) * Hd + j]);
+    g_b1[j] = b1;
+    return;
   }
+  float acc = 0.f, accb = 0.f;
+#pragma unroll 4
+  for (int b = 0; b < B; ++b) {
+    const float g = dlogit[b * E + e];
+    acc = fmaf(g, hid[static_cast<size_t>(b) * Hd + j], acc);
+    accb += g;
+  }
+  g_w2[static_cast<size_t>(e) * Hd + j] = acc;
+  if (j == 0) g_b2[e] = accb;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -915,6 +924,40 @@ __global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const SrcT* __re
   __syncthreads();
   for (int r = ty; r < 32; r += 8)
     if (bx + r < cols && by + tx < rows) dst[mat + static_cast<size_t>(bx + r) * rows + by + tx] = tile[tx][r];
+}
+
+// bf16 [rows, cols] -> bf16 [cols, rows] for rows, cols multiples of 64: 64 x 64 tiles, 16-byte global accesses on both
+// sides (a source row segment and a destination row segment are each 128 contiguous bytes = 8 lanes), staged through a
+// 33-word-stride shared tile (conflict-free 4-byte writes, <= 2-way conflicts on the transposed reads).
+__global__ void __launch_bounds__(256) transpose_bf16_64_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                int rows, int cols) {
+  __shared__ uint32_t tile[64][33];  // tile[r][w]: source row r, bf16 columns 2w and 2w+1
+  const int bx = blockIdx.x * 64, by = blockIdx.y * 64;
+  const size_t mat = static_cast<size_t>(blockIdx.z) * rows * cols;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int r = pass * 32 + (t >> 3), c8 = t & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + mat + static_cast<size_t>(by + r) * cols + bx + c8 * 8);
+    tile[r][c8 * 4 + 0] = v.x;
+    tile[r][c8 * 4 + 1] = v.y;
+    tile[r][c8 * 4 + 2] = v.z;
+    tile[r][c8 * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  const __nv_bfloat16* th = reinterpret_cast<const __nv_bfloat16*>(&tile[0][0]);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c = pass * 32 + (t >> 3), seg = t & 7;  // destination row bx + c, its source rows seg*8 .. seg*8+7
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint16_t lo = reinterpret_cast<const uint16_t*>(th)[(seg * 8 + 2 * k) * 66 + c];
+      const uint16_t hi = reinterpret_cast<const uint16_t*>(th)[(seg * 8 + 2 * k + 1) * 66 + c];
+      o[k] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+    }
+    *reinterpret_cast<uint4*>(dst + mat + static_cast<size_t>(bx + c) * rows + by + seg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 // Generic weight gradient out[n, k] = sum_r dy[r, n] * x[r, k] for shapes the tensor-core kernel does not tile
