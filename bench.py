@@ -233,10 +233,14 @@ def main():
         d, k = cfg.embed_dim, cfg.top_k
         M = B * cfg.seq_len
         up_ms, up_n = prof["up_gemm_swiglu"]
-        up_flops = 2.0 * (k * M) * (8 * d) * d  # per launch: k*M routed rows x 8d outputs x d
+        # per launch: k*M routed rows x 8d outputs x d; the last block only routes its action rows (dead-row
+        # elimination), so the AVERAGE launch does ((L-1) + A/T)/L of that
+        trim = os.environ.get("MODE_TRIM_LAST", "1") != "0"
+        launch_frac = ((cfg.n_layers - 1) + cfg.action_seq_len / cfg.seq_len) / cfg.n_layers if trim else 1.0
+        up_flops = 2.0 * (k * M) * (8 * d) * d * launch_frac
         achieved = up_flops / (up_ms / up_n * 1e-3) / 1e12
         flops = {"qkv_gemm": 6.0 * M * d * d, "proj_gemm": 2.0 * M * d * d, "up_gemm_swiglu": up_flops,
-                 "down_gemm": 2.0 * (k * M) * d * (4 * d)}
+                 "down_gemm": 2.0 * (k * M) * d * (4 * d) * launch_frac}
         # algorithmic HBM bytes per launch of the HBM-bound row kernels
         hbm_gbs = peaks.get("hbm_gbs", 6650.0)
         T_ = cfg.seq_len
@@ -266,7 +270,9 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "denoising_steps_per_bench_step": N_SAMPLING_STEPS,
                        "parallelism": f"dp{world} (independent trajectory shards, no collective)",
                        "l2": "no explicit flush: each denoising step streams 705 MB of bf16 weights (> 126 MB L2)",
-                       "weights": "random init, reference shapes (686 M params)"},
+                       "weights": "random init, reference shapes (686 M params)",
+                       "dead_rows": ("last block's experts run on the 10 action rows of each trajectory only (the other 4 "
+                                     "never reach the head); step_roofline counts the reference's full FLOPs") if trim else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(hs.numel() * 4 + hg.numel() * 4 + hx.numel() * 4),
                     "d2h_bytes_per_step": int(hx.numel() * 4)},

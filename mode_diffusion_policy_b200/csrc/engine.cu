@@ -199,6 +199,7 @@ struct mode_engine {
   bool mlp_fused;  // expert up+down projections as one dynamically scheduled launch (MODE_MLP_FUSED=1, default off; needs pair)
   int* mlp_sync;   // its tile queue head + per-M-tile dependency counters
   int tile_m;  // rows per M-tile: 256 with CTA pairs, 128 otherwise
+  int trim_rows = 0;  // inference: the last block's experts only run on the action rows (MODE_TRIM_LAST=0 disables)
   bool finalized = false;
   std::map<std::string, WeightSpec> specs;
   std::vector<void*> allocs;
@@ -520,6 +521,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
     const char* env = getenv("MODE_GEMM_CTA_PAIR");
     e->pair = env ? atoi(env) != 0 : true;
     e->tile_m = e->pair ? 256 : 128;
+    const char* trim_env = getenv("MODE_TRIM_LAST");
+    e->trim_rows = (trim_env && atoi(trim_env) == 0) ? 0 : e->A;
     env = getenv("MODE_MLP_FUSED");
     e->mlp_fused = e->pair && (env ? atoi(env) != 0 : false);  // measured +1.5 % only: opt-in
   }
@@ -878,7 +881,7 @@ static DropoutSpec dropout_spec(const mode_engine* e, float p, uint32_t stream, 
 // launch), tables [slot][L][B][..].
 static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* z_explicit,
                            int layer0, int n_layers, int slot0 = ROUTE_SLOT_EVAL, int n_slots = 1,
-                           int sigma_slot_stride = 0) {
+                           int sigma_slot_stride = 0, int trim_rows = 0) {
   ProfScope ps(e, st, PC_ROUTE);
   RouterParams r;
   r.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
@@ -902,6 +905,7 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   pl.L = e->L; pl.B = B; pl.K = e->K; pl.E = e->E; pl.T = e->T; pl.max_tiles = e->max_tiles;
   pl.up_rows_per_expert = 8 * e->d; pl.down_rows_per_expert = e->d; pl.layer0 = layer0; pl.tile_m = e->tile_m; pl.slot0 = slot0; pl.n_layers = n_layers;
   pl.route_lt_sub = 0;
+  pl.trim_rows = tok ? 0 : trim_rows;
   if (tok) {  // token-level tables have no slot dimension; the tile tables stay in the evaluation slot
     pl.sel_idx = e->tok_sel_idx; pl.pos = e->tok_pos; pl.B = B * e->T; pl.T = 1; pl.route_lt_sub = slot0 * e->L;
   }
@@ -913,7 +917,8 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
 }
 
 // One NoiseBlockMoE (modedit.py:530-595) given hA = bf16(ln_1(x)+c) and routing tables for layer l.
-static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode, int slot, const LayerIO& io) {
+static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int combine_mode, int slot, const LayerIO& io,
+                         int trim_rows = 0) {
   const int d = e->d, M = B * e->T;
   const size_t lt = (size_t)slot * e->L + l;  // layer index inside the routing tables
   // measurement aid (scripts/skip_diag.py): bit PC_x set = do not launch that kernel class; outputs are then garbage
@@ -946,6 +951,8 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   n2.x = io.x1; n2.x_out = io.xn; n2.g = e->ln2_g + (size_t)l * d; n2.pos = rv.pos; n2.perm = io.perm;
   int* row_token = mlp_drop.thr ? e->row_token + (size_t)l * e->perm_rows : nullptr;  // [L][perm_rows], training only
   n2.row_token = row_token;
+  const int t_skip = (trim_rows > 0 && !rv.per_token) ? e->T - trim_rows : 0;  // must match the plan of this layer
+  n2.t_skip = t_skip;
   n2.B = rv.units; n2.T = rv.rt; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
   const bool fused_mlp = e->mlp_fused && !io.z;  // the training forward keeps the two-launch path (it saves z)
   n2.zero = fused_mlp ? e->mlp_sync : nullptr;
@@ -994,6 +1001,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   c.pos = rv.pos; c.w = rv.sel_w;
   c.g_next = (combine_mode == 0) ? e->ln1_g + (size_t)(l + 1) * d : e->lnf_g;
   c.cvec = e->cvec; c.hA = io.hA_next; c.xnorm = e->xnorm;
+  c.t_skip = t_skip;
   c.B = rv.units; c.T = rv.rt; c.Tc = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_COMBINE);
@@ -1013,7 +1021,10 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   // layer_io: per-layer buffer sets (training); nullptr = the shared in-place inference set
   const LayerIO& io0 = layer_io ? layer_io[0] : e->io;
   const int slot = prerouted_slot >= 0 ? prerouted_slot : ROUTE_SLOT_EVAL;
-  if (prerouted_slot < 0) RET_IF(enqueue_routing(e, st, B, sigma, stride, nullptr, 0, e->L));
+  // the last block's dead rows are only dropped on the inference path (training keeps every row: its saved activations
+  // and tile tables are shared with the backward pass); pre-routed schedules were planned with the same setting
+  const int trim = layer_io ? 0 : e->trim_rows;
+  if (prerouted_slot < 0) RET_IF(enqueue_routing(e, st, B, sigma, stride, nullptr, 0, e->L, ROUTE_SLOT_EVAL, 1, 0, trim));
   EmbedParams em;
   em.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   em.sig_u = e->sig_u; em.sig_v = e->sig_v; em.goal_tok = e->goal_tok; em.state_tok = e->state_tok; em.pos = e->pos;
@@ -1026,7 +1037,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   }
   CU_OK(cudaGetLastError());
   for (int l = 0; l < e->L; ++l)
-    RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1, slot, layer_io ? layer_io[l] : e->io));
+    RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1, slot, layer_io ? layer_io[l] : e->io, l + 1 < e->L ? 0 : trim));
   if (head_mode < 0) {  // training forward: the loss/head backward kernel consumes the final-ln output directly
     e->launch_count += 1;
     return MODE_OK;
@@ -1183,7 +1194,7 @@ extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const 
   const size_t xbytes = (size_t)B * e->A * e->adim * sizeof(float);
   CU_OK(cudaMemcpyAsync(e->x_work, x_inout_dev, xbytes, cudaMemcpyDeviceToDevice, st));
   // route the whole sigma schedule (n steps x L layers) in one router + one plan launch, ahead of the captured loop
-  RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, nullptr, 0, e->L, 0, n, 1));
+  RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, nullptr, 0, e->L, 0, n, 1, e->trim_rows));
   RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
   CU_OK(cudaGraphLaunch(exec, st));
   CU_OK(cudaMemcpyAsync(x_inout_dev, e->x_work, xbytes, cudaMemcpyDeviceToDevice, st));

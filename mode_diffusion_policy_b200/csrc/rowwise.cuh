@@ -446,6 +446,7 @@ struct PlanParams {
   int layer0;                    // first layer handled by blockIdx.x == 0 (block-level entry plans a single layer)
   int tile_m;                    // rows per GEMM M-tile (128 single-CTA, 256 CTA-pair): groups are padded to it
   int slot0, n_layers;           // grid = n_slots * n_layers CTAs: slot = slot0 + blockIdx.x / n_layers
+  int trim_rows = 0;             // > 0: the LAST layer only routes the final trim_rows token rows of every unit (see below)
   int route_lt_sub = 0;              // subtracted from the table-layer index for sel_idx / pos (token-level tables: no slots)
 };
 
@@ -459,6 +460,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
   __shared__ int cnt[MAX_EXPERTS];
   __shared__ int grp_row0[MAX_EXPERTS];
   __shared__ int grp_tile0[MAX_EXPERTS + 1];
+  // Dead-row elimination: only the last action_seq_len tokens of the last block reach the output head
+  // (modedit.py:806-808) and nothing downstream attends to the others, so the last block's experts run on those rows
+  // only. The usage counters keep counting every routed token like the reference does.
+  const int Tl = (p.trim_rows > 0 && l == p.L - 1) ? p.trim_rows : p.T;
   const int* sel = p.sel_idx + static_cast<size_t>(lt - p.route_lt_sub) * p.B * p.K;
   int* pos = p.pos + static_cast<size_t>(lt - p.route_lt_sub) * p.B * p.K;
   // pass 1: rank of every (sample, slot) inside its expert group; stored temporarily in pos
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
     for (int e = 0; e < p.E; ++e) {
       grp_row0[e] = row;
       grp_tile0[e] = tile;
-      const int nt = (cnt[e] * p.T + p.tile_m - 1) / p.tile_m;
+      const int nt = (cnt[e] * Tl + p.tile_m - 1) / p.tile_m;
       row += nt * p.tile_m;
       tile += nt;
     }
@@ -502,7 +507,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
   __syncthreads();
   if (tid < p.E) atomicAdd(p.usage + static_cast<size_t>(l) * p.E + tid, static_cast<unsigned long long>(cnt[tid]) * p.T);
   // pass 2: ranks -> row positions
-  for (int i = tid; i < p.B * p.K; i += 256) pos[i] = grp_row0[sel[i]] + pos[i] * p.T;
+  for (int i = tid; i < p.B * p.K; i += 256) pos[i] = grp_row0[sel[i]] + pos[i] * Tl;
   if (p.wg_up && tid < p.E) {
     const int nt = grp_tile0[tid + 1] - grp_tile0[tid];
     p.wg_up[static_cast<size_t>(lt) * p.E + tid] = WgradProblem{grp_row0[tid], nt * p.tile_m / 64, (l * p.E + tid) * p.up_rows_per_expert, 0};
@@ -511,7 +516,7 @@ __global__ void __launch_bounds__(256) plan_kernel(const PlanParams p) {
   // pass 3: tile tables
   for (int e = 0; e < p.E; ++e) {
     const int nt = grp_tile0[e + 1] - grp_tile0[e];
-    const int rows = cnt[e] * p.T;
+    const int rows = cnt[e] * Tl;
     for (int i = tid; i < nt; i += 256) {
       GemmMTile t;
       t.a_row0 = grp_row0[e] + i * p.tile_m;
@@ -542,6 +547,7 @@ struct Ln2Params {
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
   int* zero;         // tile queue + dependency counters of the fused expert-MLP kernel that follows (or null)
   int n_zero;
+  int t_skip = 0;    // rows t < t_skip of every unit are dead (last block, see plan_kernel): neither normalised nor routed
   int* row_token = nullptr;  // optional [rows_perm]: token row of every permuted row (MLP dropout of the training path)
 };
 // (B, T) of the routed kernels are ROUTING units x rows per unit: (samples, tokens per sample) when all tokens of a
@@ -555,7 +561,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
-  const int b = row / p.T, t = row % p.T;
+  const int b = row / p.T, t = row % p.T - p.t_skip;
+  if (t < 0) return;
   float4 xv[NVEC];
   float ss = 0.f;
 #pragma unroll
@@ -608,6 +615,7 @@ struct CombineParams {
   float* xnorm;                // [B*T, d] (mode 1: final ln output, fp32)
   int B, T, K, d;
   int mode;                    // 0: next block's ln_1 + c -> hA ; 1: final ln -> xnorm ; 2: none (block-level entry)
+  int t_skip = 0;              // rows t < t_skip of every unit are dead (last block): skipped
   int Tc;                      // token rows per cvec row (tokens per sample; differs from T under per-token routing)
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
@@ -619,7 +627,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const Combin
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
-  const int b = row / p.T, t = row % p.T;
+  const int b = row / p.T, t = row % p.T - p.t_skip;
+  if (t < 0) return;
   int src_row[MAX_TOPK];
   float wk[MAX_TOPK];
 #pragma unroll

@@ -256,3 +256,30 @@ def test_fused_expert_mlp_kernel_is_bit_identical(tag, monkeypatch):
         outs.append((den.clone(), smp.clone()))
         del eng
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("tag", list(MODELS))
+def test_last_block_dead_row_elimination_is_bit_identical(tag, monkeypatch):
+    """Only the action tokens of the last block reach the output head (reference modedit.py:806-808), so the engine runs
+    the last block's experts on those rows only. Outputs are bit-identical to evaluating every row (MODE_TRIM_LAST=0),
+    for uniform-sigma sampling, per-sample-sigma denoising (ragged expert groups) and the loss; the expert-usage counters
+    keep counting every token like the reference."""
+    cfg, B = MODELS[tag]
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    g = np.load(GOLD / f"{tag}.npz")
+    sigmas = O.get_sigmas_exponential(10, 1e-3, 80.0)
+    outs = []
+    for trim in ("1", "0"):
+        monkeypatch.setenv("MODE_TRIM_LAST", trim)
+        eng = engine_for(cfg, sd, 8)
+        eng.reset_expert_usage()
+        smp = eng.sample_ddim(cu(state), cu(x0), cu(goal), sigmas)
+        den = eng.denoise(cu(state), cu(g["denoise_x"]), cu(goal), cu(g["sigma_het"]))
+        usage = [eng.expert_usage(l) for l in range(cfg.n_layers)]
+        loss, F = eng.loss(cu(state), cu((x0 / np.float32(80.0)).astype(np.float32)), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
+        outs.append((smp, den, float(loss), F, usage))
+    (s1, d1, l1, f1, u1), (s0, d0, l0, f0, u0) = outs
+    assert torch.equal(s1, s0) and torch.equal(d1, d0) and torch.equal(f1, f0) and l1 == l0
+    for (a, ta), (b, tb) in zip(u1, u0):
+        assert np.array_equal(a, b) and ta == tb
