@@ -897,7 +897,10 @@ static int enqueue_routing(mode_engine* e, cudaStream_t st, int B, const float* 
   r.multinomial = tok ? 1 : 0; r.T = e->T; r.seed = e->stoch.seed; r.step = e->stoch.step;
   r.tok_topk_idx = e->tok_topk_idx; r.tok_topk_w = e->tok_topk_w; r.tok_sel_idx = e->tok_sel_idx; r.tok_sel_w = e->tok_sel_w;
   const int distinct_rows = (stride == 0 && !z_explicit) ? 1 : B;
-  CU_OK(launch_k(router_kernel, dim3(n_slots * n_layers * distinct_rows), dim3(ROW_WARPS * 32), 0, st, r));
+  if (distinct_rows > 1)  // many rows: a warp per row, 8 rows of a layer per CTA
+    CU_OK(launch_k(router_kernel<true>, dim3(n_slots * n_layers * ((distinct_rows + ROW_WARPS - 1) / ROW_WARPS)), dim3(ROW_WARPS * 32), 0, st, r));
+  else  // one row per (slot, layer): a CTA per row
+    CU_OK(launch_k(router_kernel<false>, dim3(n_slots * n_layers), dim3(ROW_WARPS * 32), 0, st, r));
   PlanParams pl;
   pl.sel_idx = e->sel_idx; pl.pos = e->pos_tab; pl.up_tiles = e->up_tiles; pl.down_tiles = e->down_tiles;
   pl.downT_tiles = e->downT_tiles; pl.wg_up = e->wg_up; pl.wg_down = e->wg_down;

@@ -164,8 +164,14 @@ def test_full_size_properties_b256():
     assert torch.equal(full, half)
     one = torch.full((1,), 0.5, device="cuda")
     d_uniform = eng.denoise(S, X / 80.0, G, one)
+    idx_u, w_u, _ = eng.routing(3, B)
+    # same experts for every sample; the two calls use different router work layouts (one row per layer vs one row per
+    # sample), whose logits agree to fp32 rounding -> the renormalised expert weights differ by an ulp at most
     d_per = eng.denoise(S, X / 80.0, G, one.expand(B).contiguous())
-    assert torch.equal(d_uniform, d_per)
+    idx_p, w_p, _ = eng.routing(3, B)
+    assert torch.equal(d_per, eng.denoise(S, X / 80.0, G, one.expand(B).contiguous()))
+    assert np.array_equal(idx_u, idx_p) and np.abs(w_u - w_p).max() < 1e-6
+    assert rel_l2(d_uniform.cpu().numpy(), d_per.cpu().numpy()) < 2e-3
     assert eng.last_launch_count() > 0
     # A slice of the full-depth model against the oracle. With bf16 rounding between every pair of GEMMs, two
     # evaluations that differ only in fp32 accumulation order decorrelate with depth (a 1e-6 difference flips a bf16
