@@ -135,6 +135,13 @@ int mode_optimizer_bind(mode_engine_t* e, const char* name, float* param_dev, in
 int mode_optimizer_unbind_all(mode_engine_t* e);
 int mode_adamw_step(mode_engine_t* e, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     const float* grad_scale_dev, void* stream);
+/* The same update issued in n_layers + 1 launches so that a data-parallel caller can pipeline it with the gradient
+ * exchange: group l (0..n_layers-1) = block l's large tensors (>= 2^20 elements: q/k/v/c_proj, expert up/down, router
+ * W1 — exactly the per-layer buckets of parallel.GradAllReduce), group n_layers = every remaining tensor. Each group
+ * may go to its own stream as soon as its gradients are final; group n_layers must come last (it refreshes the derived
+ * weights). Launching all groups once equals one mode_adamw_step, bit for bit. */
+int mode_adamw_step_group(mode_engine_t* e, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                          const float* grad_scale_dev, int group, void* stream);
 int mode_optimizer_state(mode_engine_t* e, float** exp_avg_dev, float** exp_avg_sq_dev, int64_t* numel);
 /* Makes `stream` wait (cudaStreamWaitEvent, no host sync) until the most recent mode_train_step has finished writing the
  * gradients of block `layer` (its backward runs last-to-first), or all gradients when layer == -1. This is what lets a

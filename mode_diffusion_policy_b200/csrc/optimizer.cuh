@@ -32,6 +32,7 @@ struct AdamWParams {
   float *m, *v;
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
   const float* grad_scale;  // device scalar multiplied into every gradient (the loss's incoming gradient), or null
+  unsigned block_base;      // OptTensor::block0 of the first tensor of this launch (group launches start mid-table)
 };
 
 __device__ __forceinline__ int opt_dst_row(int r, int swiglu_half) {
@@ -54,14 +55,14 @@ __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
   int lo = 0, hi = a.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (a.tab[mid].block0 <= blockIdx.x)
+    if (a.tab[mid].block0 <= blockIdx.x + a.block_base)
       lo = mid;
     else
       hi = mid - 1;
   }
   const OptTensor t = a.tab[lo];
   const size_t numel = static_cast<size_t>(t.rows) * t.cols;
-  const size_t base = static_cast<size_t>(blockIdx.x - t.block0) * OPT_BLOCK_ELEMS;
+  const size_t base = static_cast<size_t>(blockIdx.x + a.block_base - t.block0) * OPT_BLOCK_ELEMS;
   const float gs = a.grad_scale ? *a.grad_scale : 1.0f;
   const float decay_mul = t.decay ? 1.0f - a.lr * a.wd : 1.0f;
   if (!t.transpose && (t.cols & 3) == 0 && (t.g_off & 3) == 0 && (reinterpret_cast<uintptr_t>(t.p) & 15) == 0) {

@@ -225,13 +225,23 @@ class ModeEngine:
     def optimizer_unbind_all(self) -> None:
         _lib.check(self.lib.mode_optimizer_unbind_all(self._h))
 
-    def adamw_step(self, lr, beta1, beta2, eps, weight_decay, step: int, grad_scale: Optional[torch.Tensor] = None) -> None:
-        """AdamW over every bound parameter + re-pack of the engine's weight copies, one launch (csrc/optimizer.cuh)."""
+    def adamw_step(self, lr, beta1, beta2, eps, weight_decay, step: int, grad_scale: Optional[torch.Tensor] = None,
+                   group: Optional[int] = None, stream: Optional["torch.cuda.Stream"] = None) -> None:
+        """AdamW over every bound parameter + re-pack of the engine's weight copies, one launch (csrc/optimizer.cuh).
+        `group` = l launches only block l's large tensors, `group` = n_layers the remaining ones (last): the pieces a
+        data-parallel step pipelines with its gradient exchange (`optim.EngineAdamW.step_overlapped`)."""
         gs = None
         if grad_scale is not None:
             gs = grad_scale.detach().to(device=self.device, dtype=torch.float32).reshape(1).contiguous()
-        _lib.check(self.lib.mode_adamw_step(self._h, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
-                                            int(step), C.c_void_p(gs.data_ptr()) if gs is not None else None, self._stream()))
+            self._gs_keepalive = gs  # the launch may run on a side stream after this call returns
+        gs_ptr = C.c_void_p(gs.data_ptr()) if gs is not None else None
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
+        if group is None:
+            _lib.check(self.lib.mode_adamw_step(self._h, float(lr), float(beta1), float(beta2), float(eps),
+                                                float(weight_decay), int(step), gs_ptr, st))
+        else:
+            _lib.check(self.lib.mode_adamw_step_group(self._h, float(lr), float(beta1), float(beta2), float(eps),
+                                                      float(weight_decay), int(step), gs_ptr, int(group), st))
 
     def optimizer_state(self):
         """Zero-copy views (exp_avg, exp_avg_sq) of the engine-owned moment buffers (gradient-buffer layout)."""

@@ -66,6 +66,74 @@ class EngineAdamW(torch.optim.Optimizer):
                        self.inner._loss_grad_scale)
         return loss
 
+    @torch.no_grad()
+    def step_overlapped(self, reducer, timeline=None, loss_scale=None) -> None:
+        """Data-parallel step with the gradient exchange and the optimizer pipelined layer by layer.
+
+        `reducer` is a `parallel.GradAllReduce` over the same engine. Block l's large gradient buckets are all-reduced on
+        the reducer's stream as soon as its backward is done (last block first); the optimizer launch for that block
+        (`mode_adamw_step_group`) follows on a second stream behind an event, so it runs while the next blocks' buckets
+        are still on the wire: the HBM-bound update hides behind the NVLink-bound exchange instead of waiting for all of
+        it. The small tensors and non-block parameters go last (tail buckets, group n_layers). Call after
+        `loss.backward()`; the caller's stream continues only when every group has finished. `timeline`: optional list
+        that receives (label, cuda event) pairs recorded on the streams involved (measurement aid).
+
+        `loss_scale`: None = use the gradient autograd fed into the loss (`loss.backward()` must have run; the optimizer
+        stream then waits for everything the caller's stream has enqueued, i.e. the whole backward). A float = the loss
+        was (or would have been) scaled by this constant: no `loss.backward()` is needed and block l's update may start
+        as soon as its gradients are exchanged, while the backward of blocks l-1..0 is still running — the small
+        HBM-bound optimizer CTAs co-reside with the persistent tensor-core GEMM CTAs."""
+        eng = getattr(self.inner, "_engine", None)
+        if eng is None:
+            raise RuntimeError("EngineAdamW.step_overlapped before any GCDenoiser.loss call")
+        self._bind(eng)
+        g = self.param_groups[0]
+        self._step += 1
+        dev = eng.device
+        if loss_scale is None:
+            scale = self.inner._loss_grad_scale
+        elif float(loss_scale) == 1.0:
+            scale = None
+        else:
+            if getattr(self, "_const_scale", None) is None or float(self._const_scale[0]) != float(loss_scale):
+                self._const_scale = (float(loss_scale), torch.full((1,), float(loss_scale), dtype=torch.float32, device=dev))
+                torch.cuda.current_stream(dev).synchronize()
+            scale = self._const_scale[1]
+        args = (g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._step, scale)
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_opt_stream", None) is None:
+            self._opt_stream = torch.cuda.Stream(device=dev)
+        opt_stream = self._opt_stream
+        def mark(label, stream):
+            if timeline is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                timeline.append((label, ev))
+
+        mark("backward_done", main)
+        if loss_scale is None:
+            opt_stream.wait_stream(main)  # the autograd-provided scale is produced on the caller's stream, after the backward
+        L = reducer.n_layers
+        exchange = reducer.active()
+        for layer in range(L - 1, -1, -1):
+            if exchange:
+                reducer.reduce_layer(layer)
+                mark(f"exchange_{layer}", reducer.stream)
+                opt_stream.wait_stream(reducer.stream)  # everything enqueued so far on the exchange stream, incl. this block
+            else:
+                eng.wait_grads(layer, opt_stream)
+            eng.adamw_step(*args, group=layer, stream=opt_stream)
+            mark(f"adamw_{layer}", opt_stream)
+        if exchange:
+            reducer.reduce_tail()
+            mark("exchange_tail", reducer.stream)
+            opt_stream.wait_stream(reducer.stream)
+        else:
+            eng.wait_grads(-1, opt_stream)
+        eng.adamw_step(*args, group=L, stream=opt_stream)
+        mark("adamw_rest", opt_stream)
+        main.wait_stream(opt_stream)
+
     def state_dict(self):
         sd = {"step": self._step, "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
         eng = getattr(self.inner, "_engine", None)

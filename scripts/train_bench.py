@@ -33,7 +33,11 @@ a = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
 if world > 1:
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # NCCL's kernels need 512+ threads on one SM at once; next to a small-CTA kernel with a deep queue (the optimizer)
+    # such a hole never opens unless NCCL's stream has priority over it
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = os.environ.get("MODE_NCCL_HIGH_PRIORITY", "1") == "1"
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 cfg = O.ModeConfig(n_layers=a.layers)
 B = a.batch
 inner = MoDeDiT(obs_dim=2048, goal_dim=512, device="cuda", goal_conditioned=True, action_dim=7, embed_dim=1024, embed_pdrob=0,
@@ -59,10 +63,27 @@ ap_overlap = os.environ.get("MODE_TRAIN_OVERLAP", "1") == "1"
 reducer = None
 
 
+TIMELINE = [] if os.environ.get("MODE_TRAIN_TIMELINE") == "1" else None  # per-stream event marks of the last step
+# MODE_TRAIN_PIPELINE: 1 = exchange + optimizer pipelined per layer behind the backward (default for N > 1);
+# 2 = additionally let block l's update start while blocks l-1..0 are still in backward (also valid on one GPU)
+pipe_mode = int(os.environ.get("MODE_TRAIN_PIPELINE", "1" if world > 1 else "0"))
+pipelined = pipe_mode > 0 and hasattr(opt, "step_overlapped")
+
+
 def step():
     global reducer
     opt.zero_grad(set_to_none=True)
     loss, _ = model.loss({"state_images": S}, A_, G, noise, sigma)
+    if pipelined:  # exchange and optimizer pipelined per layer (optim.EngineAdamW.step_overlapped)
+        if reducer is None:
+            reducer = parallel.GradAllReduce(inner._engine, [n for n, _ in inner.named_parameters()
+                                                             if n != "gripper_embed.weight"], a.layers)
+        if pipe_mode >= 2:  # unscaled loss: no autograd round trip, updates start while earlier blocks are in backward
+            opt.step_overlapped(reducer, timeline=TIMELINE, loss_scale=1.0)
+        else:
+            loss.backward()
+            opt.step_overlapped(reducer, timeline=TIMELINE)
+        return loss
     if world > 1:  # average the engine's flat gradient buffer before autograd hands out the views
         if ap_overlap:  # per-layer buckets on a side stream, overlapped with the rest of the backward
             if reducer is None:
@@ -84,12 +105,19 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps):
+    if TIMELINE is not None:
+        TIMELINE.clear()
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_start.record()
     loss = step()
 e1.record()
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 (ms,) = parallel.max_over_ranks([e0.elapsed_time(e1)], "cuda")
+if TIMELINE and rank == 0:
+    print("timeline of the last step (ms after its start): " +
+          ", ".join(f"{lab} {t_start.elapsed_time(ev):.2f}" for lab, ev in TIMELINE), file=sys.stderr, flush=True)
 if rank == 0:
     fwd_flops = 2.526888e12 * B / 256 * a.layers / 12
     print(json.dumps({"metric": "training-samples/sec", "value": world * B * a.steps / (ms * 1e-3), "unit": "samples/s",
@@ -98,6 +126,6 @@ if rank == 0:
                       "approx_tflops": 3 * fwd_flops * a.steps / (ms * 1e-3) / 1e12,
                       "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack",
                                  "regularisation": ("attn_pdrop 0.3, mlp_pdrop 0.1, goal_drop 0.1, per-token multinomial routing" if a.stochastic else "none (deterministic mode)"), "optimizer": opt_name,
-                                 "grad_allreduce": ("per-layer NCCL all-reduce buckets of the flat fp32 gradient buffer, overlapped with backward" if ap_overlap else "one NCCL all-reduce over the flat fp32 gradient buffer")}}), flush=True)
+                                 "grad_allreduce": ("per-layer NCCL all-reduce buckets pipelined with per-layer fused AdamW launches (step_overlapped)" if pipelined else "per-layer NCCL all-reduce buckets of the flat fp32 gradient buffer, overlapped with backward" if ap_overlap else "one NCCL all-reduce over the flat fp32 gradient buffer")}}), flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -422,3 +422,47 @@ def test_module_surface_trains_with_the_reference_default_regularisation():
     with torch.no_grad():
         le2, _ = model.loss(st, acts, goal_t, noise, sig)
     assert float(le2) < 0.9 * float(le), (float(le), float(le2))
+
+
+def test_grouped_optimizer_launches_equal_the_single_launch():
+    """EngineAdamW.step_overlapped issues the update as n_layers + 1 launches (block l's large tensors as soon as their
+    gradients are final, the rest last) on side streams; with a single rank there is nothing to exchange and the result
+    must equal `step()` bit for bit — masters, packed copies (same loss on the next step) and moments. d=1024 so that
+    the per-block groups are not empty (tensors >= 2^20 elements)."""
+    from mode_diffusion_policy_b200 import parallel
+    from mode_diffusion_policy_b200.optim import EngineAdamW
+
+    cfg = O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=1024, n_layers=2, n_heads=8, n_state_tokens=2,
+                       action_seq_len=10, num_experts=2, top_k=2)
+    B = 6
+    sd = O.make_weights_fast(cfg, seed=1234)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    rng = np.random.default_rng(5)
+    st = {"state_images": cu(state)}
+    acts, goal_t = cu((x0 / np.float32(80.0)).astype(np.float32)), cu(goal)
+    noise = cu(rng.standard_normal(x0.shape).astype(np.float32))
+    sig = cu(np.exp(rng.uniform(np.log(1e-3), np.log(80.0), B)).astype(np.float32))
+    hp = dict(lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    inner_a, model_a = _tiny_denoiser(sd, cfg)
+    inner_b, model_b = _tiny_denoiser(sd, cfg)
+    opt_a, opt_b = EngineAdamW(inner_a, **hp), EngineAdamW(inner_b, **hp)
+    reducer = None
+    for _ in range(3):
+        la, _ = model_a.loss(st, acts, goal_t, noise, sig)
+        la.backward()
+        opt_a.step()
+        lb, _ = model_b.loss(st, acts, goal_t, noise, sig)
+        lb.backward()
+        if reducer is None:
+            names = [n for n, _ in inner_b.named_parameters() if n != "gripper_embed.weight"]
+            reducer = parallel.GradAllReduce(inner_b._engine, names, cfg.n_layers)
+            assert all(len(b) > 0 for b in reducer.layer_buckets) and not reducer.active()
+        opt_b.step_overlapped(reducer)
+        assert float(la) == float(lb)
+    torch.cuda.synchronize()
+    pa, pb = dict(inner_a.named_parameters()), dict(inner_b.named_parameters())
+    for n in pa:
+        assert torch.equal(pa[n].detach(), pb[n].detach()), n
+    ma, va = inner_a._engine.optimizer_state()
+    mb, vb = inner_b._engine.optimizer_state()
+    assert torch.equal(ma, mb) and torch.equal(va, vb)
