@@ -143,6 +143,18 @@ int mode_adamw_step(mode_engine_t* e, float lr, float beta1, float beta2, float 
 int mode_adamw_step_group(mode_engine_t* e, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                           const float* grad_scale_dev, int group, void* stream);
 int mode_optimizer_state(mode_engine_t* e, float** exp_avg_dev, float** exp_avg_sq_dev, int64_t* numel);
+/* Exponential moving average of the bound parameters inside the optimizer launch (reference mode/callbacks/ema.py:
+ * ema -= (1 - decay) * (ema - w) after every step, :119-126; +8 bytes per parameter instead of a separate pass over
+ * all weights). decay in [0, 1] enables it for the following steps (may change every step: ema.py:84-92 warm-up
+ * schedule), negative disables. The first enabled step seeds the average with the weights before the update (the
+ * callback clones them at on_train_start, ema.py:96). mode_optimizer_ema_state exposes the engine-owned buffer
+ * (gradient-buffer layout: mode_grad_offset gives each parameter's span). */
+int mode_optimizer_set_ema(mode_engine_t* e, double decay);
+int mode_optimizer_ema_state(mode_engine_t* e, float** ema_dev, int64_t* numel);
+/* Sums of squares of n spans (offset, numel; host array) of the flat gradient buffer -> out_dev[n], two launches,
+ * deterministic. Replaces the per-parameter `.grad.norm().item()` loop of MoDEAgent.on_before_zero_grad
+ * (mode_agent.py:304-359: ~5 host synchronisations per parameter) by one device->host copy of n floats. */
+int mode_grad_segment_sumsq(mode_engine_t* e, const int64_t* seg_host, int n, float* out_dev, void* stream);
 /* Makes `stream` wait (cudaStreamWaitEvent, no host sync) until the most recent mode_train_step has finished writing the
  * gradients of block `layer` (its backward runs last-to-first), or all gradients when layer == -1. This is what lets a
  * data-parallel caller all-reduce layer l's sections on a side stream while layers l-1..0 are still in backward — the

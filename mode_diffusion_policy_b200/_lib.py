@@ -65,6 +65,9 @@ SYMBOLS = {
     "mode_optimizer_unbind_all": (C.c_int, [_P]),
     "mode_adamw_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "mode_adamw_step_group": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "mode_optimizer_set_ema": (C.c_int, [_P, C.c_double]),
+    "mode_optimizer_ema_state": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "mode_grad_segment_sumsq": (C.c_int, [_P, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mode_optimizer_state": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mode_train_input_grads": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "mode_sample_ddim": (C.c_int, [_P, _F, _F, _F, C.POINTER(C.c_float), C.c_int, C.c_int, _P]),

@@ -33,7 +33,19 @@ struct AdamWParams {
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
   const float* grad_scale;  // device scalar multiplied into every gradient (the loss's incoming gradient), or null
   unsigned block_base;      // OptTensor::block0 of the first tensor of this launch (group launches start mid-table)
+  // Exponential moving average of the updated weights in the same pass (reference mode/callbacks/ema.py:119-126:
+  // diff = ema - w; diff *= 1 - decay; ema -= diff). Engine-owned flat buffer with the gradient layout; null = off.
+  // ema_init: the first step seeds the average with the weights BEFORE the update (the callback clones them at
+  // on_train_start, ema.py:96).
+  float* ema;
+  float ema_one_minus_decay;
+  int ema_init;
 };
+
+__device__ __forceinline__ float ema_update(float ema, float p_old, float p_new, const AdamWParams& a) {
+  const float e = a.ema_init ? p_old : ema;
+  return __fsub_rn(e, __fmul_rn(__fsub_rn(e, p_new), a.ema_one_minus_decay));  // no FMA contraction: torch does sub, mul, sub
+}
 
 __device__ __forceinline__ int opt_dst_row(int r, int swiglu_half) {
   if (swiglu_half <= 0) return r;
@@ -70,6 +82,7 @@ __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
     if (i >= numel) return;
     const size_t gi = t.g_off + i;  // sections are 128-byte aligned
     float4 p = *reinterpret_cast<const float4*>(t.p + i);
+    const float4 p_old = p;
     const float4 g = *reinterpret_cast<const float4*>(a.grads + gi);
     float4 m = *reinterpret_cast<const float4*>(a.m + gi);
     float4 v = *reinterpret_cast<const float4*>(a.v + gi);
@@ -80,6 +93,15 @@ __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
     *reinterpret_cast<float4*>(t.p + i) = p;
     *reinterpret_cast<float4*>(a.m + gi) = m;
     *reinterpret_cast<float4*>(a.v + gi) = v;
+    if (a.ema) {
+      float4 em = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!a.ema_init) em = *reinterpret_cast<const float4*>(a.ema + gi);
+      em.x = ema_update(em.x, p_old.x, p.x, a);
+      em.y = ema_update(em.y, p_old.y, p.y, a);
+      em.z = ema_update(em.z, p_old.z, p.z, a);
+      em.w = ema_update(em.w, p_old.w, p.w, a);
+      *reinterpret_cast<float4*>(a.ema + gi) = em;
+    }
     const int r = static_cast<int>(i / t.cols), c = static_cast<int>(i % t.cols);
     const size_t o = (t.dst_row0 + opt_dst_row(r, t.swiglu_half)) * static_cast<size_t>(t.cols) + c;
     if (t.to_bf16) {
@@ -97,10 +119,12 @@ __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
     if (i >= numel) return;
     const size_t gi = t.g_off + i;
     float m = a.m[gi], v = a.v[gi];
-    const float p = adamw_update(t.p[i], a.grads[gi] * gs, m, v, a, decay_mul);
+    const float p_old = t.p[i];
+    const float p = adamw_update(p_old, a.grads[gi] * gs, m, v, a, decay_mul);
     t.p[i] = p;
     a.m[gi] = m;
     a.v[gi] = v;
+    if (a.ema) a.ema[gi] = ema_update(a.ema_init ? 0.f : a.ema[gi], p_old, p, a);
     const int r = static_cast<int>(i / t.cols), c = static_cast<int>(i % t.cols);
     if (t.transpose) {
       reinterpret_cast<float*>(t.dst)[static_cast<size_t>(c) * t.rows + r] = p;
@@ -112,6 +136,63 @@ __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
         reinterpret_cast<float*>(t.dst)[o] = p;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Per-tensor sums of squares of the flat gradient buffer in two launches and ONE device->host copy: the reference's
+// gradient monitoring (MoDEAgent.on_before_zero_grad, mode_agent.py:304-359) calls `.item()` several times per
+// parameter (~1400 host synchronisations per step for the 12-layer model). Deterministic: fixed chunking, fixed order.
+constexpr int SUMSQ_CHUNK = 8192;  // elements per block of the first pass
+
+struct SumsqSegment {
+  unsigned long long off, numel;  // span of the flat buffer
+  unsigned block0;                // first block of the first pass that belongs to this segment
+  unsigned pad;
+};
+
+__global__ void __launch_bounds__(256) grad_sumsq_partial_kernel(const float* __restrict__ grads, const SumsqSegment* __restrict__ seg,
+                                                                 int n_seg, float* __restrict__ partial) {
+  int lo = 0, hi = n_seg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg[mid].block0 <= blockIdx.x)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const SumsqSegment s = seg[lo];
+  const size_t begin = static_cast<size_t>(blockIdx.x - s.block0) * SUMSQ_CHUNK;
+  const size_t end = begin + SUMSQ_CHUNK < s.numel ? begin + SUMSQ_CHUNK : s.numel;
+  float acc = 0.f;
+  for (size_t i = begin + threadIdx.x; i < end; i += 256) {
+    const float g = grads[s.off + i];
+    acc = fmaf(g, g, acc);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w >= 1; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// one block per segment: its partials summed in double, fixed order
+__global__ void __launch_bounds__(256) grad_sumsq_finish_kernel(const float* __restrict__ partial, const SumsqSegment* __restrict__ seg,
+                                                                int n_blocks_total, int n_seg, float* __restrict__ out) {
+  const int sI = blockIdx.x;
+  const unsigned b0 = seg[sI].block0, b1 = sI + 1 < n_seg ? seg[sI + 1].block0 : static_cast<unsigned>(n_blocks_total);
+  double acc = 0.0;
+  for (unsigned b = b0 + threadIdx.x; b < b1; b += 256) acc += static_cast<double>(partial[b]);
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w >= 1; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[sI] = static_cast<float>(red[0]);
 }
 
 }  // namespace mode

@@ -258,6 +258,33 @@ class ModeEngine:
 
         return view(m), view(v)
 
+    def _flat_view(self, ptr: int, numel: int) -> torch.Tensor:
+        class _Dev:
+            pass
+
+        h = _Dev()
+        h.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(h, device=self.device)
+
+    def set_ema(self, decay: Optional[float]) -> None:
+        """Moving average of the bound parameters inside the optimizer launch (reference mode/callbacks/ema.py);
+        None switches it off."""
+        _lib.check(self.lib.mode_optimizer_set_ema(self._h, -1.0 if decay is None else float(decay)))
+
+    def ema_state(self) -> torch.Tensor:
+        """Zero-copy view of the engine-owned EMA buffer (gradient-buffer layout; `grad_range(name)` gives spans)."""
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.mode_optimizer_ema_state(self._h, C.byref(p), C.byref(n)))
+        return self._flat_view(p.value, n.value)
+
+    def grad_sumsq(self, spans) -> torch.Tensor:
+        """Sum of squares of each (offset, numel) span of the flat gradient buffer, as one device tensor (two launches,
+        no host synchronisation beyond the span-table upload)."""
+        seg = np.ascontiguousarray(np.asarray(spans, dtype=np.int64).reshape(-1, 2))
+        out = torch.empty(seg.shape[0], dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.mode_grad_segment_sumsq(self._h, seg.ctypes.data, seg.shape[0], out.data_ptr(), self._stream()))
+        return out
+
     def wait_grads(self, layer: int, stream: "torch.cuda.Stream") -> None:
         """Make `stream` wait until the last train_step finished block `layer`'s gradients (-1: all gradients)."""
         _lib.check(self.lib.mode_train_wait_grads(self._h, layer, C.c_void_p(stream.cuda_stream)))

@@ -379,6 +379,35 @@ class MoDeDiT(nn.Module):
             total = total + torch.log(torch.exp(logits).sum(dim=-1) + eps).pow(2).mean()
         return total / len(aux)
 
+    def grad_norms(self):
+        """Gradient monitoring of MoDEAgent.on_before_zero_grad (reference mode_agent.py:304-359) — total norm, the
+        norm of the non-block ("input") layers and per-block per-layer norms of the last training step — from the
+        engine's flat gradient buffer with two kernel launches and ONE device-to-host copy (the reference calls
+        `.item()` several times per parameter). Works with `EngineAdamW` (no `.grad` tensors needed)."""
+        eng = self._engine
+        if eng is None:
+            raise RuntimeError("MoDE engine: grad_norms() needs a preceding training-mode GCDenoiser.loss call")
+        names = [n for n, p in self.named_parameters() if n != "gripper_embed.weight" and p.requires_grad]
+        sumsq = eng.grad_sumsq([eng.grad_range(n) for n in names]).double().cpu().numpy()
+        scale = getattr(self, "_loss_grad_scale", None)
+        s2 = 1.0 if scale is None else float(scale) ** 2
+        out = {"total": 0.0, "input_layers": 0.0, "blocks": {}}
+        for n, v in zip(names, sumsq):
+            v = float(v) * s2
+            out["total"] += v
+            if "blocks" in n:
+                parts = n.split(".")
+                blk = out["blocks"].setdefault(parts[1], {})
+                layer = ".".join(parts[2:])
+                blk[layer] = blk.get(layer, 0.0) + v
+            else:
+                out["input_layers"] += v
+        out["total"], out["input_layers"] = out["total"] ** 0.5, out["input_layers"] ** 0.5
+        for blk in out["blocks"].values():
+            for k in blk:
+                blk[k] = blk[k] ** 0.5
+        return out
+
     def routing(self, layer: int, batch: int):
         """(top_k_indices, renormalised probs, clamped softmax) of the most recent call for `layer`."""
         return self._engine.routing(layer, batch)

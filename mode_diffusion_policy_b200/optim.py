@@ -25,18 +25,60 @@ def use_weight_decay(name: str) -> bool:
 
 class EngineAdamW(torch.optim.Optimizer):
     def __init__(self, inner_model: MoDeDiT, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
-                 materialize_grads: bool = False):
+                 materialize_grads: bool = False, ema_decay=None):
         """materialize_grads=False: `loss.backward()` no longer copies the engine's gradients into `.grad` (nothing reads
-        them); set True to keep `.grad` populated for gradient logging (mode_agent.py:304-359)."""
+        them); set True to keep `.grad` populated for gradient logging (mode_agent.py:304-359; or use
+        `MoDeDiT.grad_norms()`, which needs no `.grad`).
+
+        ema_decay: None (off), a float, or a callable step -> decay (the reference callback's warm-up,
+        mode/callbacks/ema.py:84-92): an exponential moving average of the updated weights is kept by the same launch
+        (`ema_state_dict()`, `swap_ema_weights()`)."""
         self.inner = inner_model
         named = [(n, p) for n, p in inner_model.named_parameters() if p.requires_grad and n != "gripper_embed.weight"]
         super().__init__([p for _, p in named], dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._names = [n for n, _ in named]
+        self._ema_decay = ema_decay
         self._step = 0
         self._bound = {}
         inner_model._skip_param_grads = not materialize_grads
         inner_model._engine_keeps_sync = True  # step() re-packs what it updates: GCDenoiser.loss need not
         inner_model._loss_grad_scale = None
+
+    def _set_ema(self, eng):
+        d = self._ema_decay
+        eng.set_ema(None if d is None else float(d(self._step) if callable(d) else d))
+
+    def ema_state_dict(self):
+        """name -> EMA tensor (reference layout, views of the engine's buffer) for every parameter this optimizer updates."""
+        eng = self.inner._engine
+        flat = eng.ema_state()
+        params = dict(self.inner.named_parameters())
+        out = {}
+        for name in self._names:
+            off, n = eng.grad_range(name)
+            out[name] = flat[off: off + n].view(params[name].shape)
+        return out
+
+    def swap_ema_weights(self):
+        """Context manager: evaluate with the averaged weights (EMA.replace_model_weights / restore_original_weights,
+        ema.py:184-195), then put the training weights back."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            params = dict(self.inner.named_parameters())
+            ema = self.ema_state_dict()
+            saved = {n: params[n].detach().clone() for n in ema}
+            with torch.no_grad():
+                for n, v in ema.items():
+                    params[n].copy_(v)  # bumps the version counters: the engine re-packs on the next call
+            try:
+                yield
+            finally:
+                with torch.no_grad():
+                    for n, v in saved.items():
+                        params[n].copy_(v)
+        return ctx()
 
     def _bind(self, eng):
         if self._bound.get("engine") is not eng:
@@ -62,6 +104,7 @@ class EngineAdamW(torch.optim.Optimizer):
         self._bind(eng)
         g = self.param_groups[0]
         self._step += 1
+        self._set_ema(eng)
         eng.adamw_step(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._step,
                        self.inner._loss_grad_scale)
         return loss
@@ -89,6 +132,7 @@ class EngineAdamW(torch.optim.Optimizer):
         self._bind(eng)
         g = self.param_groups[0]
         self._step += 1
+        self._set_ema(eng)
         dev = eng.device
         if loss_scale is None:
             scale = self.inner._loss_grad_scale

@@ -29,6 +29,7 @@ ap.add_argument("--layers", type=int, default=12)
 ap.add_argument("--stochastic", action="store_true",
                 help="the reference's default train-mode regularisation (conf/model/mode_agent.yaml: attn_pdrop 0.3, "
                      "mlp_pdrop 0.1, goal_drop 0.1, use_argmax False = per-token multinomial routing)")
+ap.add_argument("--ema", type=float, default=None, help="keep an EMA of the weights inside the optimizer launch (decay)")
 a = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
@@ -48,8 +49,8 @@ inner.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_weights_fast(cf
 model = GCDenoiser(inner, sigma_data=0.5).cuda().train()
 if os.environ.get("MODE_TRAIN_FUSED_OPT", "1") == "1":  # one engine launch: AdamW over the flat gradient buffer + re-pack
     from mode_diffusion_policy_b200.optim import EngineAdamW
-    opt = EngineAdamW(inner, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
-    opt_name = "engine fused AdamW+repack"
+    opt = EngineAdamW(inner, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, ema_decay=a.ema)
+    opt_name = "engine fused AdamW+repack" + (f"+EMA({a.ema})" if a.ema is not None else "")
 else:
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
     opt_name = "torch fused AdamW + engine re-pack"

@@ -466,3 +466,59 @@ def test_grouped_optimizer_launches_equal_the_single_launch():
     ma, va = inner_a._engine.optimizer_state()
     mb, vb = inner_b._engine.optimizer_state()
     assert torch.equal(ma, mb) and torch.equal(va, vb)
+
+
+def test_fused_ema_and_gradient_norms():
+    """the EMA of the weights kept inside the optimizer launch equals the reference callback's
+    arithmetic (mode/callbacks/ema.py:119-126: diff = ema - w; diff *= 1 - decay; ema -= diff, seeded with the initial
+    weights) bit for bit, `swap_ema_weights` evaluates with the averaged weights and restores the training weights, and
+    `MoDeDiT.grad_norms()` reproduces on_before_zero_grad's norms (mode_agent.py:304-359) from the flat buffer."""
+    from mode_diffusion_policy_b200.optim import EngineAdamW
+
+    cfg, B = MODELS["model_tiny_d256_l3_e4"]
+    g = np.load(GOLD / "model_tiny_d256_l3_e4.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    st = {"state_images": cu(state)}
+    acts, noise, sig, goal_t = cu((x0 / np.float32(80.0)).astype(np.float32)), cu(g["loss_noise"]), cu(g["sigma_het"]), cu(goal)
+    inner, model = _tiny_denoiser(sd, cfg)
+    decays = [0.5, 0.9, 0.99]
+    opt = EngineAdamW(inner, lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05, ema_decay=lambda step: decays[step - 1])
+    names = [n for n, _ in inner.named_parameters() if n != "gripper_embed.weight"]
+    ema_ref = {n: p.detach().clone() for n, p in inner.named_parameters() if n in names}
+    for i in range(3):
+        loss, _ = model.loss(st, acts, goal_t, noise, sig)
+        loss.backward()
+        if i == 0:  # gradient norms of this step against torch norms of the same buffer
+            norms = inner.grad_norms()
+            eng = inner._engine
+            want_total = 0.0
+            for n in names:
+                gn = float(eng.grad(n, dict(inner.named_parameters())[n].shape).double().norm())
+                want_total += gn ** 2
+                if n == "blocks.1.attn.c_proj.weight":
+                    assert abs(norms["blocks"]["1"]["attn.c_proj.weight"] - gn) <= 1e-5 * gn
+            assert abs(norms["total"] - want_total ** 0.5) <= 1e-5 * want_total ** 0.5
+            assert 0 < norms["input_layers"] < norms["total"] and set(norms["blocks"]) == {"0", "1", "2"}
+        opt.step()
+        params = dict(inner.named_parameters())
+        for n in names:  # the callback's arithmetic, on the updated masters
+            diff = ema_ref[n] - params[n].detach()
+            diff.mul_(1.0 - decays[i])
+            ema_ref[n].sub_(diff)
+    ema = opt.ema_state_dict()
+    for n in names:
+        assert torch.equal(ema[n], ema_ref[n]), n
+    assert not torch.equal(ema["out.weight"], dict(inner.named_parameters())["out.weight"].detach())
+    # evaluate with the averaged weights, then the training weights are back
+    model.eval()
+    with torch.no_grad():
+        l_train, _ = model.loss(st, acts, goal_t, noise, sig)
+        before = {n: p.detach().clone() for n, p in inner.named_parameters()}
+        with opt.swap_ema_weights():
+            l_ema, _ = model.loss(st, acts, goal_t, noise, sig)
+            assert torch.equal(dict(inner.named_parameters())["out.weight"].detach(), ema_ref["out.weight"])
+        l_back, _ = model.loss(st, acts, goal_t, noise, sig)
+    assert float(l_ema) != float(l_train) and float(l_back) == float(l_train)
+    for n, p in inner.named_parameters():
+        assert torch.equal(p.detach(), before[n])
