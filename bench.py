@@ -88,7 +88,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_leg(cfg, sample_B=32, repeats=1):
+def cpu_reference_leg(cfg, sample_B=64, repeats=3):
     """Times the CPU port of the reference path (oracle/, numpy fp32, all host threads) on a bounded sample of the
     workload: one full-batch-shaped denoiser call at B=sample_B, scaled linearly to B=256."""
     from oracle import mode_oracle as O
@@ -116,7 +116,7 @@ def run_reference(args, rank):
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = cpu_reference_leg(cfg, sample_B=16 if args.steps > 2 else 32)
+        base = cpu_reference_leg(cfg, sample_B=16 if args.steps > 2 else 32, repeats=1)
         if i >= args.warmup:
             vals.append(base["value"])
     v = float(np.mean(vals))
