@@ -101,13 +101,14 @@ int mode_train_step(mode_engine_t* e, const float* state_dev, const float* goal_
  *   attn_pdrop   dropout on the attention probabilities (SDPA dropout_p, modedit.py:149; conf: 0.3)
  *   mlp_pdrop    nn.Dropout between SwishGLU and the down projection of every expert (modedit.py:254; conf: 0.1)
  *   goal_drop    MoDeDiT.mask_cond: each goal feature zeroed with this probability, no rescale (modedit.py:882-893; 0.1)
+ *   embed_pdrop  nn.Dropout on the goal / image / action token embeddings (+ positions), modedit.py:779-784 (conf: 0)
  *   multinomial  use_argmax=False: every token draws its top_k experts with torch.multinomial(probs, k, False) semantics
  *                (modedit.py:389-390) instead of arg-max; routing becomes per token.
  * The random bits are a pure function of (seed, step, stream, layer, logical coordinates) (csrc/rng.cuh, restated in
  * oracle/mode_rng.py): `step` is the position of the next mode_train_step and advances by one per stochastic step, so
  * a run is reproducible from (seed, step) and the same masks can be handed to the reference for parity tests. */
-int mode_train_set_stochastic(mode_engine_t* e, float attn_pdrop, float mlp_pdrop, float goal_drop, int multinomial,
-                              unsigned long long seed, unsigned int step);
+int mode_train_set_stochastic(mode_engine_t* e, float attn_pdrop, float mlp_pdrop, float goal_drop, float embed_pdrop,
+                              int multinomial, unsigned long long seed, unsigned int step);
 /* Token-level routing of the last stochastic (multinomial) training step for `layer`: expert indices in draw order and
  * their renormalised probabilities, [B*T, top_k] each (host buffers, either may be NULL). Synchronises the device. */
 int mode_train_get_token_routing(mode_engine_t* e, int layer, int B, int32_t* idx_host, float* w_host);

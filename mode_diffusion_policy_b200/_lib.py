@@ -56,7 +56,7 @@ SYMBOLS = {
     "mode_profile_eval": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, _F, C.c_int, C.c_int, _P, _P, _P]),
     "mode_loss": (C.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, C.c_int, _P]),
     "mode_train_step": (C.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, C.c_int, _P]),
-    "mode_train_set_stochastic": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_int, C.c_ulonglong, C.c_uint]),
+    "mode_train_set_stochastic": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_ulonglong, C.c_uint]),
     "mode_train_get_token_routing": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "mode_grad_buffer": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mode_grad_offset": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

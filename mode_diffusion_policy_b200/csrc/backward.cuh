@@ -784,6 +784,20 @@ __global__ void __launch_bounds__(256) router_wgrad_small_kernel(const float* __
 //   image rows -> dstate (bf16, operand of the tok_emb weight gradient), pos[1]
 //   action rows -> action_emb.weight gradient, pos[1 + j]
 // (the sigma-token row is added to dc by dc_reduce_kernel).
+// Embedding-dropout backward: dX[row, :] *= keep/(1-p) for every non-sigma token row, in place, before embed_bwd_kernel.
+__global__ void __launch_bounds__(256) embed_dropout_bwd_kernel(float* __restrict__ dX, int rows, int T, int d, DropoutSpec drop) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i4 = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;  // float4 index
+  if (i4 >= static_cast<size_t>(rows) * d / 4) return;
+  const size_t e0 = i4 * 4;
+  if ((e0 / d) % T == 0) return;  // sigma token: not dropped
+  const float4 m = dropout_mask4(drop, static_cast<uint32_t>(e0));
+  float4 g = reinterpret_cast<float4*>(dX)[i4];
+  g = make_float4(g.x * m.x, g.y * m.y, g.z * m.z, g.w * m.w);
+  reinterpret_cast<float4*>(dX)[i4] = g;
+}
+
 struct EmbedBwdParams {
   StepScalars sc;
   const float* dX;           // [B*T, d]

@@ -245,7 +245,7 @@ struct mode_engine {
 
   // stochastic training mode (mode_train_set_stochastic): dropout probabilities, multinomial routing, RNG position
   struct {
-    float p_attn = 0.f, p_mlp = 0.f, p_goal = 0.f;
+    float p_attn = 0.f, p_mlp = 0.f, p_goal = 0.f, p_embed = 0.f;
     int multinomial = 0;
     unsigned long long seed = 0;
     uint32_t step = 0;
@@ -1034,6 +1034,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   em.w_act_t = e->w_act; em.actions = actions; em.ln1_g = e->ln1_g; em.x = io0.x_in; em.x_copy = layer_io ? io0.x1 : nullptr; em.cvec = e->cvec; em.hA = io0.hA;
   em.B = B; em.T = e->T; em.S = e->S; em.A = e->A; em.action_dim = e->adim; em.d = e->d; em.apply_c_in = apply_c_in;
   em.eps = e->cfg.rms_eps; em.inv_sqrt_d = e->inv_sqrt_d;
+  em.drop = dropout_spec(e, e->stoch.p_embed, RNG_EMBED, 0);
   {
     ProfScope ps(e, st, PC_EMBED);
     LAUNCH_ROW_KERNEL(embed_kernel, e->d, row_blocks(B * e->T), st, em);

@@ -16,7 +16,7 @@
 
 namespace mode {
 
-enum RngStream : uint32_t { RNG_GOAL = 1, RNG_ATTN = 2, RNG_MLP = 3, RNG_ROUTE = 4 };
+enum RngStream : uint32_t { RNG_GOAL = 1, RNG_ATTN = 2, RNG_MLP = 3, RNG_ROUTE = 4, RNG_EMBED = 5 };
 
 __host__ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16;

@@ -72,7 +72,17 @@ struct EmbedParams {
   int apply_c_in;          // 1: GCDenoiser.forward scales the action input by c_in (score_wrappers.py:79-80)
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
+  // training only: nn.Dropout(embed_pdrob) on the goal / image / action token embeddings (+pos), not on the sigma token
+  // (modedit.py:779-784). Element (row, col) uses half (col & 1) of word (row*d + col)/2 of stream RNG_EMBED.
+  DropoutSpec drop = DropoutSpec{0u, 0u, 1.0f};
 };
+
+// keep/scale factors of 4 consecutive elements starting at flat element index e0 (a multiple of 4)
+__device__ __forceinline__ float4 dropout_mask4(const DropoutSpec& d, uint32_t e0) {
+  const uint32_t b0 = rng_bits(d.key, e0 >> 1), b1 = rng_bits(d.key, (e0 >> 1) + 1u);
+  return make_float4((b0 & 0xffffu) < d.thr ? 0.f : d.scale, (b0 >> 16) < d.thr ? 0.f : d.scale,
+                     (b1 & 0xffffu) < d.thr ? 0.f : d.scale, (b1 >> 16) < d.thr ? 0.f : d.scale);
+}
 
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedParams p) {
@@ -122,6 +132,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedPar
           e[3] = fmaf(act[k], w.w, e[3]);
         }
         x = make_float4(e[0] + pe.x, e[1] + pe.y, e[2] + pe.z, e[3] + pe.w);
+      }
+      if (p.drop.thr && t > 0) {
+        const float4 m = dropout_mask4(p.drop, static_cast<uint32_t>(row) * p.d + col);
+        x = make_float4(x.x * m.x, x.y * m.y, x.z * m.z, x.w * m.w);
       }
       xv[i] = x;
       ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;

@@ -165,12 +165,13 @@ class ModeEngine:
                                             sigma.data_ptr(), loss.data_ptr(), out.data_ptr(), B, self._stream()))
         return loss[0], out
 
-    def set_stochastic(self, attn_pdrop=0.0, mlp_pdrop=0.0, goal_drop=0.0, multinomial=False, seed=0, step=0):
+    def set_stochastic(self, attn_pdrop=0.0, mlp_pdrop=0.0, goal_drop=0.0, multinomial=False, seed=0, step=0, embed_pdrop=0.0):
         """Stochastic regularisation of the reference's train mode for the following `train_step` calls (attention /
         expert-MLP dropout, goal masking, per-token multinomial routing; reference modedit.py:149, :254, :882-893,
         :389-390). The masks are a pure function of (seed, step, ...): `step` advances by one per stochastic step."""
         _lib.check(self.lib.mode_train_set_stochastic(self._h, float(attn_pdrop), float(mlp_pdrop), float(goal_drop),
-                                                      int(bool(multinomial)), int(seed) & (2 ** 64 - 1), int(step)))
+                                                      float(embed_pdrop), int(bool(multinomial)),
+                                                      int(seed) & (2 ** 64 - 1), int(step)))
 
     def token_routing(self, layer: int, batch: int):
         """(expert indices in draw order, renormalised probabilities), each [batch*T, top_k], of the last multinomial

@@ -241,11 +241,8 @@ class MoDeDiT(nn.Module):
         return [n for n, _ in self.named_parameters()]
 
     def check_trainable(self) -> None:
-        """Everything the reference's train mode does is built (attention / expert dropout, goal masking, per-token
-        multinomial routing) except dropout on the embeddings (`embed_pdrob`, 0 in conf/model/mode_agent.yaml)."""
-        if self._train_cfg["embed_pdrob"] and not self._warned_deterministic:
-            logger.warning("MoDE engine: embed_pdrob=%s is not applied (the reference config uses 0)", self._train_cfg["embed_pdrob"])
-            self._warned_deterministic = True
+        """Everything the reference's train mode does is built into the engine (attention / expert / embedding dropout,
+        goal masking, per-token multinomial routing); kept for callers of the earlier interface."""
 
     # ---- stochastic regularisation of the reference's train mode (modedit.py:149, :254, :389-390, :882-893)
     def set_train_rng(self, seed: int, step: int = 0) -> None:
@@ -263,10 +260,10 @@ class MoDeDiT(nn.Module):
         """Arguments of ModeEngine.set_stochastic for the next training step (all off when `deterministic_training`)."""
         c = self._train_cfg
         if getattr(self, "deterministic_training", False):
-            return dict(attn_pdrop=0.0, mlp_pdrop=0.0, goal_drop=0.0, multinomial=False, seed=0, step=0)
+            return dict(attn_pdrop=0.0, mlp_pdrop=0.0, goal_drop=0.0, embed_pdrop=0.0, multinomial=False, seed=0, step=0)
         seed, step = self._train_rng()
         return dict(attn_pdrop=c["attn_pdrop"], mlp_pdrop=c["mlp_pdrop"], goal_drop=c["goal_drop"],
-                    multinomial=not c["use_argmax"], seed=seed, step=step)
+                    embed_pdrop=c["embed_pdrob"], multinomial=not c["use_argmax"], seed=seed, step=step)
 
     def _advance_train_rng(self):
         if getattr(self, "_train_seed", None) is not None:

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-RNG_GOAL, RNG_ATTN, RNG_MLP, RNG_ROUTE = 1, 2, 3, 4
+RNG_GOAL, RNG_ATTN, RNG_MLP, RNG_ROUTE, RNG_EMBED = 1, 2, 3, 4, 5
 _U32 = np.uint32
 
 
@@ -54,6 +54,16 @@ def goal_keep_mask(seed, step, B, G, p):
     """[B, G] bool: True = the goal feature is kept (MoDeDiT.mask_cond zeroes the others, no rescale)."""
     key = rng_key(seed, step, RNG_GOAL, 0)
     return _keep_from_elements(key, np.arange(B * G, dtype=np.uint64), p).reshape(B, G)
+
+
+def embed_keep_mask(seed, step, B, T, d, p):
+    """[B, T, d] bool keep mask of the token embeddings (+pos): element (row, col) uses half (col & 1) of word
+    (row*d + col) // 2; the sigma token (t = 0) is never dropped (reference modedit.py:779-784 applies self.drop to the
+    goal, image and action tokens only)."""
+    key = rng_key(seed, step, RNG_EMBED, 0)
+    keep = _keep_from_elements(key, np.arange(B * T * d, dtype=np.uint64), p).reshape(B, T, d)
+    keep[:, 0, :] = True
+    return keep
 
 
 def attn_keep_mask(seed, step, layer, B, H, T, p):

@@ -86,7 +86,8 @@ if __name__ == "__main__":
 #   torch.bernoulli (MoDeDiT.mask_cond, modedit.py:888), F.scaled_dot_product_attention's dropout_p (:149),
 #   nn.Dropout inside every expert Mlp (:254), torch.multinomial (RouterCond, :389-390)
 # — everything else (modules, autograd) is the reference's own code.
-def golden_train_stochastic(tag, cfg, B, seed, step, p_attn=0.3, p_mlp=0.1, p_goal=0.1, router_gain=4.0):
+def golden_train_stochastic(tag, cfg, B, seed, step, p_attn=0.3, p_mlp=0.1, p_goal=0.1, router_gain=4.0, p_embed=0.0,
+                            out_prefix="train_stoch"):
     import math
 
     from oracle import mode_rng as R
@@ -94,14 +95,30 @@ def golden_train_stochastic(tag, cfg, B, seed, step, p_attn=0.3, p_mlp=0.1, p_go
     sd = O.make_weights(cfg, seed=1234, router_gain=router_gain)
     state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
     inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cpu", goal_conditioned=True,
-                    action_dim=cfg.action_dim, embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=p_attn,
+                    action_dim=cfg.action_dim, embed_dim=cfg.embed_dim, embed_pdrob=p_embed, attn_pdrop=p_attn,
                     n_layers=cfg.n_layers, n_heads=cfg.n_heads, goal_seq_len=1, obs_seq_len=1,
                     action_seq_len=cfg.action_seq_len, state_dim=7, mlp_pdrop=p_mlp, goal_drop=p_goal,
                     num_experts=cfg.num_experts, top_k=cfg.top_k, use_argmax=False, init_style="olmoe")
     inner.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()})
     model = GCDenoiser(inner, sigma_data=cfg.sigma_data).train()
     T, E, K, H, F = cfg.seq_len, cfg.num_experts, cfg.top_k, cfg.n_heads, 4 * cfg.embed_dim
-    ctx = {"attn_calls": 0, "route_calls": 0, "masks": {}, "routing": {}}
+    ctx = {"attn_calls": 0, "route_calls": 0, "embed_calls": 0, "masks": {}, "routing": {}}
+
+    class EmbedDropout(torch.nn.Module):
+        """MoDeDiT.drop (modedit.py:779-784): called on the goal token, the image tokens and the action tokens, in this
+        order; rows t = 1, 2..1+S, 2+S..T-1 of the engine's [B, T, d] mask."""
+
+        def forward(self, x):
+            call = ctx["embed_calls"] % 3
+            ctx["embed_calls"] += 1
+            S = cfg.n_state_tokens
+            lo, hi = [(1, 2), (2, 2 + S), (2 + S, T)][call]
+            assert x.shape[1] == hi - lo
+            keep = R.embed_keep_mask(seed, step, x.shape[0], T, cfg.embed_dim, p_embed)[:, lo:hi, :]
+            return x * torch.from_numpy(keep.astype(np.float32)) / (1.0 - p_embed)
+
+    if p_embed > 0:
+        inner.drop = EmbedDropout()
 
     def fake_bernoulli(pt, *a, **k):
         bs, t, dd = pt.shape
@@ -166,7 +183,8 @@ def golden_train_stochastic(tag, cfg, B, seed, step, p_attn=0.3, p_mlp=0.1, p_go
         torch.bernoulli, torch.nn.functional.scaled_dot_product_attention, torch.multinomial = saved
     assert ctx["attn_calls"] == cfg.n_layers and ctx["route_calls"] == cfg.n_layers
     out = {"loss": np.float32(loss.item()), "F": f_out.detach().numpy(), "seed": np.int64(seed), "step": np.int64(step),
-           "p": np.array([p_attn, p_mlp, p_goal], np.float32), "router_gain": np.float32(router_gain)}
+           "p": np.array([p_attn, p_mlp, p_goal], np.float32), "p_embed": np.float32(p_embed),
+           "router_gain": np.float32(router_gain)}
     out["d_state"] = st_in.grad.numpy().copy()
     out["d_goal"] = goal_in.grad.numpy().copy()
     for li in range(cfg.n_layers):
@@ -181,9 +199,9 @@ def golden_train_stochastic(tag, cfg, B, seed, step, p_attn=0.3, p_mlp=0.1, p_go
         out[f"norm/{name}"] = np.float32(np.linalg.norm(flat.astype(np.float64)))
         out[f"sum/{name}"] = np.float32(flat.astype(np.float64).sum())
         out[f"val/{name}"] = flat[idx].astype(np.float32)
-    np.savez_compressed(OUT / f"train_stoch_{tag}.npz", **out)
+    np.savez_compressed(OUT / f"{out_prefix}_{tag}.npz", **out)
     usage = [np.bincount(ctx["routing"][li].reshape(-1), minlength=E).tolist() for li in range(cfg.n_layers)]
-    print(f"train_stoch_{tag}: loss {float(loss):.6f} (deterministic {float(g['loss_value']):.6f}); expert usage per layer {usage}")
+    print(f"{out_prefix}_{tag}: loss {float(loss):.6f} (deterministic {float(g['loss_value']):.6f}); expert usage per layer {usage}")
 
 
 if __name__ == "__main__":
@@ -193,3 +211,6 @@ if __name__ == "__main__":
     golden_train_stochastic("model_wide_d512_l2_e8", MG.O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=512, n_layers=2,
                                                                      n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=8, top_k=2),
                             4, seed=77, step=0)
+    golden_train_stochastic("model_tiny_d256_l3_e4", MG.O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3,
+                                                                     n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2),
+                            5, seed=99, step=7, p_embed=0.2, out_prefix="train_stoch_embed")

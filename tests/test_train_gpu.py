@@ -266,11 +266,13 @@ def test_fused_adamw_matches_torch_adamw_and_keeps_packed_weights_in_sync():
 # multinomial routing). The goldens were produced by the REFERENCE's own modules and autograd with its four random
 # sources patched to the engine's counter-based bits (tests/golden/make_train_goldens.py::golden_train_stochastic), so
 # engine and reference see identical masks and identical expert draws.
-@pytest.mark.parametrize("tag", list(MODELS))
-def test_stochastic_training_matches_reference_with_the_same_masks(tag):
+@pytest.mark.parametrize("tag,prefix", [(t, "train_stoch") for t in MODELS] + [("model_tiny_d256_l3_e4", "train_stoch_embed")])
+def test_stochastic_training_matches_reference_with_the_same_masks(tag, prefix):
+    """`train_stoch_embed` adds dropout 0.2 on the token embeddings (embed_pdrob; 0 in the reference config)."""
     cfg, B = MODELS[tag]
     g = np.load(GOLD / f"{tag}.npz")
-    gs = np.load(GOLD / f"train_stoch_{tag}.npz")
+    gs = np.load(GOLD / f"{prefix}_{tag}.npz")
+    p_embed = float(gs["p_embed"]) if "p_embed" in gs.files else 0.0
     sd = O.make_weights(cfg, seed=1234, router_gain=float(gs["router_gain"]))
     state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
     acts = (x0 / np.float32(80.0)).astype(np.float32)
@@ -278,7 +280,7 @@ def test_stochastic_training_matches_reference_with_the_same_masks(tag):
     p_attn, p_mlp, p_goal = (float(v) for v in gs["p"])
     seed, step = int(gs["seed"]), int(gs["step"])
     args = (cu(state), cu(acts), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
-    eng.set_stochastic(p_attn, p_mlp, p_goal, True, seed, step)
+    eng.set_stochastic(p_attn, p_mlp, p_goal, True, seed, step, embed_pdrop=p_embed)
     loss, F = eng.train_step(*args)
     torch.cuda.synchronize()
     # per-token expert draws: bit-exact against torch.multinomial-semantics draws made by the reference run
@@ -310,7 +312,7 @@ def test_stochastic_training_matches_reference_with_the_same_masks(tag):
     flat = eng.flat_grads().clone()
     loss_next, _ = eng.train_step(*args)  # step + 1: fresh masks
     assert float(loss_next) != float(loss)
-    eng.set_stochastic(p_attn, p_mlp, p_goal, True, seed, step)
+    eng.set_stochastic(p_attn, p_mlp, p_goal, True, seed, step, embed_pdrop=p_embed)
     loss_again, _ = eng.train_step(*args)
     assert float(loss_again) == float(loss) and torch.equal(flat, eng.flat_grads())
     # switching the regularisation off restores the deterministic mode exactly
@@ -333,13 +335,13 @@ def test_stochastic_pieces_one_at_a_time():
     args = (cu(state), cu(acts), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
     base = float(eng.train_step(*args)[0])
     seen = set()
-    for kw in ({"attn_pdrop": 0.3}, {"mlp_pdrop": 0.1}, {"goal_drop": 0.5}, {"multinomial": True}):
+    for kw in ({"attn_pdrop": 0.3}, {"mlp_pdrop": 0.1}, {"goal_drop": 0.5}, {"multinomial": True}, {"embed_pdrop": 0.1}):
         eng.set_stochastic(seed=5, step=1, **kw)
         v = float(eng.train_step(*args)[0])
         assert np.isfinite(v) and v != base, kw
         assert torch.isfinite(eng.flat_grads()).all()
         seen.add(v)
-    assert len(seen) == 4
+    assert len(seen) == 5
     eng.set_stochastic(multinomial=True, seed=9, step=0)
     eng.reset_expert_usage()
     eng.train_step(*args)
