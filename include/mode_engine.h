@@ -162,6 +162,13 @@ int mode_grad_segment_sumsq(mode_engine_t* e, const int64_t* seg_host, int n, fl
  * role of DDP's bucketed reducer hooks in the reference (mode/training_calvin.py:97, DDPStrategy). */
 int mode_train_wait_grads(mode_engine_t* e, int layer, void* stream);
 
+/* Fused samplers: the whole sigma loop of a k-diffusion sampler over GCDenoiser as ONE CUDA-graph launch (the update is
+ * the epilogue of the output-head kernel). `sampler`: MODE_SAMPLER_DDIM = sample_ddim (gc_sampling.py:922-951, the
+ * reference default), MODE_SAMPLER_EULER = sample_euler with s_churn = 0 (:164-211), MODE_SAMPLER_DPMPP_2M =
+ * sample_dpmpp_2m (:699-734). Arguments as mode_sample_ddim. */
+enum { MODE_SAMPLER_DDIM = 0, MODE_SAMPLER_EULER = 1, MODE_SAMPLER_DPMPP_2M = 2 };
+int mode_sample(mode_engine_t* e, int sampler, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                const float* sigmas_host, int n_plus_1, int B, void* stream);
 /* sample_ddim (gc_sampling.py:922-951) over GCDenoiser: x_inout_dev (B, action_seq_len, action_dim) holds the initial
  * noise (randn * sigma_max, drawn by the caller as in mode_agent.py:756) and receives the denoised actions.
  * sigmas_host: n_plus_1 values, the last one normally 0 (get_sigmas_exponential, gc_sampling.py:35-38).

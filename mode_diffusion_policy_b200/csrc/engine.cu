@@ -129,17 +129,17 @@ __global__ void router_hidden_kernel(const float* __restrict__ W1, const float* 
   if (lane == 0) z[item] = acc + b1[j];
 }
 
+constexpr int SCHED_COEFS = 4;  // update coefficients per sampler step (HeadParams::coefs)
 struct ScheduleArg {
-  float v[3 * 64];
+  float v[(1 + SCHED_COEFS) * 64];
   int n;
 };
-// Writes the per-step {sigma} and {sigma_next/sigma, expm1(-h)} tables the captured graph reads.
+// Writes the per-step {sigma} and update-coefficient tables the captured graph reads.
 __global__ void set_schedule_kernel(const ScheduleArg a, float* __restrict__ sig, float* __restrict__ coefs) {
   const int i = threadIdx.x;
   if (i < a.n) {
-    sig[i] = a.v[3 * i];
-    coefs[2 * i] = a.v[3 * i + 1];
-    coefs[2 * i + 1] = a.v[3 * i + 2];
+    sig[i] = a.v[(1 + SCHED_COEFS) * i];
+    for (int c = 0; c < SCHED_COEFS; ++c) coefs[SCHED_COEFS * i + c] = a.v[(1 + SCHED_COEFS) * i + 1 + c];
   }
 }
 
@@ -215,6 +215,7 @@ struct mode_engine {
 
   // workspace
   float *x, *cvec, *xnorm, *state_tok, *goal_tok, *x_work, *sig_dev, *coefs_dev, *tok_sqerr, *zbuf;
+  float* d_prev;  // previous step's denoised actions (multistep samplers)
   float *in_state, *in_goal, *in_x;  // device staging of the *_host entry points
   __nv_bfloat16 *hA, *qkv, *attn, *perm, *hbuf, *ybuf, *st_bf16, *goal_bf16;
   int *topk_idx, *sel_idx, *pos_tab, *num_tiles, *dense_counts;
@@ -571,7 +572,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(dev_alloc(e, &e->goal_tok, (size_t)goal_rows * d));
   A_(dev_alloc(e, &e->x_work, (size_t)e->maxB * e->A * e->adim));
   A_(dev_alloc(e, &e->sig_dev, 64 + (size_t)e->maxB));
-  A_(dev_alloc(e, &e->coefs_dev, 128));
+  A_(dev_alloc(e, &e->coefs_dev, SCHED_COEFS * 64));
+  A_(dev_alloc(e, &e->d_prev, (size_t)e->maxB * e->A * e->adim));
   A_(dev_alloc(e, &e->tok_sqerr, (size_t)e->maxB * e->A));
   A_(dev_alloc(e, &e->zbuf, (size_t)e->maxB * Hd));
   A_(dev_alloc(e, &e->in_state, (size_t)e->maxB * e->S * e->obs));
@@ -1049,7 +1051,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   HeadParams h;
   h.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   h.xnorm = e->xnorm; h.w_out = e->w_out; h.b_out = e->b_out; h.x_act = actions; h.out = out; h.clean = clean;
-  h.tok_sqerr = e->tok_sqerr; h.coefs = coefs;
+  h.tok_sqerr = e->tok_sqerr; h.coefs = coefs; h.d_prev = e->d_prev;
   h.B = B; h.T = e->T; h.A = e->A; h.action_dim = e->adim; h.d = e->d; h.mode = head_mode;
   {
     ProfScope ps(e, st, PC_HEAD);
@@ -1134,8 +1136,9 @@ extern "C" int mode_loss(mode_engine_t* e, const float* state_dev, const float* 
   return MODE_OK;
 }
 
-static int get_ddim_graph(mode_engine* e, int B, int n, cudaGraphExec_t* exec) {
-  const auto key = std::make_pair(B, n);
+// head_mode: 2 DDIM, 4 Euler, 5 DPM-Solver++(2M) (HeadParams::mode)
+static int get_sampler_graph(mode_engine* e, int B, int n, int head_mode, cudaGraphExec_t* exec) {
+  const auto key = std::make_pair(B, n + 128 * head_mode);
   auto it = e->graphs.find(key);
   if (it != e->graphs.end()) {
     *exec = it->second;
@@ -1147,7 +1150,7 @@ static int get_ddim_graph(mode_engine* e, int B, int n, cudaGraphExec_t* exec) {
   CU_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   int rc = MODE_OK;
   for (int i = 0; i < n && rc == MODE_OK; ++i)
-    rc = enqueue_eval(e, e->cap_stream, B, e->sig_dev + i, 0, e->x_work, 1, 2, e->x_work, e->coefs_dev + 2 * i, nullptr, i);
+    rc = enqueue_eval(e, e->cap_stream, B, e->sig_dev + i, 0, e->x_work, 1, head_mode, e->x_work, e->coefs_dev + SCHED_COEFS * i, nullptr, i);
   cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
   if (rc != MODE_OK) {
     if (graph) cudaGraphDestroy(graph);
@@ -1164,24 +1167,43 @@ static int get_ddim_graph(mode_engine* e, int B, int n, cudaGraphExec_t* exec) {
   return MODE_OK;
 }
 
-// DDIM / DPM-Solver-1 step coefficients in fp32, following the op order of sample_ddim (gc_sampling.py:936-950).
-static void ddim_schedule(const float* sigmas, int n, ScheduleArg* a) {
+// Per-step update coefficients in fp32, following the op order of the reference samplers (0-dim fp32 tensor arithmetic):
+//   DDIM / DPM-Solver-1 (gc_sampling.py:936-950)  {sigma_fn(t')/sigma_fn(t), expm1(-h)}
+//   Euler, s_churn = 0 (:164-211)                 {sigma' - sigma}
+//   DPM-Solver++(2M) (:699-734)                   {ratio, expm1(-h), 1 + 1/(2r), 1/(2r)}; the last two are {1, 0} on the
+//                                                 first step and on a step that ends at sigma = 0 (first-order update)
+static void sampler_schedule(int sampler, const float* sigmas, int n, ScheduleArg* a) {
   a->n = n;
   for (int i = 0; i < n; ++i) {
+    float* v = a->v + (1 + SCHED_COEFS) * i;
     const float s = sigmas[i], sn = sigmas[i + 1];
     const float t = -logf(s), tn = -logf(sn);  // t_fn = sigma.log().neg(); log(0) = -inf -> tn = +inf
     const float h = tn - t;
     const float ratio = expf(-tn) / expf(-t);  // sigma_fn(t_next) / sigma_fn(t)
     const float em1 = expm1f(-h);              // (-h).expm1()
-    a->v[3 * i] = s;
-    a->v[3 * i + 1] = ratio;
-    a->v[3 * i + 2] = em1;
+    v[0] = s;
+    v[1] = v[2] = v[3] = v[4] = 0.f;
+    if (sampler == MODE_SAMPLER_EULER) {
+      v[1] = sn - s;
+    } else {
+      v[1] = ratio;
+      v[2] = em1;
+      v[3] = 1.f;
+      if (sampler == MODE_SAMPLER_DPMPP_2M && i > 0 && sn != 0.f) {
+        const float h_last = t - (-logf(sigmas[i - 1]));
+        const float r = h_last / h;
+        v[3] = 1.f + 1.f / (2.f * r);
+        v[4] = 1.f / (2.f * r);
+      }
+    }
   }
 }
 
-extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const float* goal_dev, float* x_inout_dev,
-                                const float* sigmas_host, int n_plus_1, int B, void* stream) {
+extern "C" int mode_sample(mode_engine_t* e, int sampler, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                           const float* sigmas_host, int n_plus_1, int B, void* stream) {
   if (!e || !state_dev || !goal_dev || !x_inout_dev || !sigmas_host) return fail(MODE_ERR_INVALID, "null argument");
+  if (sampler != MODE_SAMPLER_DDIM && sampler != MODE_SAMPLER_EULER && sampler != MODE_SAMPLER_DPMPP_2M)
+    return fail(MODE_ERR_INVALID, "unknown fused sampler %d", sampler);
   const int n = n_plus_1 - 1;
   if (n < 1 || n > 64) return fail(MODE_ERR_INVALID, "number of sampling steps must be in [1, 64]");
   for (int i = 0; i < n; ++i)
@@ -1190,9 +1212,10 @@ extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   e->launch_count = 0;
   cudaGraphExec_t exec = nullptr;
-  RET_IF(get_ddim_graph(e, B, n, &exec));
+  const int head_mode = sampler == MODE_SAMPLER_DDIM ? 2 : (sampler == MODE_SAMPLER_EULER ? 4 : 5);
+  RET_IF(get_sampler_graph(e, B, n, head_mode, &exec));
   ScheduleArg sa;
-  ddim_schedule(sigmas_host, n, &sa);
+  sampler_schedule(sampler, sigmas_host, n, &sa);
   set_schedule_kernel<<<1, 64, 0, st>>>(sa, e->sig_dev, e->coefs_dev);
   CU_OK(cudaGetLastError());
   const size_t xbytes = (size_t)B * e->A * e->adim * sizeof(float);
@@ -1204,6 +1227,11 @@ extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const 
   CU_OK(cudaMemcpyAsync(x_inout_dev, e->x_work, xbytes, cudaMemcpyDeviceToDevice, st));
   e->launch_count += 1;
   return MODE_OK;
+}
+
+extern "C" int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                                const float* sigmas_host, int n_plus_1, int B, void* stream) {
+  return mode_sample(e, MODE_SAMPLER_DDIM, state_dev, goal_dev, x_inout_dev, sigmas_host, n_plus_1, B, stream);
 }
 
 extern "C" int mode_sample_ddim_host(mode_engine_t* e, const float* state_host, const float* goal_host,

@@ -731,9 +731,10 @@ struct HeadParams {
   float* out;              // [B, A, action_dim]
   const float* clean;      // mode 3: clean actions
   float* tok_sqerr;        // mode 3: [B*A] per-token sum of squared errors (reduced deterministically afterwards)
-  const float* coefs;      // mode 2: device {sigma_next/sigma, expm1(-h)} of this step (host fp32, reference op order)
+  const float* coefs;      // modes 2, 4, 5: this step's update coefficients (host fp32, reference op order; engine.cu sampler_schedule)
+  float* d_prev;           // mode 5: the previous step's denoised actions [B, A, action_dim] (read, then overwritten)
   int B, T, A, action_dim, d;
-  int mode;                // 0 raw F, 1 denoised D, 2 DDIM update, 3 loss (out <- F)
+  int mode;                // 0 raw F, 1 denoised D, 2 DDIM update, 3 loss (out <- F), 4 Euler update, 5 DPM-Solver++(2M) update
 };
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p) {
@@ -783,8 +784,21 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p
       } else {
         // inner * c_out + action * c_skip, each product rounded separately as ATen does
         const float den = __fadd_rn(__fmul_rn(mine, c_out), __fmul_rn(xa, c_skip));
-        // (sigma_next / sigma) * action - expm1(-h) * denoised
-        result = (p.mode == 2) ? __fsub_rn(__fmul_rn(p.coefs[0], xa), __fmul_rn(p.coefs[1], den)) : den;
+        if (p.mode == 2) {
+          // (sigma_next / sigma) * action - expm1(-h) * denoised            gc_sampling.py:948-950
+          result = __fsub_rn(__fmul_rn(p.coefs[0], xa), __fmul_rn(p.coefs[1], den));
+        } else if (p.mode == 4) {
+          // d = (action - denoised) / sigma;  action + d * (sigma_next - sigma)   gc_sampling.py:73-75, :207-209
+          result = __fadd_rn(xa, __fmul_rn(__fdiv_rn(__fsub_rn(xa, den), sigma), p.coefs[0]));
+        } else if (p.mode == 5) {
+          // denoised_d = (1 + 1/(2r)) * denoised - (1/(2r)) * old_denoised (first-order on the first / last step)   :722-731
+          float target = den;
+          if (p.coefs[3] != 0.f) target = __fsub_rn(__fmul_rn(p.coefs[2], den), __fmul_rn(p.coefs[3], p.d_prev[o]));
+          p.d_prev[o] = den;
+          result = __fsub_rn(__fmul_rn(p.coefs[0], xa), __fmul_rn(p.coefs[1], target));
+        } else {
+          result = den;
+        }
       }
     }
     if (p.out) p.out[o] = result;

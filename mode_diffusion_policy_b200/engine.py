@@ -290,14 +290,21 @@ class ModeEngine:
         """Make `stream` wait until the last train_step finished block `layer`'s gradients (-1: all gradients)."""
         _lib.check(self.lib.mode_train_wait_grads(self._h, layer, C.c_void_p(stream.cuda_stream)))
 
-    def sample_ddim(self, state, x, goal, sigmas) -> torch.Tensor:
-        """sample_ddim over GCDenoiser (whole loop = one CUDA graph). `sigmas` includes the trailing 0. Returns actions."""
+    FUSED_SAMPLERS = {"ddim": 0, "euler": 1, "dpmpp_2m": 2}  # MODE_SAMPLER_* of include/mode_engine.h
+
+    def sample(self, sampler: str, state, x, goal, sigmas) -> torch.Tensor:
+        """A whole k-diffusion sampler loop over GCDenoiser as one CUDA-graph launch: "ddim" (reference sample_ddim),
+        "euler" (sample_euler with s_churn=0), "dpmpp_2m" (sample_dpmpp_2m). `sigmas` includes the trailing 0."""
         state, goal, x, _, _, B = self._prep(state, goal, x, None)
         x = x.clone()
         sig = np.ascontiguousarray(torch.as_tensor(sigmas).detach().float().cpu().numpy(), dtype=np.float32)
-        _lib.check(self.lib.mode_sample_ddim(self._h, state.data_ptr(), goal.data_ptr(), x.data_ptr(),
-                                             sig.ctypes.data_as(C.POINTER(C.c_float)), len(sig), B, self._stream()))
+        _lib.check(self.lib.mode_sample(self._h, self.FUSED_SAMPLERS[sampler], state.data_ptr(), goal.data_ptr(), x.data_ptr(),
+                                        sig.ctypes.data_as(C.POINTER(C.c_float)), len(sig), B, self._stream()))
         return x
+
+    def sample_ddim(self, state, x, goal, sigmas) -> torch.Tensor:
+        """sample_ddim over GCDenoiser (whole loop = one CUDA graph). `sigmas` includes the trailing 0. Returns actions."""
+        return self.sample("ddim", state, x, goal, sigmas)
 
     def sample_ddim_host(self, state: np.ndarray, x: np.ndarray, goal: np.ndarray, sigmas: np.ndarray) -> np.ndarray:
         """Host-buffer entry (numpy or pinned torch CPU tensors): H2D, sample, D2H, synchronised. Returns actions."""

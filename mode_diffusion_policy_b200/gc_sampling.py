@@ -1,9 +1,10 @@
 """Noise schedules and k-diffusion samplers with the reference's names and signatures
 (`mode.models.edm_diffusion.gc_sampling`, reference gc_sampling.py:26-994), written around one shared step helper.
 
-`sample_ddim` — the reference's default sampler (conf/model/mode_agent.yaml:9) — runs as ONE fused engine call (the
-whole sigma loop is a CUDA graph) whenever the model is the engine-backed GCDenoiser and no callback / scaler /
-extra_args intervene; every other sampler calls `model(state, action, goal, sigma)` = the engine's fused denoiser once
+`sample_ddim` — the reference's default sampler (conf/model/mode_agent.yaml:9) — and `sample_euler` (without churn) /
+`sample_dpmpp_2m` run as ONE fused engine call (the whole sigma loop is a CUDA graph, the update is the epilogue of the
+output-head kernel) whenever the model is the engine-backed GCDenoiser and no callback / scaler / extra_args
+intervene; every other sampler calls `model(state, action, goal, sigma)` = the engine's fused denoiser once
 per network evaluation and does its (tiny) update arithmetic in torch.
 """
 from __future__ import annotations
@@ -146,7 +147,10 @@ def sample_ddim(model, state, action, goal, sigmas, scaler=None, extra_args=None
 @torch.no_grad()
 def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
                  s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
-    """Algorithm 2 of Karras et al. without the 2nd-order correction (reference gc_sampling.py:164-211)."""
+    """Algorithm 2 of Karras et al. without the 2nd-order correction (reference gc_sampling.py:164-211). Without churn,
+    callback, scaler or extra_args the whole loop is one fused engine call."""
+    if s_churn == 0 and scaler is None and callback is None and not extra_args and hasattr(model, "sample_fused"):
+        return model.sample_fused("euler", state, action, goal, sigmas)
     lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
     for i in range(len(sigmas) - 1):
         action, sigma_hat = _churn(action, sigmas, i, s_churn, s_tmin, s_tmax, s_noise)
@@ -272,7 +276,9 @@ def sample_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None,
 
 @torch.no_grad()
 def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None):
-    """DPM-Solver++(2M) (reference gc_sampling.py:699-734)."""
+    """DPM-Solver++(2M) (reference gc_sampling.py:699-734); fused into one engine call when nothing intervenes."""
+    if scaler is None and callback is None and not extra_args and hasattr(model, "sample_fused"):
+        return model.sample_fused("dpmpp_2m", state, action, goal, sigmas)
     lp = _Loop(model, state, goal, scaler, extra_args, callback)
     old = None
     for i in range(len(sigmas) - 1):

@@ -128,5 +128,11 @@ class GCDenoiser(nn.Module):
         goal = m._goals(goal, False)
         return self._engine(action.shape[0]).sample_ddim(state["state_images"], action, goal, sigmas).to(action.dtype)
 
+    def sample_fused(self, sampler, state, action, goal, sigmas):
+        """Fused "ddim" / "euler" / "dpmpp_2m" sampler loops (engine `mode_sample`): one CUDA-graph launch each."""
+        m = self.inner_model
+        goal = m._goals(goal, False)
+        return self._engine(action.shape[0]).sample(sampler, state["state_images"], action, goal, sigmas).to(action.dtype)
+
     def get_params(self):
         return self.inner_model.parameters()

@@ -289,3 +289,49 @@ def test_last_block_dead_row_elimination_is_bit_identical(tag, monkeypatch):
     assert torch.equal(s1, s0) and torch.equal(d1, d0) and torch.equal(f1, f0) and l1 == l0
     for (a, ta), (b, tb) in zip(u1, u0):
         assert np.array_equal(a, b) and ta == tb
+
+
+def test_fused_euler_and_dpmpp_2m_samplers():
+    """`mode_sample`: sample_euler (no churn) and sample_dpmpp_2m as ONE CUDA-graph launch each, with the update as the
+    head kernel's epilogue in the reference's fp32 op order. Against (a) the reference's own Euler golden and the
+    oracle, (b) the step-by-step python loops over the fused denoiser (forced by a no-op callback), (c) at the C-ABI
+    level, DPM++(2M) degenerates to DDIM when there is a single step, and replay is bit-identical."""
+    from mode_diffusion_policy_b200 import gc_sampling as S
+    from mode_diffusion_policy_b200.modedit import MoDeDiT
+    from mode_diffusion_policy_b200.score_wrappers import GCDenoiser
+
+    cfg, B = MODELS["model_tiny_d256_l3_e4"]
+    g = np.load(GOLD / "model_tiny_d256_l3_e4.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cuda", goal_conditioned=True, action_dim=7,
+                    embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=0.3, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                    goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7, num_experts=4, top_k=2,
+                    init_style="olmoe", max_batch=8)
+    inner.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    model = GCDenoiser(inner, sigma_data=0.5).cuda().eval()
+    st = {"state_images": cu(state)}
+    sig = cu(g["sigmas"])
+    noop = lambda d: None  # noqa: E731  (a callback forces the python loop)
+    for name, fn in (("euler", S.sample_euler), ("dpmpp_2m", S.sample_dpmpp_2m)):
+        before = inner._engine.last_launch_count() if inner._engine is not None else 0
+        fused = fn(model, st, cu(x0), cu(goal), sig, disable=True)
+        looped = fn(model, st, cu(x0), cu(goal), sig, disable=True, callback=noop)
+        assert torch.isfinite(fused).all()
+        assert rel_l2(fused.cpu().numpy(), looped.cpu().numpy()) < TOL, name
+        assert torch.equal(fused, fn(model, st, cu(x0), cu(goal), sig, disable=True)), name  # replay
+        del before
+    e = S.sample_euler(model, st, cu(x0), cu(goal), sig, disable=True).cpu().numpy()
+    assert rel_l2(e, O.sample_euler(sd, cfg, state, x0, goal, g["sigmas"], "bf16")) < TOL
+    assert rel_l2(e, g["euler_actions"]) < 2e-2
+    # Euler's update equals DDIM's in exact arithmetic ((sigma'/sigma) x + (1 - sigma'/sigma) D): the two fused loops agree
+    d = S.sample_ddim(model, st, cu(x0), cu(goal), sig, disable=True).cpu().numpy()
+    assert rel_l2(e, d) < TOL
+    # one step: DPM++(2M) has no history -> the DDIM update, bit for bit
+    eng = inner._engine
+    two = np.array([1.0, 0.0], np.float32)
+    a = eng.sample("dpmpp_2m", cu(state), cu(x0 / np.float32(80.0)), cu(goal), two)
+    b = eng.sample("ddim", cu(state), cu(x0 / np.float32(80.0)), cu(goal), two)
+    assert torch.equal(a, b)
+    with pytest.raises(Exception):
+        eng.sample("heun", cu(state), cu(x0), cu(goal), g["sigmas"])
