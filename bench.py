@@ -88,12 +88,13 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_leg(cfg, sample_B=64, repeats=3):
+def cpu_reference_leg(cfg, sample_B=64, repeats=3, sd=None):
     """Times the CPU port of the reference path (oracle/, numpy fp32, all host threads) on a bounded sample of the
-    workload: one full-batch-shaped denoiser call at B=sample_B, scaled linearly to B=256."""
+    workload: `repeats` full-network denoiser calls at B=sample_B, scaled linearly to B=256."""
     from oracle import mode_oracle as O
 
-    sd = O.make_weights_fast(cfg, seed=1234)
+    if sd is None:
+        sd = O.make_weights_fast(cfg, seed=1234)
     state, goal, x0 = O.make_inputs(cfg, sample_B, seed=4321)
     sig = np.full(sample_B, 0.5, np.float32)
     x = (x0 / np.float32(SIGMA_MAX)).astype(np.float32)
@@ -115,8 +116,9 @@ def run_reference(args, rank):
     cfg = O.ModeConfig()
     vals = []
     base = None
+    sd = O.make_weights_fast(cfg, seed=1234)  # once: every step times the same network
     for i in range(args.warmup + args.steps):
-        base = cpu_reference_leg(cfg, sample_B=16 if args.steps > 2 else 32, repeats=1)
+        base = cpu_reference_leg(cfg, sample_B=16 if args.steps > 2 else 32, repeats=1, sd=sd)
         if i >= args.warmup:
             vals.append(base["value"])
     v = float(np.mean(vals))
