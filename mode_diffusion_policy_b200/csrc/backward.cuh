@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(256) colsum_f32_partial_kernel(const float* __
   const int per = (n + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
   const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
   float acc = 0.f;
+#pragma unroll 8  // the loads are independent: keep 8 in flight per thread (the adds stay in row order)
   for (int i = r0; i < r1; ++i) acc += part[static_cast<size_t>(i) * cols + c];
   partial[static_cast<size_t>(blockIdx.y) * cols + c] = acc;
 }
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_partial_kernel(const __nv_bfl
   const int per = (n + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
   const int r0 = blockIdx.y * per, r1 = min(n, r0 + per);
   float acc = 0.f;
+#pragma unroll 8
   for (int r = r0; r < r1; ++r) acc += __bfloat162float(src[static_cast<size_t>(pr.row0 + r) * ld + c]);
   partial[(static_cast<size_t>(blockIdx.z) * COLSUM_CHUNKS + blockIdx.y) * cols_per_problem + c] = acc;
 }
