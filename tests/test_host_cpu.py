@@ -167,3 +167,91 @@ def test_checkpoint_loader_selects_and_remaps_denoiser_keys(tmp_path):
     empty.mkdir()
     with pytest.raises(FileNotFoundError):
         CK.load_pretrained_parameters(make(5), str(empty))
+
+
+def test_train_rng_bookkeeping_and_stochastic_arguments():
+    """Host side of the stochastic training mode: the constructor's regularisation settings reach the engine call,
+    the (seed, step) position advances once per step, and `deterministic_training` switches everything off."""
+    m = MoDeDiT(obs_dim=128, goal_dim=64, device="cpu", goal_conditioned=True, action_dim=7, embed_dim=256,
+                embed_pdrob=0.05, attn_pdrop=0.3, n_layers=2, n_heads=4, goal_seq_len=1, obs_seq_len=1, action_seq_len=10,
+                state_dim=7, mlp_pdrop=0.1, goal_drop=0.1, num_experts=4, top_k=2, use_argmax=False)
+    m.set_train_rng(1234, 7)
+    a = m._stochastic_args()
+    assert a == dict(attn_pdrop=0.3, mlp_pdrop=0.1, goal_drop=0.1, embed_pdrop=0.05, multinomial=True, seed=1234, step=7)
+    m._advance_train_rng()
+    assert m._stochastic_args()["step"] == 8
+    m.deterministic_training = True
+    off = m._stochastic_args()
+    assert not any(off[k] for k in ("attn_pdrop", "mlp_pdrop", "goal_drop", "embed_pdrop", "multinomial"))
+    m.deterministic_training = False
+    # default seed: derived from torch's seed (every process / rank its own stream), fixed once chosen
+    m2 = MoDeDiT(obs_dim=128, goal_dim=64, device="cpu", goal_conditioned=True, action_dim=7, embed_dim=256, embed_pdrob=0,
+                 attn_pdrop=0.3, n_layers=1, n_heads=4, goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7,
+                 use_argmax=True)
+    s1 = m2._stochastic_args()
+    assert s1["seed"] == m2._stochastic_args()["seed"] and s1["step"] == 0 and s1["multinomial"] is False
+
+
+def test_optimizer_groups_match_the_reducers_per_layer_buckets():
+    """`mode_adamw_step_group` puts block l's tensors of >= 2^20 elements in group l and everything else in the last
+    group; parallel.plan_grad_buckets (default min_bucket 2^20) must make exactly those tensors the per-layer buckets,
+    so that a block's update never starts before all of its gradients have been exchanged. Checked on the reference
+    layout of the CALVIN model: flat buffer by tensor kind, like the engine's."""
+    from mode_diffusion_policy_b200 import parallel
+
+    cfg = O.ModeConfig()
+    spec = [(n, int(np.prod(s))) for n, s in O.state_dict_spec(cfg) if n != "gripper_embed.weight"]
+    # kind-major layout: tensors of the same kind (name without the block index) are contiguous over the blocks
+    def kind(n):
+        parts = n.split(".")
+        return ".".join(parts[2:]) if parts[0] == "blocks" else n
+    order = sorted(range(len(spec)), key=lambda i: (kind(spec[i][0]), spec[i][0].startswith("blocks.") and int(spec[i][0].split(".")[1])))
+    off, ranges = 0, {}
+    for i in order:
+        n, numel = spec[i]
+        ranges[n] = (off, numel)
+        off += (numel + 31) // 32 * 32
+    per_layer = [[] for _ in range(cfg.n_layers)]
+    for n, r in ranges.items():
+        if n.startswith("blocks."):
+            per_layer[int(n.split(".")[1])].append(r)
+    buckets, tail = parallel.plan_grad_buckets(per_layer, off)
+    for layer in range(cfg.n_layers):
+        big = sorted(r for n, r in ranges.items() if n.startswith(f"blocks.{layer}.") and r[1] >= 1 << 20)
+        covered = sorted(buckets[layer])
+        assert sum(n for _, n in covered) == sum(n for _, n in big)
+        for o, n in big:  # every large tensor of the block lies inside one of its buckets
+            assert any(bo <= o and o + n <= bo + bn for bo, bn in covered)
+        small = [r for n, r in ranges.items() if n.startswith(f"blocks.{layer}.") and r[1] < 1 << 20]
+        for o, n in small:  # ...and no small one does: they ride in the tail / the last optimizer group
+            assert not any(bo <= o < bo + bn for bo, bn in covered)
+            assert any(to <= o and o + n <= to + tn for to, tn in tail)
+
+
+def test_fused_sampler_dispatch_conditions():
+    """sample_euler / sample_dpmpp_2m hand the whole loop to the engine only when nothing needs the per-step python
+    loop (no churn, callback, scaler or extra_args)."""
+    class Fused(_ToyDenoiser):
+        def __init__(self):
+            super().__init__()
+            self.calls = []
+
+        def sample_fused(self, name, state, action, goal, sigmas):
+            self.calls.append(name)
+            return action
+
+        def sample_ddim(self, state, action, goal, sigmas):
+            self.calls.append("ddim")
+            return action
+
+    sig = S.get_sigmas_exponential(5, 1e-3, 80.0)
+    x0 = torch.randn(2, 10, 7)
+    m = Fused()
+    S.sample_euler(m, None, x0, None, sig)
+    S.sample_dpmpp_2m(m, None, x0, None, sig)
+    S.sample_ddim(m, None, x0, None, sig)
+    assert m.calls == ["euler", "dpmpp_2m", "ddim"]
+    S.sample_euler(m, None, x0, None, sig, s_churn=1.0)
+    S.sample_euler(m, None, x0, None, sig, callback=lambda d: None)
+    S.sample_dpmpp_2m(m, None, x0, None, sig, extra_args={"uncond": False})
+    assert m.calls == ["euler", "dpmpp_2m", "ddim"]  # all three ran the python loop
