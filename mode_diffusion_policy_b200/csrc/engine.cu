@@ -18,6 +18,7 @@
 #include "attention.cuh"
 #include "gemm.cuh"
 #include "gemm_wgrad.cuh"
+#include "gemm_small.cuh"
 #include "mlp_fused.cuh"
 #include "rowwise.cuh"
 #include "backward.cuh"
@@ -199,6 +200,7 @@ struct mode_engine {
   bool mlp_fused;  // expert up+down projections as one dynamically scheduled launch (MODE_MLP_FUSED=1, default off; needs pair)
   int* mlp_sync;   // its tile queue head + per-M-tile dependency counters
   int tile_m;  // rows per M-tile: 256 with CTA pairs, 128 otherwise
+  bool small_m = true;  // rollout-sized batches (B*T <= 16 rows) use the weight-streaming GEMM (MODE_SMALL_M=0 disables)
   int trim_rows = 0;  // inference: the last block's experts only run on the action rows (MODE_TRIM_LAST=0 disables)
   bool finalized = false;
   std::map<std::string, WeightSpec> specs;
@@ -252,6 +254,7 @@ struct mode_engine {
     uint32_t step = 0;
   } stoch;
   bool stoch_active = false;  // true only while mode_train_step enqueues its forward/backward
+  bool train_forward = false; // true while mode_train_step enqueues (its saved activations need the tensor-memory path)
   // token-level routing tables [L][maxB*T][K] (multinomial routing draws per token), permuted-row -> token map
   int *tok_topk_idx = nullptr, *tok_sel_idx = nullptr, *tok_pos = nullptr, *row_token = nullptr;
   float *tok_topk_w = nullptr, *tok_sel_w = nullptr, *goal_masked = nullptr;
@@ -415,6 +418,28 @@ static int launch_gemm(int epi, bool pair, int num_sms, cudaStream_t st, const G
 
 // p.B == 0 only configures the kernel (opt-in shared memory); done at create time so that nothing but launches happens
 // while the DDIM loop is being captured into a CUDA graph.
+// Weight-streaming GEMM for <= 16 rows per group (gemm_small.cuh). n_cols: output columns (hidden units for SwiGLU).
+static int launch_gemm_small(int epi, cudaStream_t st, const SmallGemmParams& p, int n_cols, int max_tiles) {
+  const dim3 grid(n_cols / 8, max_tiles), block(SMALL_M_WARPS * 32);
+  switch (epi) {
+    case EPI_BIAS_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_BIAS_BF16>, grid, block, 0, st, p)); break;
+    case EPI_RESID_F32: CU_OK(launch_k(gemm_small_m_kernel<EPI_RESID_F32>, grid, block, 0, st, p)); break;
+    case EPI_SWIGLU_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_SWIGLU_BF16>, grid, block, 0, st, p)); break;
+    case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_PLAIN_BF16>, grid, block, 0, st, p)); break;
+    case EPI_PLAIN_F32: CU_OK(launch_k(gemm_small_m_kernel<EPI_PLAIN_F32>, grid, block, 0, st, p)); break;
+    default: return fail(MODE_ERR_INVALID, "small-M GEMM: unsupported epilogue %d", epi);
+  }
+  CU_OK(cudaGetLastError());
+  return MODE_OK;
+}
+static SmallGemmParams small_params(const void* A, const void* W, int K, const GemmMTile* tiles, const int* ntiles,
+                                    const float* bias, void* out, int ldo, int w_row_off) {
+  SmallGemmParams p;
+  p.A = reinterpret_cast<const __nv_bfloat16*>(A); p.W = reinterpret_cast<const __nv_bfloat16*>(W);
+  p.m_tiles = tiles; p.num_m_tiles = ntiles; p.bias = bias; p.out = out; p.K = K; p.ldo = ldo; p.w_row_off = w_row_off;
+  return p;
+}
+
 template <int DH, int MT>
 static int launch_attn_t(cudaStream_t st, const AttnParams& p) {
   constexpr int smem = ATTN_WARPS * 3 * (16 * MT) * (DH + 8) * 2;
@@ -522,6 +547,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
     const char* env = getenv("MODE_GEMM_CTA_PAIR");
     e->pair = env ? atoi(env) != 0 : true;
     e->tile_m = e->pair ? 256 : 128;
+    const char* small_env = getenv("MODE_SMALL_M");
+    e->small_m = !(small_env && atoi(small_env) == 0);
     const char* trim_env = getenv("MODE_TRIM_LAST");
     e->trim_rows = (trim_env && atoi(trim_env) == 0) ? 0 : e->A;
     env = getenv("MODE_MLP_FUSED");
@@ -847,6 +874,15 @@ static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* sta
   cast_bf16_kernel<<<(unsigned)((n_st + 255) / 256), 256, 0, st>>>(state_dev, e->st_bf16, n_st);
   cast_bf16_kernel<<<(unsigned)((n_g + 255) / 256), 256, 0, st>>>(goal_dev, e->goal_bf16, n_g);
   CU_OK(cudaGetLastError());
+  const bool small = e->small_m && !e->train_forward && B * e->S <= SMALL_M_MAX_ROWS && e->obs % 256 == 0 && e->gdim % 256 == 0;
+  if (small) {
+    RET_IF(launch_gemm_small(EPI_PLAIN_F32, st, small_params(e->st_bf16, e->w_tok, e->obs, e->dense_tiles + e->dense_cap,
+                                                             e->dense_counts + 1, nullptr, e->state_tok, e->d, 0), e->d, 1));
+    RET_IF(launch_gemm_small(EPI_PLAIN_F32, st, small_params(e->goal_bf16, e->w_goal, e->gdim, e->dense_tiles + 2 * e->dense_cap,
+                                                             e->dense_counts + 2, nullptr, e->goal_tok, e->d, 0), e->d, 1));
+    e->launch_count += 4;
+    return MODE_OK;
+  }
   GemmParams p = gemm_params(e->tm_st, e->tm_wtok, e->to_state, e->dense_tiles + e->dense_cap, e->dense_counts + 1,
                              e->d, e->obs, nullptr);
   RET_IF(launch_gemm(EPI_PLAIN_F32, e->pair, e->num_sms, st, p));
@@ -932,9 +968,15 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   GemmParams p = gemm_params(io.tm_hA, e->tm_wqkv, io.to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
   enable_stream_k(e, p);
+  // rollout-sized batch: every group has <= 16 rows -> weight-streaming kernels (gemm_small.cuh)
+  const bool small = e->small_m && !io.z && !e->train_forward && M <= SMALL_M_MAX_ROWS && d % 256 == 0;
+  const int small_groups = e->E < B * e->K ? e->E : B * e->K;  // upper bound on routed groups
   {
     ProfScope ps(e, st, PC_QKV);
-    if (!(skip >> PC_QKV & 1)) RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
+    if (small)
+      RET_IF(launch_gemm_small(EPI_BIAS_BF16, st, small_params(io.hA, e->w_qkv, d, e->dense_tiles, e->dense_counts, e->b_qkv,
+                                                               io.qkv, 3 * d, l * 3 * d), 3 * d, 1));
+    else if (!(skip >> PC_QKV & 1)) RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
   }
   AttnParams a;
   a.qkv = io.qkv; a.out = io.attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
@@ -948,7 +990,10 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   p.w_row_off = l * d;
   {
     ProfScope ps(e, st, PC_PROJ);
-    if (!(skip >> PC_PROJ & 1)) RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
+    if (small)
+      RET_IF(launch_gemm_small(EPI_RESID_F32, st, small_params(io.attn, e->w_proj, d, e->dense_tiles, e->dense_counts, nullptr,
+                                                               io.x1, d, l * d), d, 1));
+    else if (!(skip >> PC_PROJ & 1)) RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
   Ln2Params n2;
   const RouteView rv = route_view(e, B, lt, l);
@@ -959,7 +1004,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   const int t_skip = (trim_rows > 0 && !rv.per_token) ? e->T - trim_rows : 0;  // must match the plan of this layer
   n2.t_skip = t_skip;
   n2.B = rv.units; n2.T = rv.rt; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
-  const bool fused_mlp = e->mlp_fused && !io.z;  // the training forward keeps the two-launch path (it saves z)
+  const bool fused_mlp = e->mlp_fused && !io.z && !small;  // the training forward keeps the two-launch path (it saves z)
   n2.zero = fused_mlp ? e->mlp_sync : nullptr;
   n2.n_zero = 1 + e->max_tiles;
   {
@@ -991,6 +1036,9 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
         p.tmap_out2 = io.to_z;
         p.drop = mlp_drop; p.row_token = row_token; p.drop_rows_per_expert = 8 * d; p.drop_E = e->E; p.drop_half_F = e->F / 2;
         RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
+      } else if (small) {
+        RET_IF(launch_gemm_small(EPI_SWIGLU_BF16, st, small_params(io.perm, e->w_up, d, e->up_tiles + lt * e->max_tiles,
+                                                                   e->num_tiles + lt, e->b_up, io.h, e->F, 0), e->F, small_groups));
       } else if (!(skip >> PC_UP & 1)) {
         RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
       }
@@ -998,7 +1046,10 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     enable_stream_k(e, pd);
     {
       ProfScope ps(e, st, PC_DOWN);
-      if (!(skip >> PC_DOWN & 1)) RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
+      if (small)
+        RET_IF(launch_gemm_small(EPI_PLAIN_BF16, st, small_params(io.h, e->w_down, e->F, e->down_tiles + lt * e->max_tiles,
+                                                                  e->num_tiles + lt, nullptr, io.y, d, 0), d, small_groups));
+      else if (!(skip >> PC_DOWN & 1)) RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
     }
   }
   CombineParams c;

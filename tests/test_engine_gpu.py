@@ -335,3 +335,52 @@ def test_fused_euler_and_dpmpp_2m_samplers():
     assert torch.equal(a, b)
     with pytest.raises(Exception):
         eng.sample("heun", cu(state), cu(x0), cu(goal), g["sigmas"])
+
+
+@pytest.mark.parametrize("tag", list(MODELS))
+def test_small_batch_weight_streaming_path(tag, monkeypatch):
+    """B = 1 (the reference's rollout mode, MoDEAgent.step): every GEMM group has <= 16 rows and runs through the
+    weight-streaming mma.sync kernels (csrc/gemm_small.cuh) instead of the tensor-memory kernels. Same bf16 operands,
+    different accumulation order: parity against the oracle's contract, and against the tensor-memory path
+    (MODE_SMALL_M=0) within the same tolerance; routing identical; replay bit-identical."""
+    cfg, _ = MODELS[tag]
+    g = np.load(GOLD / f"{tag}.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, 5, seed=4321)
+    sigmas = O.get_sigmas_exponential(10, 1e-3, 80.0)
+    for b in (0, 3):  # two different trajectories, each as a batch of one
+        sl = slice(b, b + 1)
+        outs = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("MODE_SMALL_M", flag)
+            eng = engine_for(cfg, sd, 4)
+            den = eng.denoise(cu(state[sl]), cu(g["denoise_x"][sl]), cu(goal[sl]), cu(g["sigma_het"][sl]))
+            idx = [eng.routing(l, 1)[0].copy() for l in range(cfg.n_layers)]
+            smp = eng.sample_ddim(cu(state[sl]), cu(x0[sl]), cu(goal[sl]), sigmas)
+            assert torch.equal(smp, eng.sample_ddim(cu(state[sl]), cu(x0[sl]), cu(goal[sl]), sigmas))
+            outs[flag] = (den.cpu().numpy(), smp.cpu().numpy(), idx, eng.last_launch_count())
+        want_den = O.denoiser_forward(sd, cfg, state[sl], g["denoise_x"][sl], goal[sl], g["sigma_het"][sl], "bf16")
+        want_smp = O.sample_ddim(sd, cfg, state[sl], x0[sl], goal[sl], sigmas, "bf16")
+        for flag in ("1", "0"):
+            assert rel_l2(outs[flag][0], want_den) < TOL, (flag, rel_l2(outs[flag][0], want_den))
+            assert rel_l2(outs[flag][1], want_smp) < TOL, (flag, rel_l2(outs[flag][1], want_smp))
+        assert rel_l2(outs["1"][0], outs["0"][0]) < TOL and rel_l2(outs["1"][1], outs["0"][1]) < TOL
+        for a, c in zip(outs["1"][2], outs["0"][2]):
+            assert np.array_equal(a, c)
+
+
+def test_small_batch_path_at_calvin_widths(monkeypatch):
+    """d = 1024, obs 2048, goal 512 (2 layers): here the observation / goal embeddings take the weight-streaming path too.
+    B = 1 against the tensor-memory path and the oracle."""
+    cfg = O.ModeConfig(n_layers=2)
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, 2, seed=4321)
+    sig = np.array([0.7], np.float32)
+    xs = (x0[:1] / np.float32(80.0)).astype(np.float32)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MODE_SMALL_M", flag)
+        eng = engine_for(cfg, sd, 2)
+        res[flag] = eng.denoise(cu(state[:1]), cu(xs), cu(goal[:1]), cu(sig)).cpu().numpy()
+    want = O.denoiser_forward(sd, cfg, state[:1], xs, goal[:1], sig, "bf16")
+    assert rel_l2(res["1"], want) < TOL and rel_l2(res["0"], want) < TOL and rel_l2(res["1"], res["0"]) < TOL
