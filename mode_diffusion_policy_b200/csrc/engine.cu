@@ -418,19 +418,26 @@ static int launch_gemm(int epi, bool pair, int num_sms, cudaStream_t st, const G
 
 // p.B == 0 only configures the kernel (opt-in shared memory); done at create time so that nothing but launches happens
 // while the DDIM loop is being captured into a CUDA graph.
-// Weight-streaming GEMM for <= 16 rows per group (gemm_small.cuh). n_cols: output columns (hidden units for SwiGLU).
-static int launch_gemm_small(int epi, cudaStream_t st, const SmallGemmParams& p, int n_cols, int max_tiles) {
+// Weight-streaming GEMM for <= 32 rows per group (gemm_small.cuh). n_cols: output columns (hidden units for SwiGLU);
+// max_rows: upper bound on the rows of any group (selects the number of 16-row tiles per CTA).
+template <int MT>
+static int launch_gemm_small_mt(int epi, cudaStream_t st, const SmallGemmParams& p, int n_cols, int max_tiles) {
   const dim3 grid(n_cols / 8, max_tiles), block(SMALL_M_WARPS * 32);
   switch (epi) {
-    case EPI_BIAS_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_BIAS_BF16>, grid, block, 0, st, p)); break;
-    case EPI_RESID_F32: CU_OK(launch_k(gemm_small_m_kernel<EPI_RESID_F32>, grid, block, 0, st, p)); break;
-    case EPI_SWIGLU_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_SWIGLU_BF16>, grid, block, 0, st, p)); break;
-    case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_PLAIN_BF16>, grid, block, 0, st, p)); break;
-    case EPI_PLAIN_F32: CU_OK(launch_k(gemm_small_m_kernel<EPI_PLAIN_F32>, grid, block, 0, st, p)); break;
+    case EPI_BIAS_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_BIAS_BF16, MT>, grid, block, 0, st, p)); break;
+    case EPI_RESID_F32: CU_OK(launch_k(gemm_small_m_kernel<EPI_RESID_F32, MT>, grid, block, 0, st, p)); break;
+    case EPI_SWIGLU_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_SWIGLU_BF16, MT>, grid, block, 0, st, p)); break;
+    case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_small_m_kernel<EPI_PLAIN_BF16, MT>, grid, block, 0, st, p)); break;
+    case EPI_PLAIN_F32: CU_OK(launch_k(gemm_small_m_kernel<EPI_PLAIN_F32, MT>, grid, block, 0, st, p)); break;
     default: return fail(MODE_ERR_INVALID, "small-M GEMM: unsupported epilogue %d", epi);
   }
   CU_OK(cudaGetLastError());
   return MODE_OK;
+}
+static int launch_gemm_small(int epi, cudaStream_t st, const SmallGemmParams& p, int n_cols, int max_tiles, int max_rows) {
+  if (max_rows <= 16) return launch_gemm_small_mt<1>(epi, st, p, n_cols, max_tiles);
+  if (max_rows <= SMALL_M_MAX_ROWS) return launch_gemm_small_mt<2>(epi, st, p, n_cols, max_tiles);
+  return fail(MODE_ERR_INVALID, "small-M GEMM: %d rows per group exceed %d", max_rows, SMALL_M_MAX_ROWS);
 }
 static SmallGemmParams small_params(const void* A, const void* W, int K, const GemmMTile* tiles, const int* ntiles,
                                     const float* bias, void* out, int ldo, int w_row_off) {
@@ -877,9 +884,9 @@ static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* sta
   const bool small = e->small_m && !e->train_forward && B * e->S <= SMALL_M_MAX_ROWS && e->obs % 256 == 0 && e->gdim % 256 == 0;
   if (small) {
     RET_IF(launch_gemm_small(EPI_PLAIN_F32, st, small_params(e->st_bf16, e->w_tok, e->obs, e->dense_tiles + e->dense_cap,
-                                                             e->dense_counts + 1, nullptr, e->state_tok, e->d, 0), e->d, 1));
+                                                             e->dense_counts + 1, nullptr, e->state_tok, e->d, 0), e->d, 1, B * e->S));
     RET_IF(launch_gemm_small(EPI_PLAIN_F32, st, small_params(e->goal_bf16, e->w_goal, e->gdim, e->dense_tiles + 2 * e->dense_cap,
-                                                             e->dense_counts + 2, nullptr, e->goal_tok, e->d, 0), e->d, 1));
+                                                             e->dense_counts + 2, nullptr, e->goal_tok, e->d, 0), e->d, 1, B));
     e->launch_count += 4;
     return MODE_OK;
   }
@@ -975,7 +982,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     ProfScope ps(e, st, PC_QKV);
     if (small)
       RET_IF(launch_gemm_small(EPI_BIAS_BF16, st, small_params(io.hA, e->w_qkv, d, e->dense_tiles, e->dense_counts, e->b_qkv,
-                                                               io.qkv, 3 * d, l * 3 * d), 3 * d, 1));
+                                                               io.qkv, 3 * d, l * 3 * d), 3 * d, 1, M));
     else if (!(skip >> PC_QKV & 1)) RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
   }
   AttnParams a;
@@ -992,7 +999,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     ProfScope ps(e, st, PC_PROJ);
     if (small)
       RET_IF(launch_gemm_small(EPI_RESID_F32, st, small_params(io.attn, e->w_proj, d, e->dense_tiles, e->dense_counts, nullptr,
-                                                               io.x1, d, l * d), d, 1));
+                                                               io.x1, d, l * d), d, 1, M));
     else if (!(skip >> PC_PROJ & 1)) RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
   Ln2Params n2;
@@ -1038,7 +1045,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
         RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
       } else if (small) {
         RET_IF(launch_gemm_small(EPI_SWIGLU_BF16, st, small_params(io.perm, e->w_up, d, e->up_tiles + lt * e->max_tiles,
-                                                                   e->num_tiles + lt, e->b_up, io.h, e->F, 0), e->F, small_groups));
+                                                                   e->num_tiles + lt, e->b_up, io.h, e->F, 0), e->F, small_groups, M));
       } else if (!(skip >> PC_UP & 1)) {
         RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
       }
@@ -1048,7 +1055,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
       ProfScope ps(e, st, PC_DOWN);
       if (small)
         RET_IF(launch_gemm_small(EPI_PLAIN_BF16, st, small_params(io.h, e->w_down, e->F, e->down_tiles + lt * e->max_tiles,
-                                                                  e->num_tiles + lt, nullptr, io.y, d, 0), d, small_groups));
+                                                                  e->num_tiles + lt, nullptr, io.y, d, 0), d, small_groups, M));
       else if (!(skip >> PC_DOWN & 1)) RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
     }
   }

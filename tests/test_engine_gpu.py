@@ -61,8 +61,16 @@ def test_block_forward_parity(tag, d, H, E, T):
     assert rel_l2(y, g["y"]) < 2e-2, rel_l2(y, g["y"])  # vs the reference's fp32 block: bf16 operand rounding only
 
 
+@pytest.fixture(params=["1", "0"], ids=["small_m_on", "small_m_off"])
+def small_m(request, monkeypatch):
+    """Batches of <= 2 trajectories take the weight-streaming GEMM path (csrc/gemm_small.cuh) unless MODE_SMALL_M=0; the
+    golden parity tests run with either setting."""
+    monkeypatch.setenv("MODE_SMALL_M", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("tag", list(MODELS))
-def test_network_denoiser_loss_parity(tag):
+def test_network_denoiser_loss_parity(tag, small_m):
     cfg, B = MODELS[tag]
     g = np.load(GOLD / f"{tag}.npz")
     sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
@@ -92,7 +100,7 @@ def test_network_denoiser_loss_parity(tag):
 
 
 @pytest.mark.parametrize("tag", list(MODELS))
-def test_ddim_sample_parity(tag):
+def test_ddim_sample_parity(tag, small_m):
     cfg, B = MODELS[tag]
     g = np.load(GOLD / f"{tag}.npz")
     sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
@@ -348,14 +356,13 @@ def test_small_batch_weight_streaming_path(tag, monkeypatch):
     sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
     state, goal, x0 = O.make_inputs(cfg, 5, seed=4321)
     sigmas = O.get_sigmas_exponential(10, 1e-3, 80.0)
-    for b in (0, 3):  # two different trajectories, each as a batch of one
-        sl = slice(b, b + 1)
+    for sl in (slice(0, 1), slice(3, 4), slice(1, 3)):  # two single trajectories (16-row tiles), one pair (2 x 16 rows)
         outs = {}
         for flag in ("1", "0"):
             monkeypatch.setenv("MODE_SMALL_M", flag)
             eng = engine_for(cfg, sd, 4)
             den = eng.denoise(cu(state[sl]), cu(g["denoise_x"][sl]), cu(goal[sl]), cu(g["sigma_het"][sl]))
-            idx = [eng.routing(l, 1)[0].copy() for l in range(cfg.n_layers)]
+            idx = [eng.routing(l, sl.stop - sl.start)[0].copy() for l in range(cfg.n_layers)]
             smp = eng.sample_ddim(cu(state[sl]), cu(x0[sl]), cu(goal[sl]), sigmas)
             assert torch.equal(smp, eng.sample_ddim(cu(state[sl]), cu(x0[sl]), cu(goal[sl]), sigmas))
             outs[flag] = (den.cpu().numpy(), smp.cpu().numpy(), idx, eng.last_launch_count())
