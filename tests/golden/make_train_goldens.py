@@ -71,14 +71,6 @@ def golden_train(tag, cfg, B, router_gain=30.0):
     print(f"train_{tag}: loss {float(loss):.6f}; {len(names)} tensors; no-grad tensors: {len(unused)}")
 
 
-if __name__ == "__main__":
-    torch.set_grad_enabled(True)
-    golden_train("model_tiny_d256_l3_e4", MG.O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3,
-                                                          n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2), 5)
-    golden_train("model_wide_d512_l2_e8", MG.O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=512, n_layers=2,
-                                                          n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=8, top_k=2), 4)
-
-
 # ------------------------------------------------------------------------------------------------------------------
 # Stochastic training mode (the reference's default: attn_pdrop 0.3, mlp_pdrop 0.1, goal_drop 0.1, use_argmax=False).
 # torch's generator cannot be reproduced by the engine, so the REFERENCE is run with the engine's masks instead: the
@@ -204,13 +196,15 @@ def golden_train_stochastic(tag, cfg, B, seed, step, p_attn=0.3, p_mlp=0.1, p_go
     print(f"{out_prefix}_{tag}: loss {float(loss):.6f} (deterministic {float(g['loss_value']):.6f}); expert usage per layer {usage}")
 
 
+TINY = MG.O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3, n_heads=4, n_state_tokens=2,
+                       action_seq_len=10, num_experts=4, top_k=2)
+WIDE = MG.O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=512, n_layers=2, n_heads=4, n_state_tokens=2,
+                       action_seq_len=10, num_experts=8, top_k=2)
+
 if __name__ == "__main__":
-    golden_train_stochastic("model_tiny_d256_l3_e4", MG.O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3,
-                                                                     n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2),
-                            5, seed=20261017, step=3)
-    golden_train_stochastic("model_wide_d512_l2_e8", MG.O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=512, n_layers=2,
-                                                                     n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=8, top_k=2),
-                            4, seed=77, step=0)
-    golden_train_stochastic("model_tiny_d256_l3_e4", MG.O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3,
-                                                                     n_heads=4, n_state_tokens=2, action_seq_len=10, num_experts=4, top_k=2),
-                            5, seed=99, step=7, p_embed=0.2, out_prefix="train_stoch_embed")
+    torch.set_grad_enabled(True)
+    golden_train("model_tiny_d256_l3_e4", TINY, 5)
+    golden_train("model_wide_d512_l2_e8", WIDE, 4)
+    golden_train_stochastic("model_tiny_d256_l3_e4", TINY, 5, seed=20261017, step=3)
+    golden_train_stochastic("model_wide_d512_l2_e8", WIDE, 4, seed=77, step=0)
+    golden_train_stochastic("model_tiny_d256_l3_e4", TINY, 5, seed=99, step=7, p_embed=0.2, out_prefix="train_stoch_embed")
