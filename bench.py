@@ -89,22 +89,33 @@ def host_cores():
 
 
 def cpu_reference_leg(cfg, sample_B=64, repeats=3, sd=None):
-    """Times the CPU port of the reference path (oracle/, numpy fp32, all host threads) on a bounded sample of the
-    workload: `repeats` full-network denoiser calls at B=sample_B, scaled linearly to B=256."""
-    from oracle import mode_oracle as O
+    """Times the reference's CPU path on the host cores on a bounded sample of the workload: `repeats` full-network
+    denoiser calls at B=sample_B, scaled linearly to B=256. The reference's own modules need /root/reference, which does
+    not exist on the GPU box, so the timed code is oracle/mode_ref_torch.py: an op-for-op torch-CPU restatement (same
+    ATen kernels, same structure: router MLP on all B*T rows, embeddings recomputed per call, per-expert boolean
+    gather/scatter), pinned to the reference by the goldens (tests/test_oracle.py). `sd`: torch state_dict to reuse."""
+    import torch
 
+    from oracle import mode_oracle as O
+    from oracle import mode_ref_torch as RT
+
+    torch.set_num_threads(host_cores())
     if sd is None:
-        sd = O.make_weights_fast(cfg, seed=1234)
+        sd = RT.to_torch(O.make_weights_fast(cfg, seed=1234))
     state, goal, x0 = O.make_inputs(cfg, sample_B, seed=4321)
-    sig = np.full(sample_B, 0.5, np.float32)
-    x = (x0 / np.float32(SIGMA_MAX)).astype(np.float32)
-    O.denoiser_forward(sd, cfg, state[:2], x[:2], goal[:2], sig[:2], "fp32")  # warm BLAS threads / page in weights
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        O.denoiser_forward(sd, cfg, state, x, goal, sig, "fp32")
-    dt = (time.perf_counter() - t0) / repeats
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    S, G = t(state), t(goal)
+    sig = torch.full((sample_B,), 0.5)
+    x = t((x0 / np.float32(SIGMA_MAX)).astype(np.float32))
+    with torch.no_grad():
+        RT.denoiser_forward(sd, cfg, S[:2], x[:2], G[:2], sig[:2])  # warm the thread pool / page in the weights
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            RT.denoiser_forward(sd, cfg, S, x, G, sig)
+        dt = (time.perf_counter() - t0) / repeats
     steps_per_s = (sample_B / B_PER_GPU) / dt
     return {"value": steps_per_s, "unit": UNIT, "cores": host_cores(), "kind": "port",
+            "implementation": "torch-CPU restatement of the reference modules, op for op (oracle/mode_ref_torch.py), fp32",
             "sample": f"{repeats} denoiser call(s) at B={sample_B} ({dt:.2f} s each), scaled linearly to B={B_PER_GPU}"}
 
 
@@ -116,9 +127,11 @@ def run_reference(args, rank):
     cfg = O.ModeConfig()
     vals = []
     base = None
-    sd = O.make_weights_fast(cfg, seed=1234)  # once: every step times the same network
+    from oracle import mode_ref_torch as RT
+
+    sd = RT.to_torch(O.make_weights_fast(cfg, seed=1234))  # once: every step times the same network
     for i in range(args.warmup + args.steps):
-        base = cpu_reference_leg(cfg, sample_B=16 if args.steps > 2 else 32, repeats=1, sd=sd)
+        base = cpu_reference_leg(cfg, sample_B=64, repeats=2 if args.steps > 2 else 4, sd=sd)
         if i >= args.warmup:
             vals.append(base["value"])
     v = float(np.mean(vals))
@@ -126,7 +139,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * N_SAMPLING_STEPS / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference path on host cores (numpy port of the PyTorch modules)"},
+            "config": {"workload": WORKLOAD, "note": "reference path on host cores (torch-CPU restatement of the reference's PyTorch modules, op for op)"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

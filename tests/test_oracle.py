@@ -115,3 +115,31 @@ def test_router_ties_take_lowest_index():
     r = O.router_forward(sd, 0, np.zeros((3, 256), np.float32), cfg)
     assert np.array_equal(r["idx"], np.tile([0, 1], (3, 1)))
     np.testing.assert_allclose(r["w"], 0.5)
+
+
+@pytest.mark.parametrize("tag", list(MODELS))
+def test_torch_cpu_restatement_matches_reference(tag):
+    """oracle/mode_ref_torch.py — the op-for-op torch-CPU restatement timed as the CPU baseline (`bench.py --impl
+    reference`) — against the same reference-generated goldens: network output, top-k indices of every layer (the
+    reference routes every token: all T rows of a sample must agree), denoiser output and the 10-step DDIM sample."""
+    import torch
+
+    from oracle import mode_ref_torch as RT
+
+    cfg, B = MODELS[tag]
+    g = np.load(GOLD / f"{tag}.npz")
+    sd = RT.to_torch(O.make_weights(cfg, seed=1234, router_gain=30.0))
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    with torch.no_grad():
+        acts = t((x0 / np.float32(80.0)).astype(np.float32))
+        Fo, routing = RT.modedit_forward(sd, cfg, t(state), acts, t(goal), t(g["sigma_het"]), return_routing=True)
+        D = RT.denoiser_forward(sd, cfg, t(state), t(g["denoise_x"]), t(goal), t(g["sigma_het"]))
+        smp = RT.sample_ddim(sd, cfg, t(state), t(x0), t(goal), t(g["sigmas"]))
+    assert rel_l2(Fo.numpy(), g["forward_F"]) < 5e-6
+    for l in range(cfg.n_layers):
+        idx = routing[l].numpy()  # (B, T, k)
+        assert (idx == idx[:, :1, :]).all()
+        assert np.array_equal(idx[:, 0, :], g["forward_idx"][l])
+    assert rel_l2(D.numpy(), g["denoise_D"]) < 5e-6
+    assert rel_l2(smp.numpy(), g["ddim_actions"]) < 2e-5
