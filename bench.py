@@ -88,7 +88,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_leg(cfg, sample_B=64, repeats=3, sd=None):
+def cpu_reference_leg(cfg, sample_B=B_PER_GPU, repeats=4, sd=None):
     """Times the reference's CPU path on the host cores on a bounded sample of the workload: `repeats` full-network
     denoiser calls at B=sample_B, scaled linearly to B=256. The reference's own modules need /root/reference, which does
     not exist on the GPU box, so the timed code is oracle/mode_ref_torch.py: an op-for-op torch-CPU restatement (same
@@ -116,7 +116,8 @@ def cpu_reference_leg(cfg, sample_B=64, repeats=3, sd=None):
     steps_per_s = (sample_B / B_PER_GPU) / dt
     return {"value": steps_per_s, "unit": UNIT, "cores": host_cores(), "kind": "port",
             "implementation": "torch-CPU restatement of the reference modules, op for op (oracle/mode_ref_torch.py), fp32",
-            "sample": f"{repeats} denoiser call(s) at B={sample_B} ({dt:.2f} s each), scaled linearly to B={B_PER_GPU}"}
+            "sample": f"{repeats} denoiser call(s) at B={sample_B} ({dt:.2f} s each)" +
+                      ("" if sample_B == B_PER_GPU else f", scaled linearly to B={B_PER_GPU}")}
 
 
 def run_reference(args, rank):
@@ -131,7 +132,7 @@ def run_reference(args, rank):
 
     sd = RT.to_torch(O.make_weights_fast(cfg, seed=1234))  # once: every step times the same network
     for i in range(args.warmup + args.steps):
-        base = cpu_reference_leg(cfg, sample_B=64, repeats=2 if args.steps > 2 else 4, sd=sd)
+        base = cpu_reference_leg(cfg, sample_B=B_PER_GPU, repeats=1, sd=sd)  # one full-batch network evaluation per step
         if i >= args.warmup:
             vals.append(base["value"])
     v = float(np.mean(vals))
