@@ -16,11 +16,13 @@ from .score_wrappers import GCDenoiser
 class DenoisingPolicy:
     def __init__(self, model: GCDenoiser, sampler_type="ddim", num_sampling_steps=10, sigma_data=0.5, sigma_min=0.001,
                  sigma_max=80.0, noise_scheduler="exponential", act_window_size=10, action_dim=7,
-                 sigma_sample_density_type="loglogistic", device="cuda"):
+                 sigma_sample_density_type="loglogistic", device="cuda", sigma_sample_density_mean=-1.2,
+                 sigma_sample_density_std=1.2):
         self.model, self.sampler_type, self.num_sampling_steps = model, sampler_type, num_sampling_steps
         self.sigma_data, self.sigma_min, self.sigma_max = sigma_data, sigma_min, sigma_max
         self.noise_scheduler, self.act_window_size, self.action_dim = noise_scheduler, act_window_size, action_dim
         self.sigma_sample_density_type = sigma_sample_density_type
+        self.sigma_sample_density_mean, self.sigma_sample_density_std = sigma_sample_density_mean, sigma_sample_density_std
         self.device = device
 
     def load_pretrained_parameters(self, ckpt_path, strict: bool = False):
@@ -71,15 +73,37 @@ class DenoisingPolicy:
         return self.sample_loop(sigmas, x, state, latent_goal, latent_plan, self.sampler_type, extra_args)
 
     def make_sample_density(self):
-        if self.sigma_sample_density_type == "loglogistic":
-            import math
-            from functools import partial
+        """Training noise-level density by `sigma_sample_density_type` (reference mode_agent.py:692-731; the shipped
+        config uses 'loglogistic'). 'split-lognormal' reads its parameters from an empty config dict in the reference
+        and therefore raises KeyError there; it does here too."""
+        import math
+        from functools import partial
 
+        kind = self.sigma_sample_density_type
+        if kind == "lognormal":
+            return partial(utils.rand_log_normal, loc=self.sigma_sample_density_mean, scale=self.sigma_sample_density_std)
+        if kind == "loglogistic":
             return partial(utils.rand_log_logistic, loc=math.log(self.sigma_data), scale=0.5,
                            min_value=self.sigma_min, max_value=self.sigma_max)
+        if kind == "loguniform":
+            return partial(utils.rand_log_uniform, min_value=self.sigma_min, max_value=self.sigma_max)
+        if kind == "uniform":
+            return partial(utils.rand_uniform, min_value=self.sigma_min, max_value=self.sigma_max)
+        if kind == "v-diffusion":
+            return partial(utils.rand_v_diffusion, sigma_data=self.sigma_data, min_value=self.sigma_min,
+                           max_value=self.sigma_max)
+        if kind == "discrete":
+            # the reference passes the float `num_sampling_steps * 1e5` on to torch.linspace (a TypeError); int() here
+            sigmas = self.get_noise_schedule(int(self.num_sampling_steps * 1e5), "exponential")
+            return partial(utils.rand_discrete, values=sigmas)
+        if kind == "split-lognormal":
+            raise KeyError("mean")  # the reference indexes an empty sd_config here (mode_agent.py:725-729)
         raise ValueError("Unknown sample density type")
 
     def diffusion_loss(self, perceptual_emb, latent_goal, actions):
+        """Score-matching loss of one batch (reference mode_agent.py:659-672): train mode, per-sample sigma from the
+        training density, caller-side Gaussian noise, `GCDenoiser.loss`."""
+        self.model.train()
         sigmas = self.make_sample_density()(shape=(len(actions),), device=self.device).to(self.device)
         noise = torch.randn_like(actions)
         loss, _ = self.model.loss(perceptual_emb, actions, latent_goal, noise, sigmas)

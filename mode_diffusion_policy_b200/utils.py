@@ -35,3 +35,25 @@ def rand_log_uniform(shape, min_value, max_value, device="cpu", dtype=torch.floa
 
 def rand_uniform(shape, min_value, max_value, device="cpu", dtype=torch.float32):
     return torch.rand(shape, device=device, dtype=dtype) * (max_value - min_value) + min_value
+
+
+def rand_v_diffusion(shape, sigma_data=1.0, min_value=0.0, max_value=float("inf"), device="cpu", dtype=torch.float32):
+    """Truncated v-diffusion timestep density (reference utils.py:176-181)."""
+    cdf_lo = math.atan(min_value / sigma_data) * 2 / math.pi
+    cdf_hi = math.atan(max_value / sigma_data) * 2 / math.pi
+    u = torch.rand(shape, device=device, dtype=dtype) * (cdf_hi - cdf_lo) + cdf_lo
+    return torch.tan(u * math.pi / 2) * sigma_data
+
+
+def rand_split_log_normal(shape, loc, scale_1, scale_2, device="cpu", dtype=torch.float32):
+    """Split log-normal: half-normal magnitudes to the left (scale_1) or right (scale_2) of `loc` (reference :184-191)."""
+    n = torch.randn(shape, device=device, dtype=dtype).abs()
+    u = torch.rand(shape, device=device, dtype=dtype)
+    left, right = n * -scale_1 + loc, n * scale_2 + loc
+    return torch.where(u < scale_1 / (scale_1 + scale_2), left, right).exp()
+
+
+def rand_discrete(shape, values, device="cpu", dtype=torch.float32):
+    """Uniform draws from a table of noise levels (reference utils.py:194-198)."""
+    idx = torch.randint(0, len(values), shape, device=device)
+    return torch.index_select(values, 0, idx).to(dtype)

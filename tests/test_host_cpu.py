@@ -255,3 +255,46 @@ def test_fused_sampler_dispatch_conditions():
     S.sample_euler(m, None, x0, None, sig, callback=lambda d: None)
     S.sample_dpmpp_2m(m, None, x0, None, sig, extra_args={"uncond": False})
     assert m.calls == ["euler", "dpmpp_2m", "ddim"]  # all three ran the python loop
+
+
+def test_training_noise_densities_match_reference_draws():
+    """every `sigma_sample_density_type` of MoDEAgent.make_sample_density (mode_agent.py:692-731) —
+    the same torch seed must give the same bits as the reference's utils functions (tests/golden/sample_densities.npz,
+    generated by tests/golden/make_density_goldens.py), and the policy wrapper dispatches to them with the reference's
+    parameters."""
+    import math
+    from pathlib import Path
+
+    from mode_diffusion_policy_b200 import utils as U
+    from mode_diffusion_policy_b200.agent import DenoisingPolicy
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "sample_densities.npz")
+    cases = {
+        "lognormal": lambda: U.rand_log_normal((64,), loc=-1.2, scale=1.2),
+        "loglogistic": lambda: U.rand_log_logistic((64,), loc=math.log(0.5), scale=0.5, min_value=0.001, max_value=80.0),
+        "loguniform": lambda: U.rand_log_uniform((64,), min_value=0.001, max_value=80.0),
+        "uniform": lambda: U.rand_uniform((64,), min_value=0.001, max_value=80.0),
+        "v-diffusion": lambda: U.rand_v_diffusion((64,), sigma_data=0.5, min_value=0.001, max_value=80.0),
+        "split-lognormal": lambda: U.rand_split_log_normal((64,), loc=-1.2, scale_1=0.8, scale_2=1.4),
+        "discrete": lambda: U.rand_discrete((64,), values=torch.linspace(0.001, 80.0, 1000)),
+    }
+    for name, fn in cases.items():
+        torch.manual_seed(1234)
+        assert np.array_equal(fn().numpy(), g[name]), name
+    # the wrapper's dispatch (reference parameters: loc = ln sigma_data, scale 0.5, [sigma_min, sigma_max], ...)
+    for kind in ("lognormal", "loglogistic", "loguniform", "uniform", "v-diffusion"):
+        pol = DenoisingPolicy(model=None, sigma_sample_density_type=kind, device="cpu")
+        torch.manual_seed(1234)
+        got = pol.make_sample_density()(shape=(64,), device="cpu").numpy()
+        assert np.array_equal(got, g[kind]), kind
+    pol = DenoisingPolicy(model=None, sigma_sample_density_type="discrete", device="cpu", num_sampling_steps=1e-3)
+    s = pol.make_sample_density()(shape=(16,), device="cpu")  # a table of 100 exponential noise levels (+ the final 0)
+    assert s.shape == (16,) and float(s.max()) <= 80.0 + 1e-4
+    with pytest.raises(KeyError):
+        DenoisingPolicy(model=None, sigma_sample_density_type="split-lognormal", device="cpu").make_sample_density()
+    with pytest.raises(ValueError):
+        DenoisingPolicy(model=None, sigma_sample_density_type="nope", device="cpu").make_sample_density()
+    # truncated log-logistic: inside [sigma_min, sigma_max], median at sigma_data
+    torch.manual_seed(0)
+    x = U.rand_log_logistic((20000,), loc=math.log(0.5), scale=0.5, min_value=0.001, max_value=80.0)
+    assert float(x.min()) >= 0.001 and float(x.max()) <= 80.0 and abs(float(x.median()) - 0.5) < 0.02

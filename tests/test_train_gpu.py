@@ -524,3 +524,30 @@ def test_fused_ema_and_gradient_norms():
     assert float(l_ema) != float(l_train) and float(l_back) == float(l_train)
     for n, p in inner.named_parameters():
         assert torch.equal(p.detach(), before[n])
+
+
+def test_policy_diffusion_loss_draws_sigma_and_noise_like_the_reference():
+    """MoDEAgent.diffusion_loss (reference mode_agent.py:659-672) through the policy restatement: train mode, per-sample
+    sigma from the log-logistic training density, Gaussian noise from the caller's generator, `GCDenoiser.loss` with
+    autograd attached. Replaying the torch seed reproduces the loss exactly."""
+    from mode_diffusion_policy_b200.agent import DenoisingPolicy
+
+    cfg, B = MODELS["model_tiny_d256_l3_e4"]
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    inner, model = _tiny_denoiser(sd, cfg)
+    model.eval()
+    pol = DenoisingPolicy(model, device="cuda")
+    st = {"state_images": cu(state)}
+    acts, goal_t = cu((x0 / np.float32(80.0)).astype(np.float32)), cu(goal)
+    torch.manual_seed(7)
+    loss = pol.diffusion_loss(st, goal_t, acts)
+    assert model.training and loss.requires_grad and torch.isfinite(loss)
+    torch.manual_seed(7)
+    sigmas = pol.make_sample_density()(shape=(B,), device="cuda")
+    noise = torch.randn_like(acts)
+    assert float(sigmas.min()) >= 1e-3 and float(sigmas.max()) <= 80.0
+    want, _ = model.loss(st, acts, goal_t, noise, sigmas)
+    assert float(loss) == float(want)
+    loss.backward()
+    assert dict(inner.named_parameters())["out.weight"].grad is not None
