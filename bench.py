@@ -340,7 +340,7 @@ def main():
                 "value": units_per_step * args.steps * N_SAMPLING_STEPS / (trimmed_ms * 1e-3), "unit": UNIT,
                 "note": "engine default: the last block's experts skip the 4 token rows per trajectory that cannot reach the "
                         "output head; results bit-identical to the headline run (asserted); NOT used for `value`/`e2e`"}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU leg belongs to the N=1 line only
             line["cpu_baseline"] = cpu_reference_leg(cfg)
         print(json.dumps(line), flush=True)
     if world > 1:
