@@ -96,8 +96,8 @@ def cpu_reference_leg(cfg, sample_B=B_PER_GPU, repeats=4, sd=None):
     gather/scatter), pinned to the reference by the goldens (tests/test_oracle.py). `sd`: torch state_dict to reuse."""
     import torch
 
-    from oracle import mode_oracle as O
-    from oracle import mode_ref_torch as RT
+    import synthetic_workload as O
+    from oracle import mode_ref_torch as RT  # the only use of oracle/ in this file: the CPU arm being timed
 
     torch.set_num_threads(host_cores())
     if sd is None:
@@ -121,7 +121,7 @@ def cpu_reference_leg(cfg, sample_B=B_PER_GPU, repeats=4, sd=None):
 
 
 def run_reference(args, rank):
-    from oracle import mode_oracle as O
+    import synthetic_workload as O
 
     if rank != 0:
         return
@@ -169,7 +169,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from oracle import mode_oracle as O  # inputs/weights generator + cpu_baseline leg only
+    import synthetic_workload as O  # data generators only; oracle/ (the checker) is touched by the cpu_baseline leg alone
     from mode_diffusion_policy_b200 import parallel
     from mode_diffusion_policy_b200.engine import EngineConfig, ModeEngine
 

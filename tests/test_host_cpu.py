@@ -298,3 +298,24 @@ def test_training_noise_densities_match_reference_draws():
     torch.manual_seed(0)
     x = U.rand_log_logistic((20000,), loc=math.log(0.5), scale=0.5, min_value=0.001, max_value=80.0)
     assert float(x.min()) >= 0.001 and float(x.max()) <= 80.0 and abs(float(x.median()) - 0.5) < 0.02
+
+
+def test_synthetic_workload_equals_the_oracles_generators():
+    """bench.py's engine arm takes its model shape, random weights, inputs and noise schedule from synthetic_workload.py
+    (it must not touch oracle/); the generators are the oracle's, bit for bit, so the benchmark runs on the numbers the
+    parity tests check."""
+    import synthetic_workload as W
+
+    kw = dict(embed_dim=256, n_layers=2, n_heads=4, obs_dim=128, goal_dim=64, num_experts=4)
+    cw, co = W.ModeConfig(**kw), O.ModeConfig(**kw)
+    assert W.ModeConfig() == W.ModeConfig() and vars(W.ModeConfig()) == vars(O.ModeConfig()) and cw.seq_len == co.seq_len
+    assert W.state_dict_spec(cw) == O.state_dict_spec(co)
+    a, b = W.make_weights_fast(cw, seed=1234), O.make_weights_fast(co, seed=1234)
+    assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    for x, y in zip(W.make_inputs(cw, 3, seed=7), O.make_inputs(co, 3, seed=7)):
+        assert np.array_equal(x, y)
+    assert np.array_equal(W.get_sigmas_exponential(10, 1e-3, 80.0), O.get_sigmas_exponential(10, 1e-3, 80.0))
+    # the engine arm of bench.py does not import the oracle
+    src = (Path(__file__).resolve().parents[1] / "bench.py").read_text()
+    main_src = src[src.index("def main():"):]
+    assert "oracle" not in main_src.replace("oracle/ (the checker)", "")
