@@ -143,3 +143,27 @@ def test_torch_cpu_restatement_matches_reference(tag):
         assert np.array_equal(idx[:, 0, :], g["forward_idx"][l])
     assert rel_l2(D.numpy(), g["denoise_D"]) < 5e-6
     assert rel_l2(smp.numpy(), g["ddim_actions"]) < 2e-5
+
+
+@pytest.mark.parametrize("tag,prefix", [(t, "train_stoch") for t in MODELS] + [("model_tiny_d256_l3_e4", "train_stoch_embed")])
+def test_train_mode_oracle_matches_reference_under_the_engines_masks(tag, prefix):
+    """oracle/mode_oracle_train.py (numpy train-mode forward with the masks of oracle/mode_rng.py) against the goldens the
+    REFERENCE produced with its random sources patched to the same bits: expert draws identical for every token and
+    layer, network output and loss to fp32 accuracy. This pins the mask conventions (which bit drops which element,
+    the 1/(1-p) scalings, the draw algorithm) on the CPU, independently of the CUDA kernels that implement them."""
+    from oracle import mode_oracle_train as OT
+
+    cfg, B = MODELS[tag]
+    g = np.load(GOLD / f"{tag}.npz")
+    gs = np.load(GOLD / f"{prefix}_{tag}.npz")
+    sd = O.make_weights(cfg, seed=1234, router_gain=float(gs["router_gain"]))
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    p_attn, p_mlp, p_goal = (float(v) for v in gs["p"])
+    loss, Fo, draws = OT.denoiser_loss_train(sd, cfg, state, acts, goal, g["loss_noise"], g["sigma_het"], seed=int(gs["seed"]),
+                                             step=int(gs["step"]), p_attn=p_attn, p_mlp=p_mlp, p_goal=p_goal,
+                                             p_embed=float(gs["p_embed"]), multinomial=True)
+    for layer in range(cfg.n_layers):
+        assert np.array_equal(draws[layer], gs[f"routing/{layer}"]), layer
+    assert rel_l2(Fo, gs["F"]) < 1e-5, rel_l2(Fo, gs["F"])
+    assert abs(loss - float(gs["loss"])) <= 1e-5 * abs(float(gs["loss"]))
