@@ -72,6 +72,13 @@ int mode_set_weight(mode_engine_t* e, const char* name, const void* data, int is
                     int ndim);
 /* Verifies every tensor was provided, precomputes the sigma-embedding and router affine forms. Synchronous. */
 int mode_finalize_weights(mode_engine_t* e);
+/* The same two calls with the packing kernels (and the "weights ready" event) on `stream` — the stream on which the
+ * caller's parameter updates were enqueued — instead of the legacy default stream. The plain entries above are these
+ * with stream = NULL. A repack is additionally ordered after the engine's own earlier work only if that work ran on the
+ * same stream (the Python layer always passes torch's current stream to both). */
+int mode_set_weight_on_stream(mode_engine_t* e, const char* ref_name, const void* data, int is_device,
+                              const int64_t* shape, int ndim, void* stream);
+int mode_finalize_weights_on_stream(mode_engine_t* e, void* stream);
 
 /* MoDeDiT.forward(states, actions, goals, sigma) (modedit.py:741-809), eval mode: raw network output F.
  * state_dev (B, n_state_tokens, obs_dim); goal_dev (B, goal_dim); actions_dev, out_dev (B, action_seq_len, action_dim);
@@ -152,6 +159,10 @@ int mode_optimizer_state(mode_engine_t* e, float** exp_avg_dev, float** exp_avg_
  * (gradient-buffer layout: mode_grad_offset gives each parameter's span). */
 int mode_optimizer_set_ema(mode_engine_t* e, double decay);
 int mode_optimizer_ema_state(mode_engine_t* e, float** ema_dev, int64_t* numel);
+/* Checkpoint resume: the caller has copied a saved average into the buffer above; the next step must update it instead
+ * of seeding it from the current weights (the reference's EMA callback restores its averages the same way,
+ * mode/callbacks/ema.py:150-160). */
+int mode_optimizer_ema_mark_seeded(mode_engine_t* e);
 /* Sums of squares of n spans (offset, numel; host array) of the flat gradient buffer -> out_dev[n], two launches,
  * deterministic. Replaces the per-parameter `.grad.norm().item()` loop of MoDEAgent.on_before_zero_grad
  * (mode_agent.py:304-359: ~5 host synchronisations per parameter) by one device->host copy of n floats. */
@@ -190,6 +201,10 @@ int mode_block_forward(mode_engine_t* e, int layer, const float* x_dev, const fl
  * idx_host (B, top_k) int32 in torch.topk order, w_host (B, top_k) renormalised probabilities, probs_host (B, E)
  * clamped softmax; any may be NULL. Synchronises the device. */
 int mode_get_routing(mode_engine_t* e, int layer, int B, int32_t* idx_host, float* w_host, float* probs_host);
+/* The same for evaluation `step` (0-based) of the most recent fused sampler call (mode_sample*): the whole sigma schedule
+ * is routed ahead of the loop, one table slot per network evaluation (gc_sampling.py:945 feeds sigmas[i] to every
+ * sample, so each (step, layer) has one routing decision). step = -1: the most recent evaluation (as above). */
+int mode_get_routing_at(mode_engine_t* e, int step, int layer, int B, int32_t* idx_host, float* w_host, float* probs_host);
 
 /* NoiseBlockMoE.get_expert_usage / total_tokens_processed / reset_expert_usage (modedit.py:597-605). Synchronises. */
 int mode_get_expert_usage(mode_engine_t* e, int layer, int64_t* usage_host /* [num_experts] */,

@@ -51,6 +51,8 @@ SYMBOLS = {
     "mode_last_error": (C.c_char_p, []),
     "mode_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "mode_finalize_weights": (C.c_int, [_P]),
+    "mode_set_weight_on_stream": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int, _P]),
+    "mode_finalize_weights_on_stream": (C.c_int, [_P, _P]),
     "mode_forward": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, _F, C.c_int, _P]),
     "mode_denoise": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, _F, C.c_int, _P]),
     "mode_profile_eval": (C.c_int, [_P, _F, _F, _F, _F, C.c_int, _F, C.c_int, C.c_int, _P, _P, _P]),
@@ -67,6 +69,7 @@ SYMBOLS = {
     "mode_adamw_step_group": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mode_optimizer_set_ema": (C.c_int, [_P, C.c_double]),
     "mode_optimizer_ema_state": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "mode_optimizer_ema_mark_seeded": (C.c_int, [_P]),
     "mode_grad_segment_sumsq": (C.c_int, [_P, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mode_optimizer_state": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mode_train_input_grads": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -75,6 +78,7 @@ SYMBOLS = {
     "mode_sample_ddim_host": (C.c_int, [_P, _F, _F, _F, C.POINTER(C.c_float), C.c_int, C.c_int, _P]),
     "mode_block_forward": (C.c_int, [_P, C.c_int, _F, _F, _F, C.c_int, _P]),
     "mode_get_routing": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "mode_get_routing_at": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "mode_get_expert_usage": (C.c_int, [_P, C.c_int, _P, _P]),
     "mode_reset_expert_usage": (C.c_int, [_P]),
     "mode_last_launch_count": (C.c_int64, [_P]),

@@ -25,7 +25,7 @@ class LoadReport:
     ignored: int = 0                                    # encoder / CLIP / unrelated tensors in the file
 
 
-def read_state_dict(ckpt_path: str) -> dict:
+def read_state_dict(ckpt_path: str, trust_pickle: bool = False) -> dict:
     """Directory with model_cleaned.safetensors / model_cleaned.pt, or a single .safetensors / .pt / .ckpt file
     (reference mode_agent.py:143-161)."""
     if os.path.isdir(ckpt_path):
@@ -41,7 +41,14 @@ def read_state_dict(ckpt_path: str) -> dict:
         from safetensors.torch import load_file
 
         return load_file(ckpt_path)
-    data = torch.load(ckpt_path, map_location="cpu", weights_only=True)
+    try:
+        data = torch.load(ckpt_path, map_location="cpu", weights_only=True)
+    except Exception:
+        # Lightning .ckpt files pickle hyper-parameter objects next to the tensors; the reference loads them with
+        # plain torch.load (mode_agent.py:155-161). Opt in explicitly: unpickling runs code from the file.
+        if not trust_pickle:
+            raise
+        data = torch.load(ckpt_path, map_location="cpu", weights_only=False)
     return data["state_dict"] if isinstance(data, dict) and "state_dict" in data else data
 
 
@@ -62,11 +69,14 @@ def denoiser_state_dict(state_dict: dict, model_keys) -> tuple[dict, int]:
     return out, ignored
 
 
-def load_pretrained_parameters(inner_model: torch.nn.Module, ckpt_path: str, strict: bool = False) -> LoadReport:
+def load_pretrained_parameters(inner_model: torch.nn.Module, ckpt_path: str, strict: bool = False,
+                               freeze_routers: bool = False, trust_pickle: bool = False) -> LoadReport:
     """Load the denoiser's weights from a MoDE checkpoint into `inner_model` (a MoDeDiT). Shape mismatches are skipped
-    (strict=False, the reference's default) or raise (strict=True). The engine re-packs lazily on the next call."""
+    (strict=False, the reference's default) or raise (strict=True). The engine re-packs lazily on the next call.
+    `freeze_routers=True` freezes the routers afterwards like the reference's fine-tuning path
+    (`prepare_model_for_finetuning`, mode_agent.py:762-769); `trust_pickle=True` allows Lightning `.ckpt` files."""
     current = inner_model.state_dict()
-    found, ignored = denoiser_state_dict(read_state_dict(ckpt_path), current.keys())
+    found, ignored = denoiser_state_dict(read_state_dict(ckpt_path, trust_pickle), current.keys())
     rep = LoadReport(ignored=ignored)
     new_state = {}
     for key, tensor in found.items():
@@ -83,6 +93,8 @@ def load_pretrained_parameters(inner_model: torch.nn.Module, ckpt_path: str, str
         raise RuntimeError(f"Failed to load weights from {ckpt_path}: missing {rep.missing[:5]}, "
                            f"shape mismatches {rep.skipped_shape[:5]}")
     inner_model.load_state_dict(new_state, strict=False)
+    if freeze_routers and hasattr(inner_model, "freeze_router"):
+        inner_model.freeze_router()
     return rep
 
 

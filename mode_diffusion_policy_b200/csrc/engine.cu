@@ -703,9 +703,10 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   return MODE_OK;
 }
 
-extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* data, int is_device,
-                               const int64_t* shape, int ndim) {
+extern "C" int mode_set_weight_on_stream(mode_engine_t* e, const char* name, const void* data, int is_device,
+                                         const int64_t* shape, int ndim, void* stream) {
   if (!e || !name || !data) return fail(MODE_ERR_INVALID, "null argument");
+  cudaStream_t pst = reinterpret_cast<cudaStream_t>(stream);
   auto it = e->specs.find(name);
   if (it == e->specs.end()) return fail(MODE_ERR_UNKNOWN_NAME, "'%s' is not a MoDeDiT state_dict key for this configuration", name);
   WeightSpec& s = it->second;
@@ -720,26 +721,32 @@ extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* d
   const int threads = 256;
   const unsigned blocks = (unsigned)((numel + threads - 1) / threads);
   if (is_device) {
-    // device source: pack straight from the caller's tensor, stream-ordered on the default stream, no synchronisation
-    // (a training loop re-packs all 686 M parameters after every optimiser step)
+    // device source: pack straight from the caller's tensor, stream-ordered on the CALLER's stream (the one its
+    // parameter updates were enqueued on), no synchronisation (a training loop with a torch optimizer re-packs all
+    // 686 M parameters after every step)
     if (!s.transpose && s.cols % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
       const size_t n4 = numel / 4;
-      pack_rows_vec4_kernel<<<(unsigned)((n4 + threads - 1) / threads), threads>>>(
+      pack_rows_vec4_kernel<<<(unsigned)((n4 + threads - 1) / threads), threads, 0, pst>>>(
           reinterpret_cast<const float4*>(data), s.dst, s.rows, s.cols / 4, s.dst_row0, s.swiglu_half, s.to_bf16);
     } else {
-      pack_rows_kernel<<<blocks, threads>>>(reinterpret_cast<const float*>(data), s.dst, s.rows, s.cols, s.dst_row0,
-                                            s.swiglu_half, s.to_bf16, s.transpose ? 1 : 0);
+      pack_rows_kernel<<<blocks, threads, 0, pst>>>(reinterpret_cast<const float*>(data), s.dst, s.rows, s.cols, s.dst_row0,
+                                                    s.swiglu_half, s.to_bf16, s.transpose ? 1 : 0);
     }
     CU_OK(cudaGetLastError());
     return MODE_OK;
   }
   if (numel > e->stage_elems) return fail(MODE_ERR_INVALID, "'%s' larger than the staging buffer", name);
-  CU_OK(cudaMemcpy(e->stage, data, numel * sizeof(float), cudaMemcpyHostToDevice));
-  pack_rows_kernel<<<blocks, threads>>>(e->stage, s.dst, s.rows, s.cols, s.dst_row0, s.swiglu_half, s.to_bf16,
-                                        s.transpose ? 1 : 0);
+  CU_OK(cudaMemcpyAsync(e->stage, data, numel * sizeof(float), cudaMemcpyHostToDevice, pst));
+  pack_rows_kernel<<<blocks, threads, 0, pst>>>(e->stage, s.dst, s.rows, s.cols, s.dst_row0, s.swiglu_half, s.to_bf16,
+                                                s.transpose ? 1 : 0);
   CU_OK(cudaGetLastError());
-  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaStreamSynchronize(pst));  // the staging buffer and the caller's host array are reused right away
   return MODE_OK;
+}
+
+extern "C" int mode_set_weight(mode_engine_t* e, const char* name, const void* data, int is_device,
+                               const int64_t* shape, int ndim) {
+  return mode_set_weight_on_stream(e, name, data, is_device, shape, ndim, nullptr);
 }
 
 // Quantities derived from the packed weights (the sigma-affine collapse of DESIGN.md §5), recomputed whenever they change.
@@ -758,19 +765,22 @@ static int refresh_derived(mode_engine* e, cudaStream_t st) {
   return MODE_OK;
 }
 
-extern "C" int mode_finalize_weights(mode_engine_t* e) {
+extern "C" int mode_finalize_weights_on_stream(mode_engine_t* e, void* stream) {
   if (!e) return fail(MODE_ERR_INVALID, "null engine");
+  cudaStream_t pst = reinterpret_cast<cudaStream_t>(stream);
   for (auto& kv : e->specs)
     if (!kv.second.provided && !kv.second.ignore) return fail(MODE_ERR_STATE, "weight '%s' was never set", kv.first.c_str());
-  RET_IF(refresh_derived(e, nullptr));
+  RET_IF(refresh_derived(e, pst));
   // no host synchronisation: host-source weights were already synchronised in mode_set_weight, device-source packing is
-  // stream-ordered; the first call on another stream waits for this event (ensure_batch)
+  // stream-ordered on `stream`; the first call on any stream waits for this event (ensure_batch)
   if (!e->weights_ready) CU_OK(cudaEventCreateWithFlags(&e->weights_ready, cudaEventDisableTiming));
-  CU_OK(cudaEventRecord(e->weights_ready, nullptr));
+  CU_OK(cudaEventRecord(e->weights_ready, pst));
   e->weights_wait_pending = true;
   e->finalized = true;
   return MODE_OK;
 }
+
+extern "C" int mode_finalize_weights(mode_engine_t* e) { return mode_finalize_weights_on_stream(e, nullptr); }
 
 // ------------------------------------------------------------------------------------------------ batch tables
 static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
@@ -970,8 +980,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   const int d = e->d, M = B * e->T;
   const size_t lt = (size_t)slot * e->L + l;  // layer index inside the routing tables
   // measurement aid (scripts/skip_diag.py): bit PC_x set = do not launch that kernel class; outputs are then garbage
-  const char* skip_env = getenv("MODE_DEBUG_SKIP");
-  const unsigned skip = skip_env ? (unsigned)strtoul(skip_env, nullptr, 0) : 0u;
+  static const unsigned skip = getenv("MODE_DEBUG_SKIP") ? (unsigned)strtoul(getenv("MODE_DEBUG_SKIP"), nullptr, 0) : 0u;
   GemmParams p = gemm_params(io.tm_hA, e->tm_wqkv, io.to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
   enable_stream_k(e, p);
@@ -1334,17 +1343,23 @@ extern "C" int mode_block_forward(mode_engine_t* e, int layer, const float* x_de
   return MODE_OK;
 }
 
-extern "C" int mode_get_routing(mode_engine_t* e, int layer, int B, int32_t* idx_host, float* w_host, float* probs_host) {
+extern "C" int mode_get_routing_at(mode_engine_t* e, int step, int layer, int B, int32_t* idx_host, float* w_host,
+                                   float* probs_host) {
   if (!e) return fail(MODE_ERR_INVALID, "null engine");
   if (layer < 0 || layer >= e->L || B < 1 || B > e->maxB) return fail(MODE_ERR_INVALID, "layer/B out of range");
+  if (step < -1 || step >= ROUTE_SLOT_EVAL) return fail(MODE_ERR_INVALID, "step %d out of range", step);
   CU_OK(cudaDeviceSynchronize());
-  const size_t lt = (size_t)e->last_slot * e->L + layer;
+  const size_t lt = (size_t)(step < 0 ? e->last_slot : step) * e->L + layer;
   const size_t o = lt * B * e->K;
   if (idx_host) CU_OK(cudaMemcpy(idx_host, e->topk_idx + o, (size_t)B * e->K * sizeof(int), cudaMemcpyDeviceToHost));
   if (w_host) CU_OK(cudaMemcpy(w_host, e->topk_w + o, (size_t)B * e->K * sizeof(float), cudaMemcpyDeviceToHost));
   if (probs_host)
     CU_OK(cudaMemcpy(probs_host, e->probs + lt * B * e->E, (size_t)B * e->E * sizeof(float), cudaMemcpyDeviceToHost));
   return MODE_OK;
+}
+
+extern "C" int mode_get_routing(mode_engine_t* e, int layer, int B, int32_t* idx_host, float* w_host, float* probs_host) {
+  return mode_get_routing_at(e, -1, layer, B, idx_host, w_host, probs_host);
 }
 
 extern "C" int mode_get_expert_usage(mode_engine_t* e, int layer, int64_t* usage_host, int64_t* total_tokens_host) {

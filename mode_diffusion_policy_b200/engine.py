@@ -54,6 +54,8 @@ class ModeEngine:
         _lib.check(self.lib.mode_create(C.byref(c), C.byref(h)))
         self._h = h
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self.train_generation = 0      # number of train_step calls: each one overwrites the flat gradient buffer
+        self.has_train_state = False   # optimizer moments / EMA / exported zero-copy views live in this engine
 
     def close(self):
         if getattr(self, "_h", None):
@@ -79,9 +81,9 @@ class ModeEngine:
                 keep = np.ascontiguousarray(w, dtype=np.float32)
                 is_dev, ptr, shape = 0, keep.ctypes.data, keep.shape
             shp = (C.c_int64 * len(shape))(*shape)
-            _lib.check(self.lib.mode_set_weight(self._h, name.encode(), ptr, is_dev, shp, len(shape)))
+            _lib.check(self.lib.mode_set_weight_on_stream(self._h, name.encode(), ptr, is_dev, shp, len(shape), self._stream()))
             del keep
-        _lib.check(self.lib.mode_finalize_weights(self._h))
+        _lib.check(self.lib.mode_finalize_weights_on_stream(self._h, self._stream()))
 
     # ---------------------------------------------------------------- evaluations
     @staticmethod
@@ -163,6 +165,7 @@ class ModeEngine:
         loss = torch.empty(1, dtype=torch.float32, device=action.device)
         _lib.check(self.lib.mode_train_step(self._h, state.data_ptr(), goal.data_ptr(), action.data_ptr(), noise.data_ptr(),
                                             sigma.data_ptr(), loss.data_ptr(), out.data_ptr(), B, self._stream()))
+        self.train_generation += 1
         return loss[0], out
 
     def set_stochastic(self, attn_pdrop=0.0, mlp_pdrop=0.0, goal_drop=0.0, multinomial=False, seed=0, step=0, embed_pdrop=0.0):
@@ -185,6 +188,7 @@ class ModeEngine:
     def flat_grads(self) -> torch.Tensor:
         """Zero-copy torch view of the engine-owned flat fp32 gradient buffer (one all-reduce synchronises DP ranks)."""
         if getattr(self, "_flat", None) is None:
+            self.has_train_state = True
             ptr, n = C.c_void_p(), C.c_int64()
             _lib.check(self.lib.mode_grad_buffer(self._h, C.byref(ptr), C.byref(n)))
 
@@ -221,6 +225,7 @@ class ModeEngine:
         """Register the fp32 master of reference parameter `name`; mode_adamw_step updates it in place."""
         if not (param.is_cuda and param.dtype == torch.float32 and param.is_contiguous()):
             raise ValueError(f"{name}: the fused optimizer needs a contiguous fp32 CUDA parameter")
+        self.has_train_state = True
         _lib.check(self.lib.mode_optimizer_bind(self._h, name.encode(), C.c_void_p(param.data_ptr()), int(bool(weight_decay))))
 
     def optimizer_unbind_all(self) -> None:
@@ -274,9 +279,14 @@ class ModeEngine:
 
     def ema_state(self) -> torch.Tensor:
         """Zero-copy view of the engine-owned EMA buffer (gradient-buffer layout; `grad_range(name)` gives spans)."""
+        self.has_train_state = True
         p, n = C.c_void_p(), C.c_int64()
         _lib.check(self.lib.mode_optimizer_ema_state(self._h, C.byref(p), C.byref(n)))
         return self._flat_view(p.value, n.value)
+
+    def ema_mark_seeded(self) -> None:
+        """After restoring a checkpointed average into `ema_state()`: keep it instead of re-seeding from the weights."""
+        _lib.check(self.lib.mode_optimizer_ema_mark_seeded(self._h))
 
     def grad_sumsq(self, spans) -> torch.Tensor:
         """Sum of squares of each (offset, numel) span of the flat gradient buffer, as one device tensor (two launches,
@@ -333,12 +343,14 @@ class ModeEngine:
         return out
 
     # ---------------------------------------------------------------- introspection
-    def routing(self, layer: int, B: int):
+    def routing(self, layer: int, B: int, step: int = -1):
+        """(top-k indices in torch.topk order, renormalised weights, clamped probabilities) of layer `layer` for the most
+        recent evaluation, or for evaluation `step` of the most recent fused sampler call."""
         k, E = self.cfg.top_k, self.cfg.num_experts
         idx = np.empty((B, k), dtype=np.int32)
         w = np.empty((B, k), dtype=np.float32)
         probs = np.empty((B, E), dtype=np.float32)
-        _lib.check(self.lib.mode_get_routing(self._h, layer, B, idx.ctypes.data, w.ctypes.data, probs.ctypes.data))
+        _lib.check(self.lib.mode_get_routing_at(self._h, step, layer, B, idx.ctypes.data, w.ctypes.data, probs.ctypes.data))
         return idx, w, probs
 
     def expert_usage(self, layer: int):

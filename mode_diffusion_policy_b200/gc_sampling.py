@@ -125,6 +125,15 @@ def _churn(x, sigmas, i, s_churn, s_tmin, s_tmax, s_noise):
     return x, sigma_hat
 
 
+def _fusable(model, attr, sigmas, scaler, extra_args, callback) -> bool:
+    """The engine's one-launch samplers take at most 64 evaluations at strictly positive sigmas (only the trailing
+    sigma may be 0); every other schedule the reference samplers accept runs through the host loop."""
+    if scaler is not None or callback is not None or extra_args or not hasattr(model, attr):
+        return False
+    s = torch.as_tensor(sigmas)
+    return 2 <= s.numel() <= 65 and bool((s[:-1] > 0).all())
+
+
 def _exp_step(x, denoised, t, t_next):
     """x <- (sigma(t')/sigma(t)) x - expm1(-(t'-t)) D : the DPM-Solver-1 / DDIM update (reference gc_sampling.py:950)."""
     return (_sig(t_next) / _sig(t)) * x - (-(t_next - t)).expm1() * denoised
@@ -134,7 +143,7 @@ def _exp_step(x, denoised, t, t_next):
 @torch.no_grad()
 def sample_ddim(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, eta=1.0):
     """DPM-Solver-1 / DDIM (reference gc_sampling.py:922-951)."""
-    if scaler is None and callback is None and not extra_args and hasattr(model, "sample_ddim"):
+    if _fusable(model, "sample_ddim", sigmas, scaler, extra_args, callback):
         return model.sample_ddim(state, action, goal, sigmas)  # fused: one CUDA-graph launch for the whole loop
     lp = _Loop(model, state, goal, scaler, extra_args, callback)
     for i in range(len(sigmas) - 1):
@@ -149,7 +158,7 @@ def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=Non
                  s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
     """Algorithm 2 of Karras et al. without the 2nd-order correction (reference gc_sampling.py:164-211). Without churn,
     callback, scaler or extra_args the whole loop is one fused engine call."""
-    if s_churn == 0 and scaler is None and callback is None and not extra_args and hasattr(model, "sample_fused"):
+    if s_churn == 0 and _fusable(model, "sample_fused", sigmas, scaler, extra_args, callback):
         return model.sample_fused("euler", state, action, goal, sigmas)
     lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
     for i in range(len(sigmas) - 1):
@@ -277,7 +286,7 @@ def sample_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None,
 @torch.no_grad()
 def sample_dpmpp_2m(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None):
     """DPM-Solver++(2M) (reference gc_sampling.py:699-734); fused into one engine call when nothing intervenes."""
-    if scaler is None and callback is None and not extra_args and hasattr(model, "sample_fused"):
+    if _fusable(model, "sample_fused", sigmas, scaler, extra_args, callback):
         return model.sample_fused("dpmpp_2m", state, action, goal, sigmas)
     lp = _Loop(model, state, goal, scaler, extra_args, callback)
     old = None

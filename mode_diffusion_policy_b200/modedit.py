@@ -126,7 +126,8 @@ class NoiseBlockMoE(nn.Module):
     def forward(self, x, c, context=None, custom_attn_mask=None):
         """NoiseBlockMoE.forward(x, c) through the engine's block-level entry (BASELINE.json configs[0])."""
         if self.training:
-            raise NotImplementedError("train-mode routing (multinomial) and dropout are not in the engine yet")
+            raise NotImplementedError("MoDE engine: the block-level entry is eval-only; train-mode regularisation runs "
+                                      "inside GCDenoiser.loss")
         return self._owner[0]._ensure_engine(x.shape[0]).block_forward(self._layer_idx, x, c)
 
 
@@ -226,6 +227,7 @@ class MoDeDiT(nn.Module):
         cfg = self._engine_cfg
         if self._engine is None or batch > self._engine.cfg.max_batch:
             if self._engine is not None:
+                self._refuse_if_train_state(f"batch {batch} exceeds max_batch={self._engine.cfg.max_batch}")
                 self._engine.close()
             cfg.max_batch = max(cfg.max_batch, batch)
             self._engine = ModeEngine(cfg)
@@ -235,6 +237,15 @@ class MoDeDiT(nn.Module):
             self._engine.load_state_dict({k: v for k, v in self.state_dict().items()})
             self._weights_key = key
         return self._engine
+
+    def _refuse_if_train_state(self, why: str) -> None:
+        """The engine owns the Adam moments, the EMA buffer and the flat gradient buffer (and torch holds zero-copy views
+        of them): re-creating it mid-training would silently reset the optimizer and leave those views dangling."""
+        if self._engine is not None and self._engine.has_train_state:
+            raise RuntimeError(
+                f"MoDE engine: {why}, which needs a new engine, but this one holds training state (optimizer moments / "
+                "EMA / gradient views). Construct MoDeDiT(max_batch=...) for the largest batch you will use (validation "
+                "included) and set sigma_data before the first training step.")
 
     @property
     def _param_names(self):
@@ -271,10 +282,11 @@ class MoDeDiT(nn.Module):
 
     def set_sigma_data(self, sigma_data: float) -> None:
         if float(sigma_data) != self._engine_cfg.sigma_data:
-            self._engine_cfg.sigma_data = float(sigma_data)
             if self._engine is not None:
+                self._refuse_if_train_state("sigma_data changed")
                 self._engine.close()
                 self._engine = None
+            self._engine_cfg.sigma_data = float(sigma_data)
 
     # ------------------------------------------------------------------ reference surface
     def _goals(self, goals, uncond):
@@ -289,7 +301,8 @@ class MoDeDiT(nn.Module):
 
     def forward(self, states, actions, goals, sigma, uncond: Optional[bool] = False):
         if self.training:
-            raise NotImplementedError("MoDE engine: training-mode forward (dropout, multinomial routing) is not built yet")
+            raise NotImplementedError("MoDE engine: in train mode the network runs inside GCDenoiser.loss (fused forward + "
+                                      "backward with dropout / multinomial routing); call .eval() for a plain forward")
         eng = self._ensure_engine(actions.shape[0])
         goals = self._goals(goals, uncond)
         sigma = torch.as_tensor(sigma, device=actions.device)

@@ -40,6 +40,7 @@ class EngineAdamW(torch.optim.Optimizer):
         self._ema_decay = ema_decay
         self._step = 0
         self._bound = {}
+        self._consumed_generation = None  # engine.train_generation of the gradients the last step() used
         inner_model._skip_param_grads = not materialize_grads
         inner_model._engine_keeps_sync = True  # step() re-packs what it updates: GCDenoiser.loss need not
         inner_model._loss_grad_scale = None
@@ -80,6 +81,19 @@ class EngineAdamW(torch.optim.Optimizer):
                         params[n].copy_(v)
         return ctx()
 
+    def _check_fresh_gradients(self, eng):
+        """step() reads the engine's flat buffer, which every training-mode loss() overwrites: exactly one loss() per
+        step() (no gradient accumulation across calls) unless `.grad` tensors are materialised and accumulated by autograd."""
+        if not self.inner._skip_param_grads:
+            return
+        gen = eng.train_generation
+        if self._consumed_generation is not None and gen > self._consumed_generation + 1:
+            raise RuntimeError(
+                f"EngineAdamW(materialize_grads=False): {gen - self._consumed_generation} training-mode loss() calls since "
+                "the last step(), but only the last one's gradients are in the engine's buffer. Gradient accumulation "
+                "(e.g. Lightning accumulate_grad_batches > 1) needs a larger per-call batch instead.")
+        self._consumed_generation = gen
+
     def _bind(self, eng):
         if self._bound.get("engine") is not eng:
             eng.optimizer_unbind_all()
@@ -102,6 +116,7 @@ class EngineAdamW(torch.optim.Optimizer):
         if eng is None:
             raise RuntimeError("EngineAdamW.step before any GCDenoiser.loss call")
         self._bind(eng)
+        self._check_fresh_gradients(eng)
         g = self.param_groups[0]
         self._step += 1
         self._set_ema(eng)
@@ -130,6 +145,7 @@ class EngineAdamW(torch.optim.Optimizer):
         if eng is None:
             raise RuntimeError("EngineAdamW.step_overlapped before any GCDenoiser.loss call")
         self._bind(eng)
+        self._check_fresh_gradients(eng)
         g = self.param_groups[0]
         self._step += 1
         self._set_ema(eng)
@@ -179,19 +195,33 @@ class EngineAdamW(torch.optim.Optimizer):
         main.wait_stream(opt_stream)
 
     def state_dict(self):
-        sd = {"step": self._step, "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+        """Moments, the EMA buffer (the reference's EMA callback checkpoints its averages, ema.py:137-160) and the
+        position of the counter-based train-mode random stream, so a resumed run neither re-seeds the average nor replays
+        the same dropout masks / expert draws."""
+        sd = {"step": self._step, "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}],
+              "train_rng": (getattr(self.inner, "_train_seed", None), getattr(self.inner, "_train_step", 0))}
         eng = getattr(self.inner, "_engine", None)
         if eng is not None and self._step > 0:
             m, v = eng.optimizer_state()
             sd["exp_avg"], sd["exp_avg_sq"] = m.clone(), v.clone()
+            if self._ema_decay is not None:
+                sd["ema"] = eng.ema_state().clone()
         return sd
 
     def load_state_dict(self, sd):
         self._step = int(sd["step"])
         for k, v in sd["param_groups"][0].items():
             self.param_groups[0][k] = v
+        seed, step = sd.get("train_rng", (None, 0))
+        if seed is not None:
+            self.inner.set_train_rng(seed, step)
         if "exp_avg" in sd:
             eng = self.inner._ensure_engine(1)
+            self._bind(eng)
             m, v = eng.optimizer_state()
             m.copy_(sd["exp_avg"])
             v.copy_(sd["exp_avg_sq"])
+            if "ema" in sd and self._ema_decay is not None:
+                self._set_ema(eng)          # allocates the buffer (seeded from the current weights) ...
+                eng.ema_state().copy_(sd["ema"])  # ... then restore the checkpointed average
+                eng.ema_mark_seeded()

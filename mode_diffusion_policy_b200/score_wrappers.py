@@ -47,6 +47,7 @@ class _EngineLoss(torch.autograd.Function):
         eng.set_stochastic(**stoch)
         inner._last_step_multinomial = stoch["multinomial"]
         loss, out = eng.train_step(state_images, action, goal, noise, sigma)
+        ctx.generation = eng.train_generation  # the flat gradient buffer now holds THIS call's gradients
         inner._advance_train_rng()
         ctx.eng, ctx.names, ctx.shapes = eng, inner._param_names, [tuple(p.shape) for p in params]
         ctx.inner = inner
@@ -59,6 +60,11 @@ class _EngineLoss(torch.autograd.Function):
     def backward(ctx, g_loss, _g_out):
         grads = []
         inner = ctx.inner
+        if ctx.eng.train_generation != ctx.generation:
+            raise RuntimeError(
+                "MoDE engine: GCDenoiser.loss was called again before this loss was back-propagated; the engine keeps ONE "
+                "set of gradients (its flat buffer), so each training-mode loss() must be followed by its backward() "
+                "before the next loss() (sum micro-batch losses into one call, or call backward per micro-batch).")
         if getattr(inner, "_skip_param_grads", False):
             # optim.EngineAdamW reads the engine's flat gradient buffer directly: no per-parameter copies
             inner._loss_grad_scale = g_loss.detach()
@@ -98,7 +104,8 @@ class GCDenoiser(nn.Module):
     def _engine(self, batch):
         m = self.inner_model
         if m.training:
-            raise NotImplementedError("MoDE engine: training-mode forward (dropout, multinomial routing) is not built yet")
+            raise NotImplementedError("MoDE engine: in train mode use GCDenoiser.loss (fused forward + backward); call "
+                                      ".eval() for denoising / sampling")
         return m._ensure_engine(batch)
 
     def forward(self, state, action, goal, sigma, uncond=False, **kwargs):

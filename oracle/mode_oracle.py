@@ -370,13 +370,17 @@ def get_scalings(sigma, sigma_data):
     return c_skip, c_out, c_in
 
 
-def denoiser_forward(sd, cfg, state, actions, goal, sigma, prec="fp32"):
+def denoiser_forward(sd, cfg, state, actions, goal, sigma, prec="fp32", return_routing=False):
     """GCDenoiser.forward, score_wrappers.py:65-80: inner(c_in * x) * c_out + x * c_skip."""
     B = actions.shape[0]
     sigma = np.broadcast_to(np.asarray(sigma, dtype=F32).reshape(-1), (B,)).copy()
     c_skip, c_out, c_in = (t[:, None, None] for t in get_scalings(sigma, cfg.sigma_data))
-    f = modedit_forward(sd, cfg, state, (actions * c_in).astype(F32), goal, sigma, prec)
-    return ((f * c_out).astype(F32) + (actions * c_skip).astype(F32)).astype(F32)
+    f = modedit_forward(sd, cfg, state, (actions * c_in).astype(F32), goal, sigma, prec, return_routing=return_routing)
+    routing = None
+    if return_routing:
+        f, routing = f
+    d = ((f * c_out).astype(F32) + (actions * c_skip).astype(F32)).astype(F32)
+    return (d, routing) if return_routing else d
 
 
 def denoiser_loss(sd, cfg, state, action, goal, noise, sigma, prec="fp32"):

@@ -1,0 +1,135 @@
+"""CPU tests against the round-2 reference goldens (tests/golden/make_full_goldens.py):
+
+* the numpy oracle at BASELINE.json's full size (12 layers, d=1024, 4 experts) against the REFERENCE's own fp32 run — network
+  F, denoiser D, the 10-step DDIM sample and the router's top-k indices of every (step, layer), for the reference's
+  effective init (`rg1`) and the wide-margin variant (`rg30`);
+* all seven sigma schedules against the reference's values;
+* every sampler's host loop (`mode_diffusion_policy_b200.gc_sampling`) against the reference's sampler run, with the
+  oracle (fp32) standing in for the denoiser and the reference's recorded noise replayed — this pins the loop logic
+  itself (update formulas, churn, ancestral noise, multistep history) independently of the GPU.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mode_oracle as O
+from mode_diffusion_policy_b200 import gc_sampling as S
+
+GOLD = Path(__file__).resolve().parent / "golden"
+FULL = O.ModeConfig()
+TINY = O.ModeConfig(obs_dim=128, goal_dim=64, action_dim=7, embed_dim=256, n_layers=3, n_heads=4, n_state_tokens=2,
+                    action_seq_len=10, num_experts=4, top_k=2)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def _digest(sd):
+    import hashlib
+
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k]).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("gain", [30, 1])
+def test_oracle_matches_reference_at_full_depth(gain):
+    g = np.load(GOLD / f"model_full_d1024_l12_e4_rg{gain}.npz")
+    B = int(g["B"])
+    sd = O.make_weights(FULL, seed=1234, router_gain=float(gain))
+    assert _digest(sd) == str(g["weights_sha256"])
+    state, goal, x0 = O.make_inputs(FULL, B, seed=4321)
+    sig = g["sigma_het"]
+    acts = (x0 / np.float32(80.0)).astype(np.float32)
+    F, routing = O.modedit_forward(sd, FULL, state, acts, goal, sig, "fp32", return_routing=True)
+    assert rel_l2(F, g["forward_F"]) < 5e-6
+    for l in range(FULL.n_layers):
+        assert np.array_equal(routing[l]["idx"], g["forward_idx"][l]), l
+        np.testing.assert_allclose(routing[l]["probs"], g["forward_probs"][l], atol=2e-6)
+    D = O.denoiser_forward(sd, FULL, state, g["denoise_x"], goal, sig, "fp32")
+    assert rel_l2(D, g["denoise_D"]) < 5e-6
+    # the DDIM sample, one evaluation at a time so that every step's routing and denoiser output is compared
+    x = x0.copy()
+    sigmas = g["sigmas"]
+    for i, (ratio, em1) in enumerate(O.ddim_coefficients(sigmas)):
+        s_i = np.full(B, sigmas[i], np.float32)
+        den, r = O.denoiser_forward(sd, FULL, state, x, goal, s_i, "fp32", return_routing=True)
+        for l in range(FULL.n_layers):
+            assert np.array_equal(r[l]["idx"], g["ddim_idx"][i, l]), (i, l)
+        assert rel_l2(den, g["ddim_denoised"][i]) < 2e-5, i
+        x = (ratio * x - em1 * den).astype(np.float32)
+    assert rel_l2(x, g["ddim_actions"]) < 2e-5
+
+
+def test_all_sigma_schedules_match_reference_values():
+    g = np.load(GOLD / "schedules.npz")
+    for n in (10, 25):
+        got = {
+            "karras": S.get_sigmas_karras(n, 1e-3, 80.0, 7, "cpu"),
+            "exponential": S.get_sigmas_exponential(n, 1e-3, 80.0, "cpu"),
+            "linear": S.get_sigmas_linear(n, 1e-3, 80.0, device="cpu"),
+            "vp": S.get_sigmas_vp(n, device="cpu"),
+            "cosine_beta": S.cosine_beta_schedule(n, device="cpu"),
+            "ve": S.get_sigmas_ve(n, 1e-3, 80.0, device="cpu"),
+            "iddpm": S.get_iddpm_sigmas(n, 1e-3, 80.0, device="cpu"),
+        }
+        for name, v in got.items():
+            want = g[f"{name}_{n}"]
+            assert v.dtype == torch.float32 and tuple(v.shape) == want.shape, name
+            np.testing.assert_allclose(v.numpy(), want, rtol=1e-6, atol=0, err_msg=f"{name}_{n}")
+
+
+class _OracleDenoiser:
+    """GCDenoiser stand-in on the CPU: the fp32 numpy oracle (pinned to the reference by the goldens)."""
+
+    def __init__(self, sd, cfg):
+        self.sd, self.cfg = sd, cfg
+
+    def __call__(self, state, x, goal, sigma, **kw):
+        d = O.denoiser_forward(self.sd, self.cfg, state["state_images"].numpy(), x.numpy(), goal.numpy(),
+                               sigma.numpy().astype(np.float32), "fp32")
+        return torch.from_numpy(d)
+
+
+class NoiseTape:
+    """Replays the reference run's torch.randn_like draws (one tensor per call, in call order)."""
+
+    def __init__(self, noise, device="cpu"):
+        self.noise, self.i, self.device = noise, 0, device
+
+    def __call__(self, like, *a, **k):
+        z = torch.from_numpy(self.noise[self.i]).to(device=like.device, dtype=like.dtype)
+        self.i += 1
+        return z
+
+
+SAMPLER_CALLS = {  # golden key -> (function name, kwargs) exactly as MoDEAgent.sample_loop calls them (mode_agent.py:796-838)
+    "lms": ("sample_lms", {}), "heun": ("sample_heun", dict(s_churn=0, s_tmin=0)),
+    "heun_churn": ("sample_heun", dict(s_churn=4.0, s_tmin=0)), "euler": ("sample_euler", {}),
+    "euler_churn": ("sample_euler", dict(s_churn=4.0)), "ancestral": ("sample_dpm_2_ancestral", {}),
+    "euler_ancestral": ("sample_euler_ancestral", {}), "dpm": ("sample_dpm_2", {}),
+    "dpmpp_2s_ancestral": ("sample_dpmpp_2s_ancestral", {}), "dpmpp_2m": ("sample_dpmpp_2m", {}),
+    "ddim": ("sample_ddim", {}), "dpmpp_2s": ("sample_dpmpp_2s", {}), "dpmpp_2_with_lms": ("sample_dpmpp_2_with_lms", {}),
+}
+
+
+@pytest.mark.parametrize("key", list(SAMPLER_CALLS))
+def test_sampler_host_loops_match_reference_samplers(key, monkeypatch):
+    g = np.load(GOLD / "samplers_tiny_d256_l3_e4.npz")
+    sd = O.make_weights(TINY, seed=1234, router_gain=30.0)
+    assert _digest(sd) == str(g["weights_sha256"])
+    state, goal, x0 = O.make_inputs(TINY, 5, seed=4321)
+    model = _OracleDenoiser(sd, TINY)
+    tape = NoiseTape(g["noise_tape"])
+    monkeypatch.setattr(torch, "randn_like", tape)
+    name, kw = SAMPLER_CALLS[key]
+    out = getattr(S, name)(model, {"state_images": torch.from_numpy(state)}, torch.from_numpy(x0), torch.from_numpy(goal),
+                           torch.from_numpy(g["sigmas"]), disable=True, **kw)
+    assert tape.i == int(g[key + "_draws"]), "the loop must consume the caller's RNG exactly like the reference"
+    assert rel_l2(out.numpy(), g[key]) < 5e-5, rel_l2(out.numpy(), g[key])
