@@ -159,6 +159,8 @@ def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=Non
     """Algorithm 2 of Karras et al. without the 2nd-order correction (reference gc_sampling.py:164-211). Without churn,
     callback, scaler or extra_args the whole loop is one fused engine call."""
     if s_churn == 0 and _fusable(model, "sample_fused", sigmas, scaler, extra_args, callback):
+        for _ in range(len(sigmas) - 1):  # the reference draws eps every step even when gamma = 0 (gc_sampling.py:196):
+            torch.randn_like(action)      # leave the caller's RNG where the reference would
         return model.sample_fused("euler", state, action, goal, sigmas)
     lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
     for i in range(len(sigmas) - 1):

@@ -77,7 +77,7 @@ def test_headline_configuration_against_the_reference(gain):
     assert ties_f + ties_s == 0  # the committed goldens have no decision closer than 1e-5
     assert e_F <= gap("forward_F") and e_D <= gap("denoise_D") and e_S <= gap("ddim_actions")
     # absolute bounds (observed: F/D 3e-3..5e-3 at 12 layers = the bf16-operand noise floor; sample ~2e-3)
-    assert e_F < 8e-3 and e_D < 8e-3 and e_S < 4e-3
+    assert e_F < 6.5e-3 and e_D < 4.5e-3 and e_S < 3.2e-3  # observed x 1.5 (profiles/r02_reference_parity.log)
 
     # the per-step denoiser outputs along the reference's OWN trajectory (no error carried from step to step)
     worst = 0.0
@@ -88,7 +88,7 @@ def test_headline_configuration_against_the_reference(gain):
             worst = max(worst, rel_l2(d_i, g["ddim_denoised"][i]))
         x = (ratio * x - em1 * g["ddim_denoised"][i]).astype(np.float32)
     print(f"rg{gain} denoiser on the reference trajectory (steps 0/4/9): worst {worst:.3e}")
-    assert worst < 8e-3
+    assert worst < 5.5e-3
 
 
 def _modules(cfg, sd, max_batch=8):
@@ -124,7 +124,7 @@ def test_every_sampler_against_the_reference_sampler(key, monkeypatch):
         assert tape.i == int(g[key + "_draws"]), (how, tape.i)
     e_d, e_h = rel_l2(outs["dispatch"], g[key]), rel_l2(outs["host_loop"], g[key])
     print(f"\n{key}: engine vs reference sampler: dispatch {e_d:.3e}, host loop {e_h:.3e}")
-    # bf16 tensor-core operands vs the reference's fp32 run of a 3-layer model: the existing DDIM / Euler goldens sit at
-    # 3e-3..6e-3; second-order and ancestral samplers evaluate the network up to twice per step
-    assert e_d < 1.2e-2 and e_h < 1.2e-2
+    # bf16 tensor-core operands vs the reference's fp32 run of a 3-layer model; observed 1.0e-3..1.7e-3
+    # (profiles/r02_reference_parity.log), bound = observed x 1.5
+    assert e_d < 2.6e-3 and e_h < 2.6e-3
     assert rel_l2(outs["dispatch"], outs["host_loop"]) < 2e-3
