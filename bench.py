@@ -88,62 +88,224 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_leg(cfg, sample_B=B_PER_GPU, repeats=4, sd=None):
-    """Times the reference's CPU path on the host cores on a bounded sample of the workload: `repeats` full-network
-    denoiser calls at B=sample_B, scaled linearly to B=256. The reference's own modules need /root/reference, which does
-    not exist on the GPU box, so the timed code is oracle/mode_ref_torch.py: an op-for-op torch-CPU restatement (same
-    ATen kernels, same structure: router MLP on all B*T rows, embeddings recomputed per call, per-expert boolean
-    gather/scatter), pinned to the reference by the goldens (tests/test_oracle.py). `sd`: torch state_dict to reuse."""
-    import torch
+REF_SAMPLE_B = 64  # the CPU arms time a bounded sample of the workload: a quarter of the 256-trajectory batch
 
-    import synthetic_workload as O
-    from oracle import mode_ref_torch as RT  # the only use of oracle/ in this file: the CPU arm being timed
 
-    torch.set_num_threads(host_cores())
-    if sd is None:
-        sd = RT.to_torch(O.make_weights_fast(cfg, seed=1234))
-    state, goal, x0 = O.make_inputs(cfg, sample_B, seed=4321)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
-    S, G = t(state), t(goal)
-    sig = torch.full((sample_B,), 0.5)
-    x = t((x0 / np.float32(SIGMA_MAX)).astype(np.float32))
-    with torch.no_grad():
-        RT.denoiser_forward(sd, cfg, S[:2], x[:2], G[:2], sig[:2])  # warm the thread pool / page in the weights
+def engine_config_record(B, world, trim):
+    """`config` of the JSON line; both arms print the same keys and values for the same command line."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "denoising_steps_per_bench_step": N_SAMPLING_STEPS,
+            "parallelism": f"dp{world} (independent trajectory shards, no collective)",
+            "l2": "no explicit flush: each denoising step streams 705 MB of bf16 weights (> 126 MB L2)",
+            "weights": "random init, reference shapes (686 M params)",
+            "dead_rows": ("last block's experts run on the 10 action rows of each trajectory only (the other 4 "
+                          "never reach the head); step_roofline counts the reference's full FLOPs") if trim
+            else "none: every token row of every block is evaluated"}
+
+
+class CpuArm:
+    """The reference's CPU path for the sampling loop on the host cores, fp32, all cores.
+
+    kind "reference": the reference's OWN modules (MoDeDiT, GCDenoiser, sample_ddim), unmodified, when a checkout is
+    reachable (MODE_REF, /root/reference, baseline/_ref/mode) — the case in the build container. kind "port": on the GPU
+    box no checkout exists (a Python reference cannot travel; `pip install --target baseline/_ref` of its setup.py yields an
+    empty distribution because mode/ has no __init__.py), so the timed code is oracle/mode_ref_torch.py, an
+    op-for-op torch-CPU restatement with the reference's execution structure, pinned to it by the goldens."""
+
+    def __init__(self, cfg):
+        import torch
+
+        import synthetic_workload as O
+
+        self.torch, self.O, self.cfg = torch, O, cfg
+        torch.set_num_threads(host_cores())
+        torch.set_grad_enabled(False)
+        sd_np = O.make_weights_fast(cfg, seed=1234)
+        self.kind, self.impl = "port", "torch-CPU restatement of the reference modules, op for op (oracle/mode_ref_torch.py), fp32"
+        self.model = None
+        for root in (os.environ.get("MODE_REF"), "/root/reference", str(ROOT / "baseline" / "_ref")):
+            if root and os.path.isfile(os.path.join(root, "mode", "models", "networks", "modedit.py")):
+                try:
+                    self._load_reference(root, sd_np)
+                    self.kind, self.impl = "reference", f"the reference's own MoDeDiT / GCDenoiser / sample_ddim from {root}, fp32"
+                    break
+                except Exception as exc:  # an unusable checkout: fall through to the port, say why
+                    print(f"bench: reference at {root} not usable ({exc!r}); timing the port", file=sys.stderr)
+        if self.model is None:
+            from oracle import mode_ref_torch as RT  # the only use of oracle/ in this file: the CPU arm being timed
+
+            self.RT, self.sd = RT, RT.to_torch(sd_np)
+
+    def _load_reference(self, root, sd_np):
+        import types
+
+        torch = self.torch
+        for n in ["hydra", "hydra.utils", "torchsde", "torchdiffeq", "matplotlib", "matplotlib.pyplot"]:
+            if n not in sys.modules:
+                try:
+                    __import__(n)
+                except Exception:
+                    sys.modules[n] = types.ModuleType(n)  # imported at module top by the reference, unused on this path
+        if not hasattr(sys.modules["hydra"], "utils"):
+            sys.modules["hydra"].utils = sys.modules["hydra.utils"]
+        if not hasattr(sys.modules["hydra.utils"], "instantiate"):
+            sys.modules["hydra.utils"].instantiate = lambda cfg, *a, **k: cfg
+        if not hasattr(sys.modules["torchdiffeq"], "odeint"):
+            sys.modules["torchdiffeq"].odeint = None
+        if not hasattr(sys.modules["matplotlib"], "pyplot"):
+            sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        sys.path.insert(0, root)
+        from mode.models.edm_diffusion.gc_sampling import sample_ddim
+        from mode.models.edm_diffusion.score_wrappers import GCDenoiser
+        from mode.models.networks.modedit import MoDeDiT
+
+        c = self.cfg
+        inner = MoDeDiT(obs_dim=c.obs_dim, goal_dim=c.goal_dim, device="cpu", goal_conditioned=True, action_dim=c.action_dim,
+                        embed_dim=c.embed_dim, embed_pdrob=0, attn_pdrop=0.3, n_layers=c.n_layers, n_heads=c.n_heads,
+                        goal_seq_len=1, obs_seq_len=1, action_seq_len=c.action_seq_len, state_dim=7,
+                        num_experts=c.num_experts, top_k=c.top_k, init_style="olmoe")
+        inner.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd_np.items()})
+        self.model, self.ref_sample_ddim = GCDenoiser(inner, sigma_data=c.sigma_data).eval(), sample_ddim
+
+    def inputs(self, B):
+        torch = self.torch
+        state, goal, x0 = self.O.make_inputs(self.cfg, B, seed=4321)
+        sig = torch.from_numpy(self.O.get_sigmas_exponential(N_SAMPLING_STEPS, SIGMA_MIN, SIGMA_MAX))
+        return torch.from_numpy(state), torch.from_numpy(goal), torch.from_numpy(x0), sig
+
+    def sample(self, S, G, X, sig):
+        """One full 10-step DDIM sample (10 network evaluations) of the given trajectories; returns seconds."""
         t0 = time.perf_counter()
-        for _ in range(repeats):
-            RT.denoiser_forward(sd, cfg, S, x, G, sig)
-        dt = (time.perf_counter() - t0) / repeats
-    steps_per_s = (sample_B / B_PER_GPU) / dt
-    return {"value": steps_per_s, "unit": UNIT, "cores": host_cores(), "kind": "port",
-            "implementation": "torch-CPU restatement of the reference modules, op for op (oracle/mode_ref_torch.py), fp32",
-            "sample": f"{repeats} denoiser call(s) at B={sample_B} ({dt:.2f} s each)" +
-                      ("" if sample_B == B_PER_GPU else f", scaled linearly to B={B_PER_GPU}")}
+        if self.model is not None:
+            out = self.ref_sample_ddim(self.model, {"state_images": S}, X, G, sig, disable=True)
+        else:
+            out = self.RT.sample_ddim(self.sd, self.cfg, S, X, G, sig)
+        dt = time.perf_counter() - t0
+        assert bool(self.torch.isfinite(out).all())
+        return dt
+
+    def record(self, value, seconds, n):
+        return {"value": value, "unit": UNIT, "cores": host_cores(), "kind": self.kind, "implementation": self.impl,
+                "sample": f"{n} full {N_SAMPLING_STEPS}-step DDIM sample(s) of {REF_SAMPLE_B} of the {B_PER_GPU} trajectories "
+                          f"({seconds:.2f} s each, {N_SAMPLING_STEPS} network evaluations), scaled by {REF_SAMPLE_B}/{B_PER_GPU} to "
+                          f"full-batch denoising steps (CPU time is linear in the batch at these sizes, SURVEY.md §8d)"}
+
+
+def cpu_reference_leg(cfg, repeats=3):
+    """cpu_baseline of the engine arm's N=1 line: a bounded sample (about 10-30 s) of the same workload on the host cores."""
+    arm = CpuArm(cfg)
+    S, G, X, sig = arm.inputs(REF_SAMPLE_B)
+    arm.sample(S[:2], G[:2], X[:2], sig)  # warm the thread pool / page in the weights
+    dts = [arm.sample(S, G, X, sig) for _ in range(repeats)]
+    dt = float(np.mean(dts))
+    return arm.record((REF_SAMPLE_B / B_PER_GPU) * N_SAMPLING_STEPS / dt, dt, repeats)
 
 
 def run_reference(args, rank):
+    """`--impl reference`: the reference arm. A bench step = one full 10-step DDIM sample, as in the engine arm, over a
+    bounded sample of the batch (REF_SAMPLE_B of the 256 trajectories); `ms_per_step` is the measured time of such a step
+    and `value` the resulting full-batch denoising-steps/s."""
     import synthetic_workload as O
 
     if rank != 0:
         return
     cfg = O.ModeConfig()
-    vals = []
-    base = None
-    from oracle import mode_ref_torch as RT
-
-    sd = RT.to_torch(O.make_weights_fast(cfg, seed=1234))  # once: every step times the same network
+    arm = CpuArm(cfg)
+    S, G, X, sig = arm.inputs(REF_SAMPLE_B)
+    dts = []
     for i in range(args.warmup + args.steps):
-        base = cpu_reference_leg(cfg, sample_B=B_PER_GPU, repeats=1, sd=sd)  # one full-batch network evaluation per step
+        dt = arm.sample(S, G, X, sig)
         if i >= args.warmup:
-            vals.append(base["value"])
-    v = float(np.mean(vals))
-    base["value"] = v
+            dts.append(dt)
+    dt = float(np.mean(dts))
+    v = (REF_SAMPLE_B / B_PER_GPU) * N_SAMPLING_STEPS / dt
+    config = engine_config_record(B_PER_GPU, args.gpus, False)
+    config["reference_sample"] = (f"each timed step samples {REF_SAMPLE_B} of the {B_PER_GPU} trajectories on the host cores; "
+                                  f"value = ({REF_SAMPLE_B}/{B_PER_GPU}) * {N_SAMPLING_STEPS} / step time")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * N_SAMPLING_STEPS / v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference path on host cores (torch-CPU restatement of the reference's PyTorch modules, op for op)"},
-            "cpu_baseline": base,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": arm.record(v, dt, args.steps),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def train_leg(world, rank, steps, warmup, batch=128):
+    """BASELINE.json configs[3] — the one path with a collective (reference mode/training_calvin.py:92-103, DDP): training
+    step of the full MoDE (12 L, d=1024, 4 experts), noised-action MSE, per-GPU batch 128 (global 1024 on 8 GPUs), bf16
+    tensor-core operands, fused forward+backward, NCCL all-reduce of the flat fp32 gradient buffer pipelined per layer with
+    the fused AdamW (+ weight re-pack). Also times the same step WITHOUT the exchange on every rank: the difference is
+    the communication that stays exposed. Returns the `train` sub-record (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+
+    import synthetic_workload as O
+    from mode_diffusion_policy_b200 import parallel
+    from mode_diffusion_policy_b200.modedit import MoDeDiT
+    from mode_diffusion_policy_b200.optim import EngineAdamW
+    from mode_diffusion_policy_b200.score_wrappers import GCDenoiser
+
+    cfg = O.ModeConfig()
+    B = batch
+    inner = MoDeDiT(obs_dim=cfg.obs_dim, goal_dim=cfg.goal_dim, device="cuda", goal_conditioned=True, action_dim=7,
+                    embed_dim=cfg.embed_dim, embed_pdrob=0, attn_pdrop=0.3, n_layers=cfg.n_layers, n_heads=cfg.n_heads,
+                    goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7, mlp_pdrop=0.1, goal_drop=0.1,
+                    num_experts=cfg.num_experts, top_k=cfg.top_k, use_argmax=False, max_batch=B)  # conf/model/mode_agent.yaml recipe
+    inner.load_state_dict({k: torch.from_numpy(v) for k, v in O.make_weights_fast(cfg, seed=1234).items()})
+    model = GCDenoiser(inner, sigma_data=0.5).cuda().train()
+    opt = EngineAdamW(inner, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321 + rank)
+    rng = np.random.default_rng(7 + rank)
+    S, G = torch.from_numpy(state).cuda(), torch.from_numpy(goal).cuda()
+    A_ = torch.from_numpy((x0 / np.float32(SIGMA_MAX)).astype(np.float32)).cuda()
+    noise = torch.from_numpy(rng.standard_normal(x0.shape).astype(np.float32)).cuda()
+    sigma = torch.from_numpy(np.exp(rng.uniform(np.log(SIGMA_MIN), np.log(SIGMA_MAX), B)).astype(np.float32)).cuda()
+    names = [n for n, _ in inner.named_parameters() if n != "gripper_embed.weight"]
+    reducer = [None]
+
+    def step(exchange):
+        loss, _ = model.loss({"state_images": S}, A_, G, noise, sigma)
+        loss.backward()
+        if exchange and world > 1:
+            if reducer[0] is None:
+                reducer[0] = parallel.GradAllReduce(inner._engine, names, cfg.n_layers)
+            opt.step_overlapped(reducer[0])
+        else:
+            opt.step()
+        return loss
+
+    def timed(exchange):
+        for _ in range(warmup):
+            step(exchange)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step(exchange)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        (ms,) = parallel.max_over_ranks([e0.elapsed_time(e1)], "cuda")
+        return ms / steps, float(loss)
+
+    local_ms, _ = timed(False)                       # forward + backward + optimizer, no exchange (what one GPU does)
+    full_ms, loss = timed(True) if world > 1 else (local_ms, _)
+    inner._engine.close()
+    if rank != 0:
+        return None
+    flat_bytes = 4 * sum(p.numel() for n, p in inner.named_parameters() if n != "gripper_embed.weight")
+    return {"metric": "training-samples/sec", "value": world * B / (full_ms * 1e-3), "unit": "samples/s",
+            "ms_per_step": full_ms, "ms_per_step_without_exchange": local_ms, "exposed_exchange_ms": full_ms - local_ms,
+            "steps": steps, "warmup": warmup, "global_batch": world * B, "batch_per_gpu": B, "scaling": "weak",
+            "loss": loss, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[3]: MoDE 12L d=1024 4 experts top-2, noised-action MSE, fwd + bwd + "
+                                   "gradient exchange + fused AdamW + weight re-pack, reference regularisation (attention "
+                                   "dropout 0.3, expert dropout 0.1, goal masking 0.1, per-token multinomial routing)",
+                       "collective": (f"NCCL all_reduce(AVG) of the flat fp32 gradient buffer ({flat_bytes / 1e9:.2f} GB), per-layer "
+                                      "coalesced buckets pipelined with per-layer fused AdamW launches") if world > 1
+                       else "none (one GPU)"}}
 
 
 def main():
@@ -154,6 +316,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (default: the headline 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[3] training sub-record")
+    ap.add_argument("--train-steps", type=int, default=8)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, what the driver runs): --batch trajectories per GPU; strong: --batch is the GLOBAL "
                          "batch, split evenly over the ranks (SURVEY.md §8d asks for both, labelled)")
@@ -177,7 +341,10 @@ def main():
         raise SystemExit("bench.py needs a B200: the MoDE engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL's CTAs must win SMs from the persistent GEMM grids of the training leg: high-priority communication stream
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     cfg = O.ModeConfig()
     B = args.batch
     if args.scaling == "strong":
@@ -267,6 +434,11 @@ def main():
     value = units_per_step * args.steps * N_SAMPLING_STEPS / (ms * 1e-3)
     e2e_value = units_per_step * args.steps * N_SAMPLING_STEPS / (e2e_ms * 1e-3)
 
+    # ---------------- configs[3]: the training step (the one path with a collective), all ranks take part
+    train = None
+    if not args.no_train and args.scaling == "weak" and B == B_PER_GPU:
+        train = train_leg(world, rank, args.train_steps, 3)
+
     if rank == 0:
         # ---------------- roofline of the dominant kernel: grouped expert up-projection GEMM (tcgen05, SwiGLU epilogue)
         peaks = {}
@@ -314,13 +486,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "denoising_steps_per_bench_step": N_SAMPLING_STEPS,
-                       "parallelism": f"dp{world} (independent trajectory shards, no collective)",
-                       "l2": "no explicit flush: each denoising step streams 705 MB of bf16 weights (> 126 MB L2)",
-                       "weights": "random init, reference shapes (686 M params)",
-                       "dead_rows": ("last block's experts run on the 10 action rows of each trajectory only (the other 4 "
-                                     "never reach the head); step_roofline counts the reference's full FLOPs") if trim
-                       else "none: every token row of every block is evaluated"},
+            "config": engine_config_record(B, world, trim),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(hs.numel() * 4 + hg.numel() * 4 + hx.numel() * 4),
                     "d2h_bytes_per_step": int(hx.numel() * 4)},
@@ -340,6 +506,8 @@ def main():
                 "value": units_per_step * args.steps * N_SAMPLING_STEPS / (trimmed_ms * 1e-3), "unit": UNIT,
                 "note": "engine default: the last block's experts skip the 4 token rows per trajectory that cannot reach the "
                         "output head; results bit-identical to the headline run (asserted); NOT used for `value`/`e2e`"}
+        if train is not None:
+            line["train"] = train
         if not args.no_cpu_baseline and world == 1:  # the CPU leg belongs to the N=1 line only
             line["cpu_baseline"] = cpu_reference_leg(cfg)
         print(json.dumps(line), flush=True)

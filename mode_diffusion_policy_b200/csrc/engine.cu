@@ -237,6 +237,7 @@ struct mode_engine {
   CUtensorMap to_qkv, to_x, to_state, to_goal;     // dense outputs: extent = exact rows of the current batch
 
   cudaStream_t cap_stream = nullptr;
+  std::map<std::pair<int, int>, CUtensorMap> w_maps;  // (weight matrix id, tile width) -> weight map with a width/2-row box
   std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
   std::map<std::pair<int, int>, int64_t> graph_launches;
   int64_t launch_count = 0;
@@ -841,6 +842,11 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.m_tiles = tiles;
   p.num_m_tiles = ntiles;
   p.n_blocks = N / GEMM_BLOCK_N;
+  p.bn = GEMM_BLOCK_N;
+  p.n_total = N;
+  p.out_ptr = nullptr;
+  p.ldo = 0;
+  p.out_rows = 0;
   p.k_blocks = Kdim / GEMM_BLOCK_K;
   p.bias = bias;
   p.w_row_off = 0;
@@ -854,6 +860,50 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.drop_half_F = 0;
   return p;
 }
+// Tile width of a CTA-pair GEMM with `n_m` M-tiles and N output columns: the multiple of 16 whose column tiling fills
+// whole waves of the `pairs` CTA pairs best. Cost model: waves x (width + 32); the 32 stands for the per-tile fixed
+// cost (pipeline ramp, accumulator hand-over). Ties go to the wider tile (fewer re-reads of the A rows).
+// At B = 256 (14 M-tiles of 256 rows, 74 pairs): QKV N = 3072 -> 208 (15 x 14 = 210 tiles = 3 waves of 0.81 instead of
+// 168 = 3 waves of 1.0), c_proj N = 1024 -> 208 (70 tiles, one wave), expert down (28 M-tiles) -> 208 (140 tiles = 2
+// waves of 0.81 instead of 112 = 2 waves of 1.0).
+static int choose_bn(int n_m, int N, int pairs) {
+  static const int forced = getenv("MODE_GEMM_BN") ? atoi(getenv("MODE_GEMM_BN")) : 0;
+  if (forced >= 64 && forced <= 256 && forced % 16 == 0) return forced;
+  int best = GEMM_BLOCK_N;
+  long best_cost = -1;
+  for (int bn = GEMM_BLOCK_N; bn >= 128; bn -= 16) {
+    const long tiles = (long)n_m * ((N + bn - 1) / bn);
+    const long cost = ((tiles + pairs - 1) / pairs) * (bn + 32);
+    if (best_cost < 0 || cost < best_cost) {
+      best = bn;
+      best_cost = cost;
+    }
+  }
+  return best;
+}
+
+// Switches a pair-kernel GEMM to `bn`-wide tiles: weight map with a bn/2-row box (cached per weight matrix and width),
+// raw output pointer for the columns the TMA store chunks do not cover.
+static int narrow_gemm(mode_engine* e, GemmParams& p, int bn, int which_w, const void* w_base, uint64_t w_rows, int Kdim,
+                       void* out_ptr, int ldo, int out_rows) {
+  if (!e->pair || bn == GEMM_BLOCK_N) return MODE_OK;
+  const auto key = std::make_pair(which_w, bn);
+  auto it = e->w_maps.find(key);
+  if (it == e->w_maps.end()) {
+    CUtensorMap m;
+    RET_IF(make_tmap(&m, w_base, w_rows, (uint64_t)Kdim, (uint32_t)(bn / 2)));
+    it = e->w_maps.emplace(key, m).first;
+  }
+  p.tmap_w = it->second;
+  p.bn = bn;
+  p.n_blocks = (p.n_total + bn - 1) / bn;
+  p.out_ptr = out_ptr;
+  p.ldo = ldo;
+  p.out_rows = out_rows;
+  p.sk_enable = 0;  // stream-K partials are laid out for 256-wide tiles
+  return MODE_OK;
+}
+
 // Stream-K over the last partial wave (QKV, expert up/down). Correct (tests/test_kernels_gpu.py) but OFF by default:
 // measured on B200 the fp32 partial round trip costs as much as the removed tail (profiles/r01_gemm_variants.log), and
 // splitting K makes the accumulation order depend on the batch size, which would break the bit-exact batch-split
@@ -984,6 +1034,10 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   GemmParams p = gemm_params(io.tm_hA, e->tm_wqkv, io.to_qkv, e->dense_tiles, e->dense_counts, 3 * d, d, e->b_qkv);
   p.w_row_off = l * 3 * d;
   enable_stream_k(e, p);
+  const int pairs = e->num_sms >> 1;
+  const int n_m_dense = (M + e->tile_m - 1) / e->tile_m;
+  if (!e->train_forward)
+    RET_IF(narrow_gemm(e, p, choose_bn(n_m_dense, 3 * d, pairs), 0, e->w_qkv, (uint64_t)e->L * 3 * d, d, io.qkv, 3 * d, M));
   // rollout-sized batch: every group has <= 16 rows -> weight-streaming kernels (gemm_small.cuh)
   const bool small = e->small_m && !io.z && !e->train_forward && M <= SMALL_M_MAX_ROWS && d % 256 == 0;
   const int small_groups = e->E < B * e->K ? e->E : B * e->K;  // upper bound on routed groups
@@ -1004,6 +1058,8 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   }
   p = gemm_params(io.tm_attn, e->tm_wproj, io.to_x1, e->dense_tiles, e->dense_counts, d, d, nullptr);  // x1 += acc
   p.w_row_off = l * d;
+  if (!e->train_forward)
+    RET_IF(narrow_gemm(e, p, choose_bn(n_m_dense, d, pairs), 1, e->w_proj, (uint64_t)e->L * d, d, io.x1, d, M));
   {
     ProfScope ps(e, st, PC_PROJ);
     if (small)
@@ -1060,6 +1116,12 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
       }
     }
     enable_stream_k(e, pd);
+    if (!e->train_forward) {
+      // routed rows of this block (the last block only keeps its action rows), before group padding
+      const int routed = e->K * rv.units * (rv.rt - t_skip);
+      RET_IF(narrow_gemm(e, pd, choose_bn((routed + e->tile_m - 1) / e->tile_m, d, pairs), 2, e->w_down,
+                         (uint64_t)e->L * e->E * d, e->F, io.y, d, e->perm_rows));
+    }
     {
       ProfScope ps(e, st, PC_DOWN);
       if (small)
@@ -1386,7 +1448,11 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
   if (!a_dev || !w_dev || !out_dev) return fail(MODE_ERR_INVALID, "null argument");
   const bool pair = (epilogue & 0x100) != 0;      // bit 8 selects the CTA-pair kernel
   const bool stream_k = (epilogue & 0x200) != 0;  // bit 9 enables stream-K on the last partial wave (pair kernel)
+  const bool skip_b_debug = (epilogue & 0x400) != 0;  // bit 10: measurement aid, see gemm.cuh (garbage results)
+  const int bn = ((epilogue >> 16) & 0xff) ? ((epilogue >> 16) & 0xff) * 16 : GEMM_BLOCK_N;  // bits 16-23: tile width / 16
   epilogue &= 0xff;
+  if (bn != GEMM_BLOCK_N && (!pair || stream_k || bn < 64 || bn > 256 || epilogue == EPI_SWIGLU_BF16 || epilogue == EPI_SWIGLU_SAVE))
+    return fail(MODE_ERR_INVALID, "tile width %d needs the plain CTA-pair kernel and a non-SwiGLU epilogue", bn);
   const int tm = pair ? 256 : 128;
   if (M < 1 || N % 256 || Kdim % 64 || N < 256 || Kdim < 64) return fail(MODE_ERR_INVALID, "need N %% 256 == 0 and K %% 64 == 0");
   RET_IF(set_kernel_attrs());
@@ -1407,7 +1473,7 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
   CUtensorMap ta, tw;
   // The caller allocates A with round_up(M, 256) rows so the TMA box never exceeds the tensor extent.
   RET_IF(make_tmap(&ta, a_dev, round_up(M, 256), Kdim, 128));
-  RET_IF(make_tmap(&tw, w_dev, N, Kdim, pair ? 128 : 256));
+  RET_IF(make_tmap(&tw, w_dev, N, Kdim, pair ? bn / 2 : 256));
   const int n_out = (epilogue == EPI_SWIGLU_BF16) ? N / 2 : N;
   const int out_bytes = (epilogue == EPI_RESID_F32 || epilogue == EPI_PLAIN_F32) ? 4 : 2;
   CUtensorMap tout;
@@ -1417,6 +1483,13 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
     CU_OK(cudaMemcpyAsync(out_dev, resid_dev, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   GemmParams p = gemm_params(ta, tw, tout, d_tiles, d_n, N, Kdim, bias_dev);
+  if (bn != GEMM_BLOCK_N) {
+    p.bn = bn;
+    p.n_blocks = (N + bn - 1) / bn;
+    p.out_ptr = out_dev;
+    p.ldo = N;
+    p.out_rows = M;
+  }
   static float4* dbg_parts = nullptr;
   static int* dbg_flags = nullptr;
   if (pair && stream_k) {
@@ -1428,6 +1501,7 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
     p.sk_partials = dbg_parts;
     p.sk_flags = dbg_flags;
   }
+  if (pair && skip_b_debug) p.sk_enable |= 2;
   int rc = launch_gemm(epilogue, pair, sms, st, p);
   // MODE_GEMM_BENCH_REPS=n: time n further back-to-back launches with CUDA events and print the average
   if (rc == MODE_OK && getenv("MODE_GEMM_BENCH_REPS")) {
@@ -1442,8 +1516,8 @@ extern "C" int mode_debug_gemm(const void* a_dev, const void* w_dev, const float
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     const double flops = 2.0 * M * (double)N * Kdim;
-    printf("mode_debug_gemm%s%s M=%d N=%d K=%d epi=%d: %.3f us/launch, %.1f TFLOP/s\n", pair ? "[pair]" : "", (pair && stream_k) ? "[sk]" : "", M, N, Kdim, epilogue,
-           1e3 * ms / reps, flops * reps / (ms * 1e-3) / 1e12);
+    printf("mode_debug_gemm%s%s M=%d N=%d K=%d epi=%d bn=%d: %.3f us/launch, %.1f TFLOP/s\n", pair ? "[pair]" : "", (pair && stream_k) ? "[sk]" : "", M, N, Kdim, epilogue,
+           bn, 1e3 * ms / reps, flops * reps / (ms * 1e-3) / 1e12);
     fflush(stdout);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

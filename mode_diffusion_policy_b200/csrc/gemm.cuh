@@ -73,6 +73,22 @@ struct alignas(64) GemmParams {
   int drop_rows_per_expert;    // weight rows per expert (8d): expert = (w_row_base / this) % drop_E
   int drop_E;
   int drop_half_F;             // F / 2 = 2d
+  // Tile width of the CTA-pair kernel (multiple of 16, <= 256; 256 everywhere else). The host picks the width that
+  // fills whole waves of the 74 CTA pairs (e.g. 208 for N = 1024 / 3072 at B = 256: 5 resp. 15 column tiles instead of
+  // 4 / 12), which changes which tile an output column belongs to but not the order in which its K terms are summed.
+  // n_blocks = ceil(n_total / bn); tmap_w has a bn/2-row box; columns [bn/64*64, bn) of a tile (bf16 outputs; bn/32*32
+  // for fp32) are stored straight from registers through out_ptr, everything else through tmap_out as before.
+  int bn;
+  int n_total;                 // N of the whole GEMM (output columns / weight rows per problem)
+  void* out_ptr;               // raw output base, row stride ldo elements, rows >= out_rows are never written
+  int ldo, out_rows;
+};
+// Column geometry handed to the epilogue (defaults = the fixed 256-wide tiles of the other kernels).
+struct EpiGeom {
+  int bn = GEMM_BLOCK_N;
+  int n_total = 0x7fffffff;
+  void* out = nullptr;
+  int ldo = 0, out_rows = 0;
 };
 
 // Work decomposition of the CTA-pair kernel. Tiles of full waves are data-parallel (tile = worker + i * P). The last,
@@ -197,7 +213,8 @@ template <int EPI, bool DROP = false>
 __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, uint32_t taddr, uint32_t stage_smem, int lane,
                                                    int out_row0, const float* sbias, int nb, uint32_t& n_stores,
                                                    const SkParts sk = SkParts{nullptr, 0, 0},
-                                                   const EpiDrop dr = EpiDrop{0, 0, 0, 1.0f}) {
+                                                   const EpiDrop dr = EpiDrop{0, 0, 0, 1.0f},
+                                                   const EpiGeom g = EpiGeom{}) {
   const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
   const uint32_t sw = static_cast<uint32_t>(lane & 7);
   auto chunk_addr = [&](uint32_t buf, uint32_t j) { return buf + row_off + ((j ^ sw) << 4); };
@@ -260,8 +277,11 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
       end_chunk(buf, nb * 128 + c * 64);
     }
   } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_PLAIN_BF16) {
+    const int col0 = nb * g.bn;
+    const int nfull = g.bn >> 6;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {  // 64 output columns per store
+    for (int c = 0; c < nfull; ++c) {  // 64 output columns per store
+      if (col0 + c * 64 >= g.n_total) break;  // tile overhangs the matrix (its weight rows were out-of-range filler)
       const uint32_t buf = begin_chunk();
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -286,17 +306,63 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
           st_shared_v4(chunk_addr(buf, hh * 4 + j), pk[0], pk[1], pk[2], pk[3]);
         }
       }
-      end_chunk(buf, nb * GEMM_BLOCK_N + c * 64);
+      end_chunk(buf, col0 + c * 64);
+    }
+    // columns past the last full 64-column chunk (tile widths like 208 = 3 x 64 + 16): 16 at a time, one 32-byte
+    // sector per row, stored straight from registers
+#pragma unroll 1
+    for (int t = nfull * 64; t < g.bn; t += 16) {
+      if (col0 + t >= g.n_total) break;
+      uint32_t r[16];
+      tmem_ld_32x16(taddr + t, r);
+      tmem_ld_wait();
+      uint32_t pk[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float v0 = __uint_as_float(r[2 * u]), v1 = __uint_as_float(r[2 * u + 1]);
+        if constexpr (EPI == EPI_BIAS_BF16) {
+          v0 += sbias[t + 2 * u];
+          v1 += sbias[t + 2 * u + 1];
+        }
+        pk[u] = pack_bf16x2(v0, v1);
+      }
+      const int row = out_row0 + lane;
+      if (row < g.out_rows) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<size_t>(row) * g.ldo + col0 + t);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
     }
   } else {  // fp32 outputs: 32 columns (128 B) per store
+    const int col0 = nb * g.bn;
+    const int nfull = g.bn >> 5;
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < nfull; ++c) {
+      if (col0 + c * 32 >= g.n_total) break;
       const uint32_t buf = begin_chunk();
       uint32_t r[32];
       load_acc32(taddr + c * 32, r, sk, c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) st_shared_v4(chunk_addr(buf, j), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-      end_chunk(buf, nb * GEMM_BLOCK_N + c * 32);
+      end_chunk(buf, col0 + c * 32);
+    }
+    if ((g.bn & 16) && col0 + nfull * 32 < g.n_total) {  // the last 16 columns of a tile whose width is 16 mod 32
+      const int t = nfull * 32;
+      uint32_t r[16];
+      tmem_ld_32x16(taddr + t, r);
+      tmem_ld_wait();
+      const int row = out_row0 + lane;
+      if (row < g.out_rows) {
+        float* dst = reinterpret_cast<float*>(g.out) + static_cast<size_t>(row) * g.ldo + col0 + t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (EPI == EPI_RESID_F32)
+            red_add_v4_f32(dst + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                           __uint_as_float(r[4 * j + 3]));
+          else
+            *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+      }
     }
   }
 }
@@ -304,10 +370,12 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
 // The 128 epilogue threads copy the tile's 256 bias values into shared memory BEFORE they wait for the accumulator, so
 // the global-load latency hides behind the tile's MMAs; named barrier 1 (epilogue warps only) publishes them.
 template <int EPI>
-__device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int w_row, int epi_tid) {
+__device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int w_row, int epi_tid, int col0 = 0) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_SWIGLU_SAVE) {
-    sbias[epi_tid] = __ldg(p.bias + w_row + epi_tid);
-    sbias[128 + epi_tid] = __ldg(p.bias + w_row + 128 + epi_tid);
+    // entries past the tile width or past the matrix edge (an overhanging last tile) are never used: read nothing there
+    const int j0 = epi_tid, j1 = 128 + epi_tid;
+    sbias[j0] = (j0 < p.bn && col0 + j0 < p.n_total) ? __ldg(p.bias + w_row + j0) : 0.f;
+    sbias[j1] = (j1 < p.bn && col0 + j1 < p.n_total) ? __ldg(p.bias + w_row + j1) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
 }
@@ -328,7 +396,8 @@ __device__ __forceinline__ void gemm_epilogue_dispatch(const GemmParams& p, uint
       gemm_epilogue_warp<EPI_SWIGLU_BF16>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
     }
   } else {
-    gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk);
+    gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk, EpiDrop{0, 0, 0, 1.0f},
+                            EpiGeom{p.bn, p.n_total, p.out_ptr, p.ldo, p.out_rows});
   }
 }
 
@@ -448,7 +517,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       float* sbias = sbias_all + as * GEMM_BLOCK_N;
-      stage_bias<EPI>(p, sbias, p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N, q * 32 + lane);
+      stage_bias<EPI>(p, sbias, p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N, q * 32 + lane, nb * GEMM_BLOCK_N);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       if (q * 32 < tile.rows_valid) {  // warp-uniform: this warp's 32 rows hold at least one real row
@@ -532,30 +601,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   const int n_m = *p.num_m_tiles;
   const int total = n_m * p.n_blocks;
   const int k_blocks = p.k_blocks;
+  const int bn = p.bn, half_n = p.bn >> 1;
+  const uint32_t stage_tx = GEMM_A_BYTES + static_cast<uint32_t>(half_n) * (GEMM_BLOCK_K * 2);  // bytes per CTA per k-block
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer (both CTAs) =====================
       int stage = 0;
       uint32_t phase = 0;
-      SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable);
+      SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable & 1);
       int t, kb0, kb1;
       while (it.next(t, kb0, kb1)) {
         const int mt = t % n_m, nb = t / n_m;
         const GemmMTile tile = p.m_tiles[mt];
         const int a_row = tile.a_row0 + static_cast<int>(rank) * GEMM_BLOCK_M;
-        const int w_row = p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N + static_cast<int>(rank) * G2_HALF_N;
+        const int w_row = p.w_row_off + tile.w_row_base + nb * bn + static_cast<int>(rank) * half_n;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * G2_STAGE_BYTES;
           const uint32_t b_dst = a_dst + GEMM_A_BYTES;
           const uint32_t leader_full = mapa_cluster(full_bar(stage), 0);
+          // measurement aid (mode_debug_gemm bit 10): odd k-blocks reuse the stale weight tile of their stage, i.e. the
+          // same MMA work with 25 % less L2->SM traffic; results are garbage
+          const bool skip_b = (p.sk_enable & 2) && (kb & 1);
           if (rank == 0)
-            mbar_arrive_expect_tx(full_bar(stage), 2 * G2_STAGE_BYTES);
+            mbar_arrive_expect_tx(full_bar(stage), skip_b ? 2 * GEMM_A_BYTES : 2 * stage_tx);
           else
             mbar_arrive_cluster(leader_full);
           tma_load_2d_2sm(a_dst, &p.tmap_a, leader_full, kb * GEMM_BLOCK_K, a_row);
-          tma_load_2d_2sm(b_dst, &p.tmap_w, leader_full, kb * GEMM_BLOCK_K, w_row);
+          if (!skip_b) tma_load_2d_2sm(b_dst, &p.tmap_w, leader_full, kb * GEMM_BLOCK_K, w_row);
           if (++stage == G2_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -566,11 +640,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       // ===================== MMA issuer (leader CTA only) =====================
-      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, GEMM_BLOCK_N);
+      const uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, static_cast<uint32_t>(bn));
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable);
+      SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable & 1);
       int t, kb0, kb1;
       for (; it.next(t, kb0, kb1); ++iter) {
         const int as = iter & 1;
@@ -602,7 +676,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     const uint32_t stage_smem = epi_smem + static_cast<uint32_t>(q) * 2 * GEMM_EPI_BUF_BYTES;
     uint32_t n_stores = 0;
     int iter = 0;
-    SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable);
+    SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable & 1);
     int t, kb0, kb1;
     constexpr size_t kSlot = 8 * 8 * 128;  // float4 per CTA slot
     for (; it.next(t, kb0, kb1); ++iter) {
@@ -611,7 +685,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
       float* sbias = sbias_all + as * GEMM_BLOCK_N;
-      stage_bias<EPI>(p, sbias, p.w_row_off + tile.w_row_base + nb * GEMM_BLOCK_N, q * 32 + lane);
+      stage_bias<EPI>(p, sbias, p.w_row_off + tile.w_row_base + nb * bn, q * 32 + lane, nb * bn);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row0 = static_cast<int>(rank) * GEMM_BLOCK_M + q * 32;  // first row of this warp inside the 256-row tile

@@ -20,7 +20,7 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_gemm(M, N, K, epi, seed=0, pair=False, stream_k=False):
+def run_gemm(M, N, K, epi, seed=0, pair=False, stream_k=False, bn=256, skip_b=False):
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(seed)
     Mp = (M + 255) // 256 * 256
@@ -48,7 +48,7 @@ def run_gemm(M, N, K, epi, seed=0, pair=False, stream_k=False):
     else:
         out = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
         want = ref
-    _lib.check(lib.mode_debug_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(out), M, N, K, epi | (0x100 if pair else 0) | (0x200 if stream_k else 0), _stream()))
+    _lib.check(lib.mode_debug_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(resid), _ptr(out), M, N, K, epi | (0x100 if pair else 0) | (0x200 if stream_k else 0) | ((bn // 16) << 16 if bn != 256 else 0) | (0x400 if skip_b else 0), _stream()))
     torch.cuda.synchronize()
     return out.float(), want
 
@@ -69,6 +69,20 @@ def test_gemm_matches_fp32_reference(M, N, K, epi, mode):
     else:  # bf16 outputs: at most one bf16 ulp (plus the fp32 noise floor) from the rounded reference
         assert (err <= want.abs() * 2 ** -7 + noise).all(), err.max().item()
         assert (err > 0).float().mean().item() < 0.02  # almost all elements round identically
+
+
+@pytest.mark.parametrize("epi", [0, 1, 3, 4])
+@pytest.mark.parametrize("bn", [208, 160, 128, 240, 176])
+@pytest.mark.parametrize("M,N,K", [(3584, 1024, 1024), (3584, 3072, 1024), (7168, 1024, 4096), (300, 1024, 512), (1000, 3072, 256)])
+def test_gemm_tile_widths_are_bit_identical(M, N, K, epi, bn):
+    """CTA-pair kernel with `bn`-wide tiles (wave filling, engine.cu choose_bn): the column tiling changes which tile owns
+    an output column — overhanging last tile, 16-column register-stored tails — but not the K order of any element, so
+    the result must equal the 256-wide tiling bit for bit."""
+    got, want = run_gemm(M, N, K, epi, pair=True, bn=bn)
+    base, _ = run_gemm(M, N, K, epi, pair=True)
+    assert torch.isfinite(got).all()
+    assert torch.equal(got, base), (got - base).abs().max().item()
+    del want
 
 
 def attention_reference(qkv, gq, gk, B, T, H, Dh, eps):

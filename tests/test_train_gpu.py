@@ -549,5 +549,9 @@ def test_policy_diffusion_loss_draws_sigma_and_noise_like_the_reference():
     assert float(sigmas.min()) >= 1e-3 and float(sigmas.max()) <= 80.0
     want, _ = model.loss(st, acts, goal_t, noise, sigmas)
     assert float(loss) == float(want)
-    loss.backward()
+    # the engine keeps ONE set of gradients: the first loss was superseded by the second call, so back-propagating it
+    # must fail loudly instead of handing out the second call's gradients (advisor finding, round 1)
+    with pytest.raises(RuntimeError, match="called again before this loss was back-propagated"):
+        loss.backward()
+    want.backward()
     assert dict(inner.named_parameters())["out.weight"].grad is not None
