@@ -14,7 +14,8 @@ from dataclasses import dataclass, field
 
 import torch
 
-DENOISER_PREFIXES = ("model.inner_model.", "inner_model.", "")  # agent-level, GCDenoiser-level, MoDeDiT-level keys
+DENOISER_PREFIXES = ("model.inner_model.", "inner_model.", "inner_", "")  # agent-level, GCDenoiser-level, HF-export
+# (the reference's save_to_hf.py strips every "model." -> "inner_<key>", see save_to_hf.clean_key), MoDeDiT-level keys
 
 
 @dataclass
