@@ -192,6 +192,21 @@ int mode_sample_ddim(mode_engine_t* e, const float* state_dev, const float* goal
 int mode_sample_ddim_host(mode_engine_t* e, const float* state_host, const float* goal_host, float* x_inout_host,
                           const float* sigmas_host, int n_plus_1, int B, void* stream);
 
+/* Sampler programs: the remaining k-diffusion samplers of gc_sampling.py — sample_heun :257, sample_dpm_2 :315,
+ * sample_lms :430, sample_dpmpp_2s :956, sample_euler_ancestral :214, sample_dpm_2_ancestral :376,
+ * sample_dpmpp_2s_ancestral :874 — as ONE CUDA-graph launch. Each of their updates is a linear combination of the step's
+ * base sample X, the probe P handed to a second evaluation, the evaluation's denoised output D, up to four history
+ * tensors H and a caller-drawn noise tensor. Evaluation i runs the denoiser at sigma_eval_host[i] on X
+ * (reads_probe_host[i] = 0) or P (1); the head kernel's epilogue then applies row i of prog_host (16 floats):
+ *   {cX, cP, cD, cH0, cH1, cH2, cH3, cN, hX, hD, slot, dst, 0, 0, 0, 0}:
+ *   dst <- cX*X + cP*P + cD*D + sum_j cHj*H[j] + cN*noise_i   (dst = X if prog[11] == 0 else P)
+ *   H[slot] <- hX*x_in + hD*D  if slot >= 0                    (x_in = the evaluation's input)
+ * noise_dev: (n_evals, B, A, action_dim) fp32 drawn by the caller (RNG stays with the caller, mode_agent.py:756), or
+ * NULL. x_inout_dev receives the final X. n_evals <= 64, every sigma > 0. */
+int mode_sample_program(mode_engine_t* e, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                        const float* sigma_eval_host, const int32_t* reads_probe_host, const float* prog_host,
+                        const float* noise_dev, int n_evals, int B, void* stream);
+
 /* NoiseBlockMoE.forward(x, c) (modedit.py:530-595), eval mode, for one layer: x_dev/out_dev (B, T, d) with
  * T = 2 + n_state_tokens + action_seq_len, c_dev (B, d). */
 int mode_block_forward(mode_engine_t* e, int layer, const float* x_dev, const float* c_dev, float* out_dev, int B,

@@ -74,6 +74,8 @@ SYMBOLS = {
     "mode_optimizer_state": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mode_train_input_grads": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "mode_sample": (C.c_int, [_P, C.c_int, _F, _F, _F, C.POINTER(C.c_float), C.c_int, C.c_int, _P]),
+    "mode_sample_program": (C.c_int, [_P, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float), _F,
+                                      C.c_int, C.c_int, _P]),
     "mode_sample_ddim": (C.c_int, [_P, _F, _F, _F, C.POINTER(C.c_float), C.c_int, C.c_int, _P]),
     "mode_sample_ddim_host": (C.c_int, [_P, _F, _F, _F, C.POINTER(C.c_float), C.c_int, C.c_int, _P]),
     "mode_block_forward": (C.c_int, [_P, C.c_int, _F, _F, _F, C.c_int, _P]),

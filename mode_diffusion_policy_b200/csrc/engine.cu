@@ -218,6 +218,9 @@ struct mode_engine {
   // workspace
   float *x, *cvec, *xnorm, *state_tok, *goal_tok, *x_work, *sig_dev, *coefs_dev, *tok_sqerr, *zbuf;
   float* d_prev;  // previous step's denoised actions (multistep samplers)
+  float *x_probe = nullptr, *hist = nullptr, *prog_dev = nullptr, *noise_buf = nullptr;  // sampler programs (mode_sample_program)
+  std::map<std::string, cudaGraphExec_t> prog_graphs;
+  std::map<std::string, int64_t> prog_graph_launches;
   float *in_state, *in_goal, *in_x;  // device staging of the *_host entry points
   __nv_bfloat16 *hA, *qkv, *attn, *perm, *hbuf, *ybuf, *st_bf16, *goal_bf16;
   int *topk_idx, *sel_idx, *pos_tab, *num_tiles, *dense_counts;
@@ -504,6 +507,7 @@ extern "C" void mode_destroy(mode_engine_t* e) {
   if (!e) return;
   destroy_train(e->train);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+  for (auto& g : e->prog_graphs) cudaGraphExecDestroy(g.second);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->weights_ready) cudaEventDestroy(e->weights_ready);
   for (void* p : e->allocs) cudaFree(p);
@@ -829,6 +833,9 @@ static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);  // captured kernels embed the old maps
   e->graphs.clear();
   e->graph_launches.clear();
+  for (auto& g : e->prog_graphs) cudaGraphExecDestroy(g.second);
+  e->prog_graphs.clear();
+  e->prog_graph_launches.clear();
   e->cur_B = B;
   return MODE_OK;
 }
@@ -1151,7 +1158,8 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
 // evaluation routes itself into ROUTE_SLOT_EVAL.
 static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sigma, int stride, const float* actions,
                         int apply_c_in, int head_mode, float* out, const float* coefs, const float* clean,
-                        int prerouted_slot = -1, const LayerIO* layer_io = nullptr) {
+                        int prerouted_slot = -1, const LayerIO* layer_io = nullptr, const float* prog = nullptr,
+                        const float* noise = nullptr) {
   // layer_io: per-layer buffer sets (training); nullptr = the shared in-place inference set
   const LayerIO& io0 = layer_io ? layer_io[0] : e->io;
   const int slot = prerouted_slot >= 0 ? prerouted_slot : ROUTE_SLOT_EVAL;
@@ -1181,6 +1189,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   h.sc = StepScalars{sigma, stride, e->cfg.sigma_data};
   h.xnorm = e->xnorm; h.w_out = e->w_out; h.b_out = e->b_out; h.x_act = actions; h.out = out; h.clean = clean;
   h.tok_sqerr = e->tok_sqerr; h.coefs = coefs; h.d_prev = e->d_prev;
+  h.prog = prog; h.xbase = e->x_work; h.xprobe = e->x_probe; h.hist = e->hist; h.noise = noise;
   h.B = B; h.T = e->T; h.A = e->A; h.action_dim = e->adim; h.d = e->d; h.mode = head_mode;
   {
     ProfScope ps(e, st, PC_HEAD);
@@ -1375,6 +1384,80 @@ extern "C" int mode_sample_ddim_host(mode_engine_t* e, const float* state_host, 
   RET_IF(mode_sample_ddim(e, e->in_state, e->in_goal, e->in_x, sigmas_host, n_plus_1, B, stream));
   CU_OK(cudaMemcpyAsync(x_inout_host, e->in_x, n_x * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU_OK(cudaStreamSynchronize(st));
+  return MODE_OK;
+}
+
+// Sampler programs: any k-diffusion sampler whose update is linear in {X, P, D, history, noise} as one CUDA graph
+// (gc_sampling.py: sample_heun :257, sample_dpm_2 :315, sample_lms :430, sample_dpmpp_2s :956, the ancestral variants
+// :214 / :376 / :874). The host (mode_diffusion_policy_b200/gc_sampling.py) turns the sigma schedule into one row of
+// coefficients per network evaluation; the graph only depends on the evaluation count and on which evaluations read
+// the probe, so every schedule of the same sampler replays the same graph.
+extern "C" int mode_sample_program(mode_engine_t* e, const float* state_dev, const float* goal_dev, float* x_inout_dev,
+                                   const float* sigma_eval_host, const int32_t* reads_probe_host, const float* prog_host,
+                                   const float* noise_dev, int n_evals, int B, void* stream) {
+  if (!e || !state_dev || !goal_dev || !x_inout_dev || !sigma_eval_host || !reads_probe_host || !prog_host)
+    return fail(MODE_ERR_INVALID, "null argument");
+  if (n_evals < 1 || n_evals > 64) return fail(MODE_ERR_INVALID, "a sampler program has 1..64 network evaluations (got %d)", n_evals);
+  for (int i = 0; i < n_evals; ++i)
+    if (!(sigma_eval_host[i] > 0.f)) return fail(MODE_ERR_INVALID, "evaluation %d: sigma must be > 0", i);
+  RET_IF(ensure_batch(e, B, reinterpret_cast<cudaStream_t>(stream)));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n_el = (size_t)e->maxB * e->A * e->adim;
+  if (!e->x_probe) {
+    RET_IF(dev_alloc(e, &e->x_probe, n_el));
+    RET_IF(dev_alloc(e, &e->hist, 4 * n_el));
+    RET_IF(dev_alloc(e, &e->prog_dev, (size_t)64 * HEAD_PROG_FLOATS));
+    RET_IF(dev_alloc(e, &e->noise_buf, 64 * n_el));
+  }
+  e->launch_count = 0;
+  std::string key = std::to_string(B) + (noise_dev ? ":n:" : ":-:");
+  for (int i = 0; i < n_evals; ++i) key.push_back(reads_probe_host[i] ? 'P' : 'X');
+  const size_t cur_el = (size_t)B * e->A * e->adim;
+  auto it = e->prog_graphs.find(key);
+  if (it == e->prog_graphs.end()) {
+    const int64_t before = e->launch_count;
+    cudaGraph_t graph = nullptr;
+    CU_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = MODE_OK;
+    for (int i = 0; i < n_evals && rc == MODE_OK; ++i)
+      rc = enqueue_eval(e, e->cap_stream, B, e->sig_dev + i, 0, reads_probe_host[i] ? e->x_probe : e->x_work, 1, 6, nullptr,
+                        nullptr, nullptr, i, nullptr, e->prog_dev + (size_t)i * HEAD_PROG_FLOATS,
+                        noise_dev ? e->noise_buf + (size_t)i * cur_el : nullptr);
+    cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc != MODE_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t ex = nullptr;
+    ce = cudaGraphInstantiate(&ex, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(MODE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    it = e->prog_graphs.emplace(key, ex).first;
+    e->prog_graph_launches[key] = e->launch_count - before;
+  } else {
+    e->launch_count += e->prog_graph_launches[key];
+  }
+  ScheduleArg sa;
+  sa.n = n_evals;
+  for (int i = 0; i < n_evals; ++i) {
+    float* v = sa.v + (1 + SCHED_COEFS) * i;
+    v[0] = sigma_eval_host[i];
+    v[1] = v[2] = v[3] = v[4] = 0.f;
+  }
+  set_schedule_kernel<<<1, 64, 0, st>>>(sa, e->sig_dev, e->coefs_dev);
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaMemcpyAsync(e->prog_dev, prog_host, (size_t)n_evals * HEAD_PROG_FLOATS * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (noise_dev)
+    CU_OK(cudaMemcpyAsync(e->noise_buf, noise_dev, (size_t)n_evals * cur_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CU_OK(cudaMemsetAsync(e->hist, 0, 4 * cur_el * sizeof(float), st));
+  CU_OK(cudaMemcpyAsync(e->x_work, x_inout_dev, cur_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CU_OK(cudaMemcpyAsync(e->x_probe, x_inout_dev, cur_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, nullptr, 0, e->L, 0, n_evals, 1, e->trim_rows));
+  RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
+  CU_OK(cudaGraphLaunch(it->second, st));
+  CU_OK(cudaMemcpyAsync(x_inout_dev, e->x_work, cur_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  e->launch_count += 1;
   return MODE_OK;
 }
 

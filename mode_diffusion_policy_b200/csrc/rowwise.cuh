@@ -734,8 +734,20 @@ struct HeadParams {
   const float* coefs;      // modes 2, 4, 5: this step's update coefficients (host fp32, reference op order; engine.cu sampler_schedule)
   float* d_prev;           // mode 5: the previous step's denoised actions [B, A, action_dim] (read, then overwritten)
   int B, T, A, action_dim, d;
-  int mode;                // 0 raw F, 1 denoised D, 2 DDIM update, 3 loss (out <- F), 4 Euler update, 5 DPM-Solver++(2M) update
+  int mode;                // 0 raw F, 1 denoised D, 2 DDIM update, 3 loss (out <- F), 4 Euler update, 5 DPM-Solver++(2M) update,
+                           // 6 sampler program (below)
+  // mode 6 — one row of a "sampler program" (mode_sample_program): every k-diffusion update of gc_sampling.py is a linear
+  // combination of the step's base sample X, the probe P fed to a second evaluation, this evaluation's denoised D, up to
+  // four history tensors H (Heun's first slope, the LMS derivative history) and a caller-drawn noise tensor:
+  //   dst <- cX*X + cP*P + cD*D + sum_j cH[j]*H[j] + cN*noise,  dst = X or P;   H[slot] <- hX*x_in + hD*D  (optional)
+  // prog = {cX, cP, cD, cH0..cH3, cN, hX, hD, slot (-1: none), dst (0: X, 1: P)} as 12 floats, written by the host.
+  const float* prog;
+  float* xbase;            // X  [B, A, action_dim]
+  float* xprobe;           // P
+  float* hist;             // H  [4][B*A*action_dim]
+  const float* noise;      // this evaluation's noise tensor or nullptr
 };
+constexpr int HEAD_PROG_FLOATS = 16;
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p) {
   pdl_trigger();
@@ -796,6 +808,20 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p
           if (p.coefs[3] != 0.f) target = __fsub_rn(__fmul_rn(p.coefs[2], den), __fmul_rn(p.coefs[3], p.d_prev[o]));
           p.d_prev[o] = den;
           result = __fsub_rn(__fmul_rn(p.coefs[0], xa), __fmul_rn(p.coefs[1], target));
+        } else if (p.mode == 6) {
+          const float* c = p.prog;
+          const size_t n_el = static_cast<size_t>(p.B) * p.A * p.action_dim;
+          float v = c[2] * den;
+          if (c[0] != 0.f) v = fmaf(c[0], p.xbase[o], v);
+          if (c[1] != 0.f) v = fmaf(c[1], p.xprobe[o], v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c[3 + j] != 0.f) v = fmaf(c[3 + j], p.hist[j * n_el + o], v);
+          if (c[7] != 0.f) v = fmaf(c[7], p.noise[o], v);
+          const int slot = static_cast<int>(c[10]);
+          if (slot >= 0) p.hist[slot * n_el + o] = fmaf(c[8], xa, c[9] * den);  // every source above was read first
+          (c[11] != 0.f ? p.xprobe : p.xbase)[o] = v;
+          result = v;
         } else {
           result = den;
         }

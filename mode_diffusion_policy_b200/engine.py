@@ -312,6 +312,27 @@ class ModeEngine:
                                         sig.ctypes.data_as(C.POINTER(C.c_float)), len(sig), B, self._stream()))
         return x
 
+    def sample_program(self, state, x, goal, sigma_eval, reads_probe, prog, noise=None) -> torch.Tensor:
+        """A sampler program (include/mode_engine.h `mode_sample_program`): one CUDA-graph launch for the whole loop.
+        sigma_eval (n,), reads_probe (n,) 0/1, prog (n, 16) fp32 coefficient rows, noise (n, B, A, adim) CUDA or None."""
+        state, goal, x, _, _, B = self._prep(state, goal, x, None)
+        x = x.clone()
+        sig = np.ascontiguousarray(sigma_eval, dtype=np.float32)
+        rp = np.ascontiguousarray(reads_probe, dtype=np.int32)
+        pg = np.ascontiguousarray(prog, dtype=np.float32)
+        n = len(sig)
+        if pg.shape != (n, 16) or rp.shape != (n,):
+            raise _lib.ModeError(f"sampler program: expected ({n}, 16) coefficients and ({n},) flags")
+        if noise is not None:
+            noise = _f32_cuda(noise, "noise")
+            if tuple(noise.shape) != (n,) + tuple(x.shape):
+                raise _lib.ModeError(f"sampler program: noise must be {(n,) + tuple(x.shape)}")
+        _lib.check(self.lib.mode_sample_program(
+            self._h, state.data_ptr(), goal.data_ptr(), x.data_ptr(), sig.ctypes.data_as(C.POINTER(C.c_float)),
+            rp.ctypes.data_as(C.POINTER(C.c_int32)), pg.ctypes.data_as(C.POINTER(C.c_float)),
+            noise.data_ptr() if noise is not None else None, n, B, self._stream()))
+        return x
+
     def sample_ddim(self, state, x, goal, sigmas) -> torch.Tensor:
         """sample_ddim over GCDenoiser (whole loop = one CUDA graph). `sigmas` includes the trailing 0. Returns actions."""
         return self.sample("ddim", state, x, goal, sigmas)

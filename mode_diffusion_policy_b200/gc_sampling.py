@@ -134,6 +134,47 @@ def _fusable(model, attr, sigmas, scaler, extra_args, callback) -> bool:
     return 2 <= s.numel() <= 65 and bool((s[:-1] > 0).all())
 
 
+class SamplerProgram:
+    """A sampler written as one row of coefficients per network evaluation, for the engine's one-launch execution
+    (`GCDenoiser.sample_program` -> `mode_sample_program`). Every update in this file is linear in the step's base
+    sample X, the probe P given to a second evaluation, the denoised output D, up to four history tensors H and a noise
+    draw:   dst <- cX*X + cP*P + cD*D + sum_j cH[j]*H[j] + cN*noise,   H[slot] <- hX*x_in + hD*D.
+    The coefficients are evaluated here in float64 from the schedule (the reference evaluates the same expressions on
+    0-dim fp32 tensors; the difference is an fp32 ulp on numbers that multiply bf16-accurate network outputs)."""
+
+    def __init__(self):
+        self.sigma, self.reads_probe, self.rows, self.noise_index = [], [], [], []
+
+    def eval(self, sigma, on_probe=False, cX=0.0, cP=0.0, cD=0.0, cH=(0.0, 0.0, 0.0, 0.0), cN=0.0, hX=0.0, hD=0.0,
+             slot=-1, to_probe=False, noise=None):
+        """Append one evaluation at `sigma` on X (or P) followed by its update row; `noise`: index of the caller's draw."""
+        self.sigma.append(float(sigma))
+        self.reads_probe.append(1 if on_probe else 0)
+        self.rows.append([cX, cP, cD, *cH, cN if noise is not None else 0.0, hX, hD, float(slot), 1.0 if to_probe else 0.0,
+                          0.0, 0.0, 0.0, 0.0])
+        self.noise_index.append(noise)
+
+    def run(self, model, state, action, goal, draws):
+        """draws: the noise tensors the host loop would have drawn, in order (may be empty)."""
+        noise = None
+        if any(i is not None for i in self.noise_index):
+            zero = torch.zeros_like(action)
+            noise = torch.stack([zero if i is None else draws[i] for i in self.noise_index])
+        return model.sample_program(state, action, goal, np.asarray(self.sigma, np.float32),
+                                    np.asarray(self.reads_probe, np.int32), np.asarray(self.rows, np.float32), noise)
+
+
+def _program_ok(model, sigmas, scaler, extra_args, callback, evals_per_step=2) -> bool:
+    if scaler is not None or callback is not None or extra_args or not hasattr(model, "sample_program"):
+        return False
+    s = torch.as_tensor(sigmas)
+    return s.numel() >= 2 and evals_per_step * (s.numel() - 1) <= 64 and bool((s[:-1] > 0).all())
+
+
+def _floats(sigmas):
+    return [float(v) for v in torch.as_tensor(sigmas).detach().double().cpu()]
+
+
 def _exp_step(x, denoised, t, t_next):
     """x <- (sigma(t')/sigma(t)) x - expm1(-(t'-t)) D : the DPM-Solver-1 / DDIM update (reference gc_sampling.py:950)."""
     return (_sig(t_next) / _sig(t)) * x - (-(t_next - t)).expm1() * denoised
@@ -175,7 +216,19 @@ def sample_euler(model, state, action, goal, sigmas, scaler=None, extra_args=Non
 @torch.no_grad()
 def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
                            disable=None, eta=1.0):
-    """reference gc_sampling.py:213-254"""
+    """reference gc_sampling.py:213-254. One engine launch; the noise is drawn here, by the caller's RNG, in the order the
+    loop would draw it."""
+    if _program_ok(model, sigmas, scaler, extra_args, callback, evals_per_step=1):
+        sg, prog, draws = _floats(sigmas), SamplerProgram(), []
+        for i in range(len(sg) - 1):
+            s0 = sg[i]
+            down, up = (float(v) for v in get_ancestral_step(s0, sg[i + 1], eta=eta))
+            k = None
+            if down > 0:
+                draws.append(torch.randn_like(action))
+                k = len(draws) - 1
+            prog.eval(s0, cX=1 + (down - s0) / s0, cD=-(down - s0) / s0, cN=up, noise=k)
+        return prog.run(model, state, action, goal, draws)
     lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
     for i in range(len(sigmas) - 1):
         denoised = lp.denoise(action, sigmas[i])
@@ -191,7 +244,19 @@ def sample_euler_ancestral(model, state, action, goal, sigmas, scaler=None, extr
 @torch.no_grad()
 def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
                 s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
-    """Algorithm 2 of Karras et al. (Heun) (reference gc_sampling.py:256-312)."""
+    """Algorithm 2 of Karras et al. (Heun) (reference gc_sampling.py:256-312). Without churn the loop is one engine launch."""
+    if s_churn == 0 and _program_ok(model, sigmas, scaler, extra_args, callback):
+        sg, prog = _floats(sigmas), SamplerProgram()
+        for i in range(len(sg) - 1):
+            torch.randn_like(action)  # the reference draws eps every step even when gamma = 0 (:287)
+            s0, s1 = sg[i], sg[i + 1]
+            dt = s1 - s0
+            if s1 == 0:
+                prog.eval(s0, cX=1 + dt / s0, cD=-dt / s0)                                       # Euler step to sigma = 0
+            else:
+                prog.eval(s0, cX=1 + dt / s0, cD=-dt / s0, hX=1 / s0, hD=-1 / s0, slot=0, to_probe=True)  # H0 = d, P = X + d dt
+                prog.eval(s1, on_probe=True, cX=1.0, cH=(dt / 2, 0, 0, 0), cP=dt / (2 * s1), cD=-dt / (2 * s1))  # X += (d + d2)/2 dt
+        return prog.run(model, state, action, goal, [])
     lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
     for i in range(len(sigmas) - 1):
         action, sigma_hat = _churn(action, sigmas, i, s_churn, s_tmin, s_tmax, s_noise)
@@ -212,7 +277,19 @@ def sample_heun(model, state, action, goal, sigmas, scaler=None, extra_args=None
 @torch.no_grad()
 def sample_dpm_2(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
                  s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0):
-    """DPM-Solver-2 flavoured midpoint steps (reference gc_sampling.py:314-373)."""
+    """DPM-Solver-2 flavoured midpoint steps (reference gc_sampling.py:314-373). Without churn: one engine launch."""
+    if s_churn == 0 and _program_ok(model, sigmas, scaler, extra_args, callback):
+        sg, prog = _floats(sigmas), SamplerProgram()
+        for i in range(len(sg) - 1):
+            torch.randn_like(action)  # unused eps draw of the reference (:344)
+            s0, s1 = sg[i], sg[i + 1]
+            if s1 == 0:
+                prog.eval(s0, cX=1 + (s1 - s0) / s0, cD=-(s1 - s0) / s0)
+            else:
+                mid = math.exp(0.5 * (math.log(s0) + math.log(s1)))
+                prog.eval(s0, cX=1 + (mid - s0) / s0, cD=-(mid - s0) / s0, to_probe=True)          # P = X + d (mid - s0)
+                prog.eval(mid, on_probe=True, cX=1.0, cP=(s1 - s0) / mid, cD=-(s1 - s0) / mid)     # X += d2 (s1 - s0)
+        return prog.run(model, state, action, goal, [])
     lp = _Loop(model, state, goal, scaler, extra_args, callback)
     for i in range(len(sigmas) - 1):
         action, sigma_hat = _churn(action, sigmas, i, s_churn, s_tmin, s_tmax, s_noise)
@@ -233,7 +310,20 @@ def sample_dpm_2(model, state, action, goal, sigmas, scaler=None, extra_args=Non
 @torch.no_grad()
 def sample_dpm_2_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
                            disable=None, eta=1.0):
-    """reference gc_sampling.py:375-410"""
+    """reference gc_sampling.py:375-410. One engine launch (see sample_euler_ancestral for the noise)."""
+    if _program_ok(model, sigmas, scaler, extra_args, callback):
+        sg, prog, draws = _floats(sigmas), SamplerProgram(), []
+        for i in range(len(sg) - 1):
+            s0 = sg[i]
+            down, up = (float(v) for v in get_ancestral_step(s0, sg[i + 1], eta=eta))
+            if down == 0:
+                prog.eval(s0, cX=1 + (down - s0) / s0, cD=-(down - s0) / s0)
+            else:
+                mid = math.exp(0.5 * (math.log(s0) + math.log(down)))
+                draws.append(torch.randn_like(action))
+                prog.eval(s0, cX=1 + (mid - s0) / s0, cD=-(mid - s0) / s0, to_probe=True)
+                prog.eval(mid, on_probe=True, cX=1.0, cP=(down - s0) / mid, cD=-(down - s0) / mid, cN=up, noise=len(draws) - 1)
+        return prog.run(model, state, action, goal, draws)
     lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
     for i in range(len(sigmas) - 1):
         denoised = lp.denoise(action, sigmas[i])
@@ -270,7 +360,20 @@ def linear_multistep_coeff(order, t, i, j):
 
 @torch.no_grad()
 def sample_lms(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None, order=4):
-    """Linear multistep sampler (reference gc_sampling.py:429-466)."""
+    """Linear multistep sampler (reference gc_sampling.py:429-466). Up to order 4 the loop is one engine launch: the
+    derivative history lives in the engine's four history tensors."""
+    if order <= 4 and _program_ok(model, sigmas, scaler, extra_args, callback, evals_per_step=1):
+        sg, prog = _floats(sigmas), SamplerProgram()
+        sig32 = torch.as_tensor(sigmas).detach().cpu().numpy()
+        for i in range(len(sg) - 1):
+            cur = min(i + 1, order)
+            co = [linear_multistep_coeff(cur, sig32, i, j) for j in range(cur)]  # co[j] multiplies d_{i-j}
+            cH = [0.0] * 4
+            for j in range(1, cur):
+                cH[(i - j) % 4] = co[j]
+            # d_i = (X - D)/s_i goes to slot i % 4 (it replaces d_{i-4}, which order <= 4 no longer needs)
+            prog.eval(sg[i], cX=1 + co[0] / sg[i], cD=-co[0] / sg[i], cH=tuple(cH), hX=1 / sg[i], hD=-1 / sg[i], slot=i % 4)
+        return prog.run(model, state, action, goal, [])
     lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
     sig = sigmas.detach().cpu().numpy()
     history = []
@@ -311,7 +414,19 @@ sample_dpmpp_2_with_lms = sample_dpmpp_2m  # identical bodies in the reference (
 @torch.no_grad()
 def sample_dpmpp_2s(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None, disable=None,
                     eta=1.0):
-    """DPM-Solver++(2S) (reference gc_sampling.py:955-994)."""
+    """DPM-Solver++(2S) (reference gc_sampling.py:955-994). One engine launch."""
+    if _program_ok(model, sigmas, scaler, extra_args, callback):
+        sg, prog = _floats(sigmas), SamplerProgram()
+        for i in range(len(sg) - 1):
+            s0, s1 = sg[i], sg[i + 1]
+            if s1 == 0:
+                prog.eval(s0, cX=1 + (s1 - s0) / s0, cD=-(s1 - s0) / s0)
+            else:
+                t, tn = -math.log(s0), -math.log(s1)
+                sm = t + 0.5 * (tn - t)
+                prog.eval(s0, cX=math.exp(-sm) / s0, cD=-math.expm1(-(sm - t)), to_probe=True)
+                prog.eval(math.exp(-sm), on_probe=True, cX=s1 / s0, cD=-math.expm1(-(tn - t)))
+        return prog.run(model, state, action, goal, [])
     lp = _Loop(model, state, goal, scaler, extra_args, callback)
     for i in range(len(sigmas) - 1):
         denoised = lp.denoise(action, sigmas[i])
@@ -330,9 +445,24 @@ def sample_dpmpp_2s(model, state, action, goal, sigmas, scaler=None, extra_args=
 @torch.no_grad()
 def sample_dpmpp_2s_ancestral(model, state, action, goal, sigmas, scaler=None, extra_args=None, callback=None,
                               disable=None, eta=1.0, s_noise=1.0, noise_sampler=None):
-    """reference gc_sampling.py:873-919"""
-    lp = _Loop(model, state, goal, scaler, extra_args, callback)
+    """reference gc_sampling.py:873-919. One engine launch; `noise_sampler` is called here once per step, in order."""
     noise_sampler = default_noise_sampler(action) if noise_sampler is None else noise_sampler
+    if _program_ok(model, sigmas, scaler, extra_args, callback):
+        sg, prog, draws = _floats(sigmas), SamplerProgram(), []
+        for i in range(len(sg) - 1):
+            s0 = sg[i]
+            down, up = (float(v) for v in get_ancestral_step(s0, sg[i + 1], eta=eta))
+            draws.append(noise_sampler(torch.as_tensor(sigmas)[i], torch.as_tensor(sigmas)[i + 1]))
+            k = len(draws) - 1
+            if down == 0:
+                prog.eval(s0, cX=1 + (down - s0) / s0, cD=-(down - s0) / s0, cN=s_noise * up, noise=k)
+            else:
+                t, tn = -math.log(s0), -math.log(down)
+                sm = t + 0.5 * (tn - t)
+                prog.eval(s0, cX=math.exp(-sm) / s0, cD=-math.expm1(-(sm - t)), to_probe=True)
+                prog.eval(math.exp(-sm), on_probe=True, cX=down / s0, cD=-math.expm1(-(tn - t)), cN=s_noise * up, noise=k)
+        return prog.run(model, state, action, goal, draws)
+    lp = _Loop(model, state, goal, scaler, extra_args, callback)
     for i in range(len(sigmas) - 1):
         denoised = lp.denoise(action, sigmas[i])
         sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)

@@ -141,5 +141,12 @@ class GCDenoiser(nn.Module):
         goal = m._goals(goal, False)
         return self._engine(action.shape[0]).sample(sampler, state["state_images"], action, goal, sigmas).to(action.dtype)
 
+    def sample_program(self, state, action, goal, sigma_eval, reads_probe, prog, noise=None):
+        """A sampler program (gc_sampling.SamplerProgram) as one CUDA-graph launch (engine `mode_sample_program`)."""
+        m = self.inner_model
+        goal = m._goals(goal, False)
+        return self._engine(action.shape[0]).sample_program(state["state_images"], action, goal, sigma_eval, reads_probe,
+                                                            prog, noise).to(action.dtype)
+
     def get_params(self):
         return self.inner_model.parameters()

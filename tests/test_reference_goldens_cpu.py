@@ -133,3 +133,50 @@ def test_sampler_host_loops_match_reference_samplers(key, monkeypatch):
                            torch.from_numpy(g["sigmas"]), disable=True, **kw)
     assert tape.i == int(g[key + "_draws"]), "the loop must consume the caller's RNG exactly like the reference"
     assert rel_l2(out.numpy(), g[key]) < 5e-5, rel_l2(out.numpy(), g[key])
+
+
+class _ProgramOracle(_OracleDenoiser):
+    """CPU interpreter of sampler programs (the semantics of the engine's `mode_sample_program`, include/mode_engine.h)
+    over the fp32 oracle denoiser: checks the coefficient rows gc_sampling.py builds against the reference samplers
+    without a GPU."""
+
+    def sample_program(self, state, action, goal, sigma_eval, reads_probe, prog, noise=None):
+        X, P = action.clone(), action.clone()
+        H = [torch.zeros_like(action) for _ in range(4)]
+        self.evals = len(sigma_eval)
+        for i in range(len(sigma_eval)):
+            xin = P if reads_probe[i] else X
+            D = self(state, xin, goal, torch.full((action.shape[0],), float(sigma_eval[i])))
+            c = [float(v) for v in prog[i]]
+            v = c[0] * X + c[1] * P + c[2] * D + sum(c[3 + j] * H[j] for j in range(4))
+            if noise is not None:
+                v = v + c[7] * noise[i]
+            if int(c[10]) >= 0:
+                H[int(c[10])] = c[8] * xin + c[9] * D
+            if c[11]:
+                P = v
+            else:
+                X = v
+        return X
+
+
+PROGRAM_SAMPLERS = {"lms": 10, "heun": 19, "ancestral": 19, "euler_ancestral": 10, "dpm": 19, "dpmpp_2s_ancestral": 19,
+                    "dpmpp_2s": 19}  # golden key -> network evaluations of the 10-step schedule
+
+
+@pytest.mark.parametrize("key", list(PROGRAM_SAMPLERS))
+def test_sampler_programs_match_reference_samplers(key, monkeypatch):
+    """The one-launch form of Heun / DPM-2 / LMS / DPM++(2S) and the ancestral samplers: coefficient rows interpreted on
+    the CPU against the reference's own sampler runs, same noise draws in the same order."""
+    g = np.load(GOLD / "samplers_tiny_d256_l3_e4.npz")
+    sd = O.make_weights(TINY, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(TINY, 5, seed=4321)
+    model = _ProgramOracle(sd, TINY)
+    tape = NoiseTape(g["noise_tape"])
+    monkeypatch.setattr(torch, "randn_like", tape)
+    name, kw = SAMPLER_CALLS[key]
+    out = getattr(S, name)(model, {"state_images": torch.from_numpy(state)}, torch.from_numpy(x0), torch.from_numpy(goal),
+                           torch.from_numpy(g["sigmas"]), disable=True, **kw)
+    assert model.evals == PROGRAM_SAMPLERS[key]  # the program path ran (not the host loop)
+    assert tape.i == int(g[key + "_draws"])
+    assert rel_l2(out.numpy(), g[key]) < 5e-5, rel_l2(out.numpy(), g[key])
