@@ -252,6 +252,23 @@ int mode_debug_wgrad(const void* dy_dev, const void* x_dev, float* out_dev, int 
 int mode_debug_attention(const void* qkv_dev, const float* q_gain_dev, const float* k_gain_dev, void* out_dev,
                          int B, int T, int H, int Dh, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * FiLM-ResNet-50 token producer: the reference's FiLMResNet50Policy
+ * (mode/models/perceptual_encoders/pretrained_resnets.py:25-60), which MoDEAgent.embed_visual_obs (mode_agent.py:548-567)
+ * calls once per camera to turn images into the `state_images` tokens of the denoiser. Inference only: BatchNorm uses its
+ * running statistics and is folded into the convolution weights; every convolution runs as a tcgen05 GEMM over NHWC bf16
+ * activations with bias, shortcut add, ReLU and the stage's FiLM modulation in the epilogue.
+ * mode_resnet_set_weight takes the module's state_dict keys ("resnet.conv1.weight", "resnet.bn1.running_var",
+ * "resnet.layer2.0.downsample.0.weight", "film3.gamma.weight", ...; "*.num_batches_tracked" is accepted and ignored),
+ * fp32, reference shapes, host or device. mode_resnet_forward: images_dev (N, 3, H, W) fp32 with the H, W given at create
+ * time, cond_dev (N, cond_dim) fp32 (the language goal embedding), out_dev (N, 2048) fp32 pooled features. */
+typedef struct mode_resnet mode_resnet_t;
+int mode_resnet_create(int cond_dim, int max_images, int height, int width, mode_resnet_t** out);
+void mode_resnet_destroy(mode_resnet_t* r);
+int mode_resnet_set_weight(mode_resnet_t* r, const char* name, const float* data, int is_device, const int64_t* shape, int ndim);
+int mode_resnet_finalize(mode_resnet_t* r, void* stream);
+int mode_resnet_forward(mode_resnet_t* r, const float* images_dev, const float* cond_dev, float* out_dev, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,11 @@ SYMBOLS = {
     "mode_get_expert_usage": (C.c_int, [_P, C.c_int, _P, _P]),
     "mode_reset_expert_usage": (C.c_int, [_P]),
     "mode_last_launch_count": (C.c_int64, [_P]),
+    "mode_resnet_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "mode_resnet_destroy": (None, [_P]),
+    "mode_resnet_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "mode_resnet_finalize": (C.c_int, [_P, _P]),
+    "mode_resnet_forward": (C.c_int, [_P, _F, _F, _F, C.c_int, _P]),
     "mode_debug_gemm": (C.c_int, [_F, _F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mode_debug_wgrad": (C.c_int, [_F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mode_debug_attention": (C.c_int, [_F, _F, _F, _F, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),

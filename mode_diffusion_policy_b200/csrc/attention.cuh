@@ -40,7 +40,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-struct AttnParams {
+struct alignas(64) AttnParams {
+  // TMA view of qkv for attention_tma_kernel: [rows, 3*d] bf16, box {64 columns, 16*MT rows}, SWIZZLE_128B
+  CUtensorMap tmap_qkv;
   const __nv_bfloat16* qkv;  // [B*T, 3*d]: q | k | v, each d = H*Dh wide
   __nv_bfloat16* out;        // [B*T, d]
   const float* q_gain;       // [Dh]
@@ -239,6 +241,205 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
     const int row = r0 + lane / VPR;
     if (row < T) {
       const uint4 v = *reinterpret_cast<const uint4*>(sQ + row * LDS + sub * 8);
+      *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b) * T + row) * d + h * DH + sub * 8) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (head dims 64 and 128; the default). Same math and rounding points as attention_kernel above; what
+// changes is how the (sample, head) tile reaches shared memory and how it is laid out there:
+//   * one elected lane per warp issues 3 * DH/64 bulk tensor loads (cp.async.bulk.tensor, SASS UTMALDG) of
+//     [16*MT rows x 64 columns] boxes of q, k and v against the warp's own mbarrier (expect_tx = the tile's bytes); no
+//     thread moves data through registers and nothing is padded: rows past T are the next sample's rows (finite, masked
+//     by causality) or zero fill past the end of the tensor;
+//   * the boxes land in the 128-byte-swizzle layout (16-byte chunk c of row r at chunk c ^ (r & 7)), which makes the
+//     ldmatrix reads of 8 consecutive rows conflict-free without the 8-element row padding of the cp.async version.
+// smem address of element (row, col) of an operand whose first half-tile starts at `base` (1024-byte aligned):
+template <int TPAD>
+__device__ __forceinline__ uint32_t attn_sw128(uint32_t base, int row, int col) {
+  return base + static_cast<uint32_t>(col >> 6) * (TPAD * 128) + static_cast<uint32_t>(row) * 128u +
+         (static_cast<uint32_t>(((col & 63) >> 3) ^ (row & 7)) << 4) + static_cast<uint32_t>(col & 7) * 2u;
+}
+
+template <int DH, int MT>
+__global__ void __launch_bounds__(ATTN_WARPS * 32) attention_tma_kernel(const __grid_constant__ AttnParams p) {
+  pdl_trigger();
+  constexpr int TPAD = 16 * MT;
+  constexpr int VPR = DH / 8;            // 16-byte vectors per row
+  constexpr int ROWS_PER_IT = 32 / VPR;  // rows covered by one warp-wide vector access
+  constexpr int NH = DH / 64;            // 64-column boxes per operand
+  constexpr uint32_t OP_BYTES = TPAD * DH * 2;
+  extern __shared__ __align__(1024) uint8_t attn_tma_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * ATTN_WARPS + warp;  // (b, h)
+  // [ATTN_WARPS][3 operands][OP_BYTES] then one mbarrier per warp
+  const uint32_t smem_base = smem_u32(attn_tma_smem);
+  if ((smem_base & 1023u) != 0) __trap();  // the swizzle pattern is a function of the address bits
+  const uint32_t sQ_a = smem_base + static_cast<uint32_t>(warp) * 3u * OP_BYTES, sK_a = sQ_a + OP_BYTES, sV_a = sK_a + OP_BYTES;
+  const uint32_t bar = smem_base + ATTN_WARPS * 3u * OP_BYTES + 8u * warp;
+  if (item >= p.B * p.H) return;
+  const int b = item / p.H, h = item % p.H;
+  const int T = p.T, d = p.H * DH;
+  if (lane == 0) {
+    tma_prefetch_desc(&p.tmap_qkv);
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  pdl_wait();
+  if (lane == 0) {
+    mbar_arrive_expect_tx(bar, 3u * OP_BYTES);
+#pragma unroll
+    for (int which = 0; which < 3; ++which)
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf)
+        tma_load_2d(sQ_a + which * OP_BYTES + hf * (TPAD * 128), &p.tmap_qkv, bar, which * d + h * DH + hf * 64, b * T);
+  }
+  const int sub = lane % VPR;
+  const float inv_sqrt_dh = p.inv_sqrt_dh;
+  float gq[8], gk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {  // the gain loads overlap the tensor loads
+    gq[j] = p.q_gain[sub * 8 + j];
+    gk[j] = p.k_gain[sub * 8 + j];
+  }
+  mbar_wait(bar, 0);
+  // ---- per-head RMSNorm of q and k in place (fp32 math, bf16 storage)
+  for (int r0 = 0; r0 < TPAD; r0 += ROWS_PER_IT) {
+    const int row = r0 + lane / VPR;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t a = attn_sw128<TPAD>(which == 0 ? sQ_a : sK_a, row, sub * 8);
+      uint4 raw;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(a));
+      float v[8];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+        ss += f.x * f.x + f.y * f.y;
+      }
+#pragma unroll
+      for (int o = VPR / 2; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rn = 1.0f / fmaxf(sqrtf(ss) * inv_sqrt_dh, p.eps);  // RMSNorm.forward, modedit.py:78-80
+      const float* g = which == 0 ? gq : gk;
+      st_shared_v4(a, pack_bf16x2((v[0] * rn) * g[0], (v[1] * rn) * g[1]), pack_bf16x2((v[2] * rn) * g[2], (v[3] * rn) * g[3]),
+                   pack_bf16x2((v[4] * rn) * g[4], (v[5] * rn) * g[5]), pack_bf16x2((v[6] * rn) * g[6], (v[7] * rn) * g[7]));
+    }
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, tq = lane & 3;
+  const float scale = inv_sqrt_dh;
+#pragma unroll 1
+  for (int mi = 0; mi < MT; ++mi) {
+    if (mi * 16 >= T) break;
+    float s[2 * MT][4];
+#pragma unroll
+    for (int nj = 0; nj < 2 * MT; ++nj) s[nj][0] = s[nj][1] = s[nj][2] = s[nj][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      uint32_t a0, a1, a2, a3;
+      ldmatrix_x4(attn_sw128<TPAD>(sQ_a, mi * 16 + (lane & 15), kk * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
+#pragma unroll
+      for (int nj = 0; nj < 2 * MT; ++nj) {
+        if (nj <= 2 * mi + 1) {
+          uint32_t b0, b1;
+          ldmatrix_x2(attn_sw128<TPAD>(sK_a, nj * 8 + (lane & 7), kk * 16 + ((lane >> 3) & 1) * 8), b0, b1);
+          mma_bf16_16816(s[nj], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+    const int row_lo = mi * 16 + g, row_hi = row_lo + 8;
+    float m_lo = -INFINITY, m_hi = -INFINITY;
+#pragma unroll
+    for (int nj = 0; nj < 2 * MT; ++nj) {
+      if (nj <= 2 * mi + 1) {
+        const int c0 = nj * 8 + 2 * tq;
+        s[nj][0] = (c0 <= row_lo) ? s[nj][0] * scale : -INFINITY;
+        s[nj][1] = (c0 + 1 <= row_lo) ? s[nj][1] * scale : -INFINITY;
+        s[nj][2] = (c0 <= row_hi) ? s[nj][2] * scale : -INFINITY;
+        s[nj][3] = (c0 + 1 <= row_hi) ? s[nj][3] * scale : -INFINITY;
+        m_lo = fmaxf(m_lo, fmaxf(s[nj][0], s[nj][1]));
+        m_hi = fmaxf(m_hi, fmaxf(s[nj][2], s[nj][3]));
+      }
+    }
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+    m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+    m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int nj = 0; nj < 2 * MT; ++nj) {
+      if (nj <= 2 * mi + 1) {
+        s[nj][0] = __expf(s[nj][0] - m_lo);
+        s[nj][1] = __expf(s[nj][1] - m_lo);
+        s[nj][2] = __expf(s[nj][2] - m_hi);
+        s[nj][3] = __expf(s[nj][3] - m_hi);
+        sum_lo += s[nj][0] + s[nj][1];
+        sum_hi += s[nj][2] + s[nj][3];
+      }
+    }
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 1);
+    sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, 2);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 1);
+    sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, 2);
+    if (p.drop.thr) {
+      const uint32_t thalf = static_cast<uint32_t>(T + 1) >> 1;
+      const uint32_t w_lo = (static_cast<uint32_t>(item) * T + row_lo) * thalf, w_hi = (static_cast<uint32_t>(item) * T + row_hi) * thalf;
+#pragma unroll
+      for (int nj = 0; nj < 2 * MT; ++nj) {
+        if (nj <= 2 * mi + 1) {
+          const uint32_t cw = static_cast<uint32_t>(nj * 4 + tq);
+          const uint32_t b_lo = rng_bits(p.drop.key, w_lo + cw), b_hi = rng_bits(p.drop.key, w_hi + cw);
+          if ((b_lo & 0xffffu) < p.drop.thr) s[nj][0] = 0.f;
+          if ((b_lo >> 16) < p.drop.thr) s[nj][1] = 0.f;
+          if ((b_hi & 0xffffu) < p.drop.thr) s[nj][2] = 0.f;
+          if ((b_hi >> 16) < p.drop.thr) s[nj][3] = 0.f;
+        }
+      }
+    }
+    float o[DH / 8][4];
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+    for (int kj = 0; kj < MT; ++kj) {
+      if (kj <= mi) {
+        const uint32_t a0 = pack_bf16x2(s[2 * kj][0], s[2 * kj][1]);
+        const uint32_t a1 = pack_bf16x2(s[2 * kj][2], s[2 * kj][3]);
+        const uint32_t a2 = pack_bf16x2(s[2 * kj + 1][0], s[2 * kj + 1][1]);
+        const uint32_t a3 = pack_bf16x2(s[2 * kj + 1][2], s[2 * kj + 1][3]);
+#pragma unroll
+        for (int dn = 0; dn < DH / 8; ++dn) {
+          uint32_t b0, b1;
+          ldmatrix_x2_trans(attn_sw128<TPAD>(sV_a, kj * 16 + (lane & 15), dn * 8), b0, b1);
+          mma_bf16_16816(o[dn], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+    const float keep_scale = p.drop.thr ? p.drop.scale : 1.0f;
+    const float inv_lo = keep_scale / sum_lo, inv_hi = keep_scale / sum_hi;
+    // stage O through this tile's (now dead) Q rows so the global store is 16-byte coalesced
+    __syncwarp();
+#pragma unroll
+    for (int dn = 0; dn < DH / 8; ++dn) {
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(attn_sw128<TPAD>(sQ_a, row_lo, dn * 8 + 2 * tq)),
+                   "r"(pack_bf16x2(o[dn][0] * inv_lo, o[dn][1] * inv_lo)) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(attn_sw128<TPAD>(sQ_a, row_hi, dn * 8 + 2 * tq)),
+                   "r"(pack_bf16x2(o[dn][2] * inv_hi, o[dn][3] * inv_hi)) : "memory");
+    }
+    __syncwarp();
+  }
+  for (int r0 = 0; r0 < TPAD; r0 += ROWS_PER_IT) {
+    const int row = r0 + lane / VPR;
+    if (row < T) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "r"(attn_sw128<TPAD>(sQ_a, row, sub * 8)));
       *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b) * T + row) * d + h * DH + sub * 8) = v;
     }
   }

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <utility>
 #include <string>
@@ -21,6 +22,7 @@
 #include "gemm_small.cuh"
 #include "mlp_fused.cuh"
 #include "rowwise.cuh"
+#include "resnet.cuh"
 #include "backward.cuh"
 #include "optimizer.cuh"
 
@@ -186,6 +188,7 @@ struct LayerIO {
   float *x_in, *x1, *xn, *x_out, *x_out_copy;
   __nv_bfloat16 *hA, *qkv, *attn, *perm, *h, *y, *z, *hA_next;
   CUtensorMap tm_hA, tm_attn, tm_perm, tm_h;          // GEMM A-operand loads
+  CUtensorMap tm_qkv_attn;                             // q|k|v boxes of the TMA-staged attention kernel
   CUtensorMap to_qkv, to_x1, to_h, to_y, to_z;         // GEMM output stores
 };
 struct TrainState;
@@ -380,6 +383,7 @@ static int set_kernel_attrs() {
   RET_IF(gemm2_set_attr<EPI_PLAIN_BF16>());
   RET_IF(gemm2_set_attr<EPI_PLAIN_F32>());
   RET_IF(gemm2_set_attr<EPI_SWIGLU_SAVE>());
+  RET_IF(gemm2_set_attr<EPI_CONV_BF16>());
   RET_IF(gemm_set_attr<EPI_BIAS_BF16>());
   RET_IF(gemm_set_attr<EPI_RESID_F32>());
   RET_IF(gemm_set_attr<EPI_SWIGLU_BF16>());
@@ -403,6 +407,7 @@ static int launch_gemm(int epi, bool pair, int num_sms, cudaStream_t st, const G
       case EPI_PLAIN_BF16: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_PLAIN_BF16>, grid, block, G2_SMEM_BYTES, st, p)); break;
       case EPI_PLAIN_F32: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_PLAIN_F32>, grid, block, G2_SMEM_BYTES, st, p)); break;
       case EPI_SWIGLU_SAVE: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_SWIGLU_SAVE>, grid, block, G2_SMEM_BYTES, st, p)); break;
+      case EPI_CONV_BF16: CU_OK(launch_k(gemm_tcgen05_2cta_kernel<EPI_CONV_BF16>, grid, block, G2_SMEM_BYTES, st, p)); break;
       default: return fail(MODE_ERR_INVALID, "unknown GEMM epilogue %d", epi);
     }
   } else {
@@ -465,9 +470,41 @@ static int launch_attn_t(cudaStream_t st, const AttnParams& p) {
   CU_OK(cudaGetLastError());
   return MODE_OK;
 }
+// TMA-staged attention (attention_tma_kernel, the default for head dims 64 / 128; MODE_ATTN_TMA=0 selects the cp.async
+// staging of attention_kernel). p.tmap_qkv must describe p.qkv with a {64, 16*MT}-box (make_attn_tmap).
+static bool attn_tma_enabled() {
+  static const bool on = !(getenv("MODE_ATTN_TMA") && atoi(getenv("MODE_ATTN_TMA")) == 0);
+  return on;
+}
+template <int DH, int MT>
+static int launch_attn_tma_t(cudaStream_t st, const AttnParams& p) {
+  constexpr int smem = ATTN_WARPS * 3 * (16 * MT) * DH * 2 + 8 * ATTN_WARPS;
+  static bool attr = false;
+  if (!attr) {
+    CU_OK(cudaFuncSetAttribute(attention_tma_kernel<DH, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  if (p.B == 0) return MODE_OK;
+  const int items = p.B * p.H;
+  CU_OK(launch_k(attention_tma_kernel<DH, MT>, dim3((items + ATTN_WARPS - 1) / ATTN_WARPS), dim3(ATTN_WARPS * 32), smem, st, p));
+  CU_OK(cudaGetLastError());
+  return MODE_OK;
+}
 template <int DH>
 static int launch_attn_dh(cudaStream_t st, const AttnParams& p) {
   const int mt = (p.T + 15) / 16;
+  if constexpr (DH >= 64) {
+    if (attn_tma_enabled()) {
+      switch (mt) {
+        case 1: RET_IF((launch_attn_tma_t<DH, 1>(st, p))); break;
+        case 2: RET_IF((launch_attn_tma_t<DH, 2>(st, p))); break;
+        case 3: RET_IF((launch_attn_tma_t<DH, 3>(st, p))); break;
+        case 4: RET_IF((launch_attn_tma_t<DH, 4>(st, p))); break;
+        default: return fail(MODE_ERR_INVALID, "attention supports T <= 64 tokens (got %d)", p.T);
+      }
+      return MODE_OK;
+    }
+  }
   switch (mt) {
     case 1: return launch_attn_t<DH, 1>(st, p);
     case 2: return launch_attn_t<DH, 2>(st, p);
@@ -829,6 +866,7 @@ static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
     io.z = nullptr;
     io.tm_hA = e->tm_hA; io.tm_attn = e->tm_attn; io.tm_perm = e->tm_perm; io.tm_h = e->tm_h;
     io.to_qkv = e->to_qkv; io.to_x1 = e->to_x; io.to_h = e->to_h; io.to_y = e->to_y;
+    RET_IF(make_tmap(&io.tm_qkv_attn, e->qkv, rows[0], 3 * e->d, 16 * ((e->T + 15) / 16)));
   }
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);  // captured kernels embed the old maps
   e->graphs.clear();
@@ -854,6 +892,7 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.out_ptr = nullptr;
   p.ldo = 0;
   p.out_rows = 0;
+  p.conv = ConvEpilogue{nullptr, 0, 0, nullptr, nullptr, 1, 0};
   p.k_blocks = Kdim / GEMM_BLOCK_K;
   p.bias = bias;
   p.w_row_off = 0;
@@ -1056,6 +1095,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     else if (!(skip >> PC_QKV & 1)) RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
   }
   AttnParams a;
+  a.tmap_qkv = io.tm_qkv_attn;
   a.qkv = io.qkv; a.out = io.attn; a.q_gain = e->qn_g + (size_t)l * e->Dh; a.k_gain = e->kn_g + (size_t)l * e->Dh;
   a.B = B; a.T = e->T; a.H = e->H; a.eps = e->cfg.rms_eps; a.inv_sqrt_dh = e->inv_sqrt_dh;
   a.drop = dropout_spec(e, e->stoch.p_attn, RNG_ATTN, l);
@@ -1678,7 +1718,9 @@ extern "C" int mode_debug_attention(const void* qkv_dev, const float* q_gain_dev
   a.out = reinterpret_cast<__nv_bfloat16*>(out_dev);
   a.q_gain = q_gain_dev; a.k_gain = k_gain_dev; a.B = B; a.T = T; a.H = H; a.eps = eps;
   a.inv_sqrt_dh = static_cast<float>(pow(static_cast<double>(Dh), -0.5));
+  if (Dh >= 64 && T <= 64) RET_IF(make_tmap(&a.tmap_qkv, qkv_dev, (uint64_t)B * T, (uint64_t)3 * H * Dh, 16 * ((T + 15) / 16)));
   return launch_attn(reinterpret_cast<cudaStream_t>(stream), a, Dh);
 }
 
 #include "train.inc"
+#include "resnet.inc"

@@ -40,6 +40,18 @@ enum GemmEpilogue : int {
   EPI_PLAIN_BF16 = 3,   // out_bf16 = acc                                      (expert down-projection)
   EPI_PLAIN_F32 = 4,    // out_f32  = acc                                      (obs/goal token embeddings)
   EPI_SWIGLU_SAVE = 5,  // EPI_SWIGLU_BF16 + the pre-activations z = acc + bias -> tmap_out2 (training forward)
+  EPI_CONV_BF16 = 6,    // out_bf16 = film(relu(acc + bias + residual))  (FiLM-ResNet convolutions as GEMMs, resnet.inc)
+};
+// Extras of EPI_CONV_BF16: folded-BatchNorm bias comes through GemmParams::bias; optional residual (identity / projected
+// shortcut of a bottleneck), ReLU, and FiLM (1 + gamma[n, c]) * v + beta[n, c] with n = row / film_hw (reference
+// pretrained_resnets.py:19-23, applied to the output of each ResNet stage).
+struct ConvEpilogue {
+  const __nv_bfloat16* res;  // [rows, ld_res] or nullptr
+  int ld_res;
+  int relu;
+  const float* film_g;       // [images, film_c] or nullptr
+  const float* film_b;
+  int film_hw, film_c;
 };
 
 // One M-tile of work. For grouped GEMMs consecutive tiles may belong to different experts.
@@ -78,6 +90,7 @@ struct alignas(64) GemmParams {
   // 4 / 12), which changes which tile an output column belongs to but not the order in which its K terms are summed.
   // n_blocks = ceil(n_total / bn); tmap_w has a bn/2-row box; columns [bn/64*64, bn) of a tile (bf16 outputs; bn/32*32
   // for fp32) are stored straight from registers through out_ptr, everything else through tmap_out as before.
+  ConvEpilogue conv;           // EPI_CONV_BF16 only
   int bn;
   int n_total;                 // N of the whole GEMM (output columns / weight rows per problem)
   void* out_ptr;               // raw output base, row stride ldo elements, rows >= out_rows are never written
@@ -89,6 +102,7 @@ struct EpiGeom {
   int n_total = 0x7fffffff;
   void* out = nullptr;
   int ldo = 0, out_rows = 0;
+  ConvEpilogue conv = ConvEpilogue{nullptr, 0, 0, nullptr, nullptr, 1, 0};
 };
 
 // Work decomposition of the CTA-pair kernel. Tiles of full waves are data-parallel (tile = worker + i * P). The last,
@@ -276,6 +290,65 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
       }
       end_chunk(buf, nb * 128 + c * 64);
     }
+  } else if constexpr (EPI == EPI_CONV_BF16) {
+    const int col0 = nb * g.bn;
+    const int nfull = g.bn >> 6;  // convolution widths are multiples of 64
+    const int row = out_row0 + lane;
+    const bool row_ok = row < g.out_rows;
+    const int img = row_ok ? row / g.conv.film_hw : 0;
+#pragma unroll 1
+    for (int c = 0; c < nfull; ++c) {
+      if (col0 + c * 64 >= g.n_total) break;
+      const uint32_t buf = begin_chunk();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c32 = c * 64 + hh * 32;
+        uint32_t r[32];
+        load_acc32(taddr + c32, r, sk, c32 / 32);
+        const float4* b = reinterpret_cast<const float4*>(sbias + c32);
+        const uint4* rs = (g.conv.res && row_ok)
+                              ? reinterpret_cast<const uint4*>(g.conv.res + static_cast<size_t>(row) * g.conv.ld_res + col0 + c32)
+                              : nullptr;
+        const float4* fg = (g.conv.film_g && row_ok)
+                               ? reinterpret_cast<const float4*>(g.conv.film_g + static_cast<size_t>(img) * g.conv.film_c + col0 + c32)
+                               : nullptr;
+        const float4* fb = fg ? reinterpret_cast<const float4*>(g.conv.film_b + static_cast<size_t>(img) * g.conv.film_c + col0 + c32)
+                              : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[8];
+          const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
+          v[0] = __uint_as_float(r[8 * j + 0]) + b0.x; v[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
+          v[2] = __uint_as_float(r[8 * j + 2]) + b0.z; v[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
+          v[4] = __uint_as_float(r[8 * j + 4]) + b1.x; v[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
+          v[6] = __uint_as_float(r[8 * j + 6]) + b1.z; v[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
+          if (rs) {
+            const uint4 q = __ldg(rs + j);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = __bfloat1622float2(h2[u]);
+              v[2 * u] += f.x;
+              v[2 * u + 1] += f.y;
+            }
+          }
+          if (g.conv.relu) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
+          }
+          if (fg) {
+            const float4 g0 = __ldg(fg + 2 * j), g1 = __ldg(fg + 2 * j + 1), e0 = __ldg(fb + 2 * j), e1 = __ldg(fb + 2 * j + 1);
+            v[0] = fmaf(1.f + g0.x, v[0], e0.x); v[1] = fmaf(1.f + g0.y, v[1], e0.y);
+            v[2] = fmaf(1.f + g0.z, v[2], e0.z); v[3] = fmaf(1.f + g0.w, v[3], e0.w);
+            v[4] = fmaf(1.f + g1.x, v[4], e1.x); v[5] = fmaf(1.f + g1.y, v[5], e1.y);
+            v[6] = fmaf(1.f + g1.z, v[6], e1.z); v[7] = fmaf(1.f + g1.w, v[7], e1.w);
+          }
+          st_shared_v4(chunk_addr(buf, hh * 4 + j), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                       pack_bf16x2(v[6], v[7]));
+        }
+      }
+      end_chunk(buf, col0 + c * 64);
+    }
   } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_PLAIN_BF16) {
     const int col0 = nb * g.bn;
     const int nfull = g.bn >> 6;
@@ -371,7 +444,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
 // the global-load latency hides behind the tile's MMAs; named barrier 1 (epilogue warps only) publishes them.
 template <int EPI>
 __device__ __forceinline__ void stage_bias(const GemmParams& p, float* sbias, int w_row, int epi_tid, int col0 = 0) {
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_SWIGLU_SAVE) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_SWIGLU_SAVE || EPI == EPI_CONV_BF16) {
     // entries past the tile width or past the matrix edge (an overhanging last tile) are never used: read nothing there
     const int j0 = epi_tid, j1 = 128 + epi_tid;
     sbias[j0] = (j0 < p.bn && col0 + j0 < p.n_total) ? __ldg(p.bias + w_row + j0) : 0.f;
@@ -397,7 +470,7 @@ __device__ __forceinline__ void gemm_epilogue_dispatch(const GemmParams& p, uint
     }
   } else {
     gemm_epilogue_warp<EPI>(&p.tmap_out, taddr, stage_smem, lane, out_row0, sbias, nb, n_stores, sk, EpiDrop{0, 0, 0, 1.0f},
-                            EpiGeom{p.bn, p.n_total, p.out_ptr, p.ldo, p.out_rows});
+                            EpiGeom{p.bn, p.n_total, p.out_ptr, p.ldo, p.out_rows, p.conv});
   }
 }
 
