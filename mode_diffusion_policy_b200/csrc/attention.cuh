@@ -56,16 +56,16 @@ struct alignas(64) AttnParams {
 };
 
 // DH: head dim (32/64/128). MT: number of 16-row tiles covering T (T_pad = 16*MT).
+// Body of attention_kernel for virtual block `vblock` with `n_warps` warps per CTA and `attn_smem` holding
+// n_warps * 3 * 16*MT * (DH + 8) bf16 (also a phase of the persistent small-batch kernel, small_eval.cuh).
 template <int DH, int MT>
-__global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnParams p) {
-  pdl_trigger();
+__device__ __forceinline__ void attention_body(const AttnParams& p, int vblock, int n_warps, uint8_t* attn_smem) {
   constexpr int TPAD = 16 * MT;
   constexpr int LDS = DH + 8;            // padded row (bf16 elements): conflict-free ldmatrix
   constexpr int VPR = DH / 8;            // 16-byte vectors per row
   constexpr int ROWS_PER_IT = 32 / VPR;  // rows covered by one warp-wide vector load
-  extern __shared__ __align__(16) uint8_t attn_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * ATTN_WARPS + warp;  // (b, h)
+  const int item = vblock * n_warps + warp;  // (b, h)
   if (item >= p.B * p.H) return;
   const int b = item / p.H, h = item % p.H;
   const int T = p.T, d = p.H * DH;
@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
   __nv_bfloat16* sK = sQ + TPAD * LDS;
   __nv_bfloat16* sV = sK + TPAD * LDS;
 
-  pdl_wait();
   // ---- stage q, k, v into shared memory: all rows are requested up front with cp.async (no register staging, the
   //      whole 3 x T x Dh tile is in flight at once), then q and k are RMS-normalised in place
   const int sub = lane % VPR;  // vector index inside the row
@@ -244,6 +243,14 @@ __global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnPa
       *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b) * T + row) * d + h * DH + sub * 8) = v;
     }
   }
+}
+
+template <int DH, int MT>
+__global__ void __launch_bounds__(ATTN_WARPS * 32) attention_kernel(const AttnParams p) {
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  pdl_wait();
+  attention_body<DH, MT>(p, blockIdx.x, ATTN_WARPS, attn_smem);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -42,20 +42,18 @@ __device__ __forceinline__ void mma_bf16_16816_acc(float (&c)[4], uint32_t a0, u
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// grid (N / 8 column slabs [hidden units / 8 for SwiGLU], max M-tiles); 256 threads. MT = 16-row tiles per group
-// (1 or 2): every weight fragment a lane loads is used for all MT row tiles.
-template <int EPI, int MT>
-__global__ void __launch_bounds__(SMALL_M_WARPS * 32) gemm_small_m_kernel(const SmallGemmParams p) {
-  pdl_trigger();
+// Body for one (slab, group) task. `red_raw`: SMALL_M_WARPS * NACC * MT*128 floats of shared memory. COHERENT_A: the A rows
+// were written earlier in the SAME kernel launch (persistent small-batch kernel, small_eval.cuh) and must not be read
+// through the non-coherent path; weights always are. All threads of the CTA call this together (it synchronises).
+template <int EPI, int MT, bool COHERENT_A>
+__device__ __forceinline__ void gemm_small_body(const SmallGemmParams& p, int slab, int group, float* red_raw) {
   constexpr bool GLU = (EPI == EPI_SWIGLU_BF16);
   constexpr int NACC = GLU ? 2 : 1;
-  __shared__ float red[SMALL_M_WARPS][NACC][MT * 16 * 8];
+  float (*red)[NACC][MT * 16 * 8] = reinterpret_cast<float (*)[NACC][MT * 16 * 8]>(red_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
-  pdl_wait();
-  if (static_cast<int>(blockIdx.y) >= *p.num_m_tiles) return;
-  const GemmMTile tile = p.m_tiles[blockIdx.y];
-  const int slab = blockIdx.x;  // 8 output columns (or hidden units)
+  if (group >= *p.num_m_tiles) return;
+  const GemmMTile tile = p.m_tiles[group];
   // weight rows streamed by this lane (row g of the slab; SwiGLU: the projected row and its gate row 128 further)
   int w_row = p.w_row_off + tile.w_row_base;
   if (GLU)
@@ -79,8 +77,10 @@ __global__ void __launch_bounds__(SMALL_M_WARPS * 32) gemm_small_m_kernel(const 
     if (GLU) gv = __ldg(reinterpret_cast<const uint4*>(w1 + k0 + kc));
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      const uint4 al = __ldg(reinterpret_cast<const uint4*>(a_lo + static_cast<size_t>(m * 16) * p.K + k0 + kc));
-      const uint4 ah = __ldg(reinterpret_cast<const uint4*>(a_lo + static_cast<size_t>(m * 16 + 8) * p.K + k0 + kc));
+      const uint4* pl = reinterpret_cast<const uint4*>(a_lo + static_cast<size_t>(m * 16) * p.K + k0 + kc);
+      const uint4* ph = reinterpret_cast<const uint4*>(a_lo + static_cast<size_t>(m * 16 + 8) * p.K + k0 + kc);
+      const uint4 al = COHERENT_A ? *pl : __ldg(pl);
+      const uint4 ah = COHERENT_A ? *ph : __ldg(ph);
       mma_bf16_16816_acc(acc[m][0], al.x, ah.x, al.y, ah.y, wv.x, wv.y);
       mma_bf16_16816_acc(acc[m][0], al.z, ah.z, al.w, ah.w, wv.z, wv.w);
       if (GLU) {
@@ -129,6 +129,17 @@ __global__ void __launch_bounds__(SMALL_M_WARPS * 32) gemm_small_m_kernel(const 
     reinterpret_cast<float*>(p.out)[o] = v[0];
   }
   }
+  __syncthreads();  // `red` is reused by the caller's next task
+}
+
+// grid (N / 8 column slabs [hidden units / 8 for SwiGLU], max M-tiles); 256 threads. MT = 16-row tiles per group
+// (1 or 2): every weight fragment a lane loads is used for all MT row tiles.
+template <int EPI, int MT>
+__global__ void __launch_bounds__(SMALL_M_WARPS * 32) gemm_small_m_kernel(const SmallGemmParams p) {
+  pdl_trigger();
+  __shared__ float red[SMALL_M_WARPS * (EPI == EPI_SWIGLU_BF16 ? 2 : 1) * MT * 16 * 8];
+  pdl_wait();
+  gemm_small_body<EPI, MT, false>(p, blockIdx.x, blockIdx.y, red);
 }
 
 }  // namespace mode

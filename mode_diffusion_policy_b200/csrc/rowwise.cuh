@@ -84,11 +84,10 @@ __device__ __forceinline__ float4 dropout_mask4(const DropoutSpec& d, uint32_t e
                      (b1 & 0xffffu) < d.thr ? 0.f : d.scale, (b1 >> 16) < d.thr ? 0.f : d.scale);
 }
 
+// body of embed_kernel for virtual block `vblock` (also a phase of the persistent small-batch kernel, small_eval.cuh)
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedParams p) {
-  pdl_trigger();
-  pdl_wait();
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void embed_body(const EmbedParams& p, int vblock) {
+  const int row = vblock * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
   const int b = row / p.T, t = row % p.T;
@@ -161,6 +160,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedPar
           make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
     }
   }
+}
+template <int NVEC>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) embed_kernel(const EmbedParams p) {
+  pdl_trigger();
+  pdl_wait();
+  embed_body<NVEC>(p, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -587,13 +592,12 @@ struct Ln2Params {
 };
 // (B, T) of the routed kernels are ROUTING units x rows per unit: (samples, tokens per sample) when all tokens of a
 // sample share their experts (eval / arg-max routing), (B*T tokens, 1) under per-token multinomial routing.
+// body of ln2_permute_kernel for virtual block `vblock` (also a phase of the persistent small-batch kernel, small_eval.cuh)
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln2Params p) {
-  pdl_trigger();
-  pdl_wait();
-  if (blockIdx.x == 0 && p.zero)
+__device__ __forceinline__ void ln2_permute_body(const Ln2Params& p, int vblock) {
+  if (vblock == 0 && p.zero)
     for (int i = threadIdx.x; i < p.n_zero; i += ROW_WARPS * 32) p.zero[i] = 0;
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int row = vblock * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
   const int b = row / p.T, t = row % p.T - p.t_skip;
@@ -631,6 +635,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln
       if (k < p.K) p.row_token[dst_row[k]] = row;
   }
 }
+template <int NVEC>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln2Params p) {
+  pdl_trigger();
+  pdl_wait();
+  ln2_permute_body<NVEC>(p, blockIdx.x);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Expert combine (+ next layer's ln_1 + c): x <- xn + sum_k w_k * y[pos_k]  accumulated in ascending expert order
@@ -655,11 +665,10 @@ struct CombineParams {
   float eps;
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
+// body of combine_kernel for virtual block `vblock` (also a phase of the persistent small-batch kernel, small_eval.cuh)
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const CombineParams p) {
-  pdl_trigger();
-  pdl_wait();
-  const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void combine_body(const CombineParams& p, int vblock) {
+  const int row = vblock * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
   const int b = row / p.T, t = row % p.T - p.t_skip;
@@ -715,6 +724,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const Combin
       }
     }
 }
+template <int NVEC>
+__global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const CombineParams p) {
+  pdl_trigger();
+  pdl_wait();
+  combine_body<NVEC>(p, blockIdx.x);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Output head + EDM preconditioning + sampler update, one warp per action token:
@@ -748,11 +763,10 @@ struct HeadParams {
   const float* noise;      // this evaluation's noise tensor or nullptr
 };
 constexpr int HEAD_PROG_FLOATS = 16;
+// body of head_kernel for virtual block `vblock` (also a phase of the persistent small-batch kernel, small_eval.cuh)
 template <int NVEC>
-__global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p) {
-  pdl_trigger();
-  pdl_wait();
-  const int item = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void head_body(const HeadParams& p, int vblock) {
+  const int item = vblock * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (item >= p.B * p.A) return;
   const int b = item / p.A, j = item % p.A;
@@ -833,6 +847,12 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p
     sq = warp_sum(sq);
     if (lane == 0) p.tok_sqerr[item] = sq;
   }
+}
+template <int NVEC>
+__global__ void __launch_bounds__(ROW_WARPS * 32) head_kernel(const HeadParams p) {
+  pdl_trigger();
+  pdl_wait();
+  head_body<NVEC>(p, blockIdx.x);
 }
 
 // Deterministic mean of the per-token squared errors: loss = sum / (B*A*action_dim)  (.pow(2).flatten(1).mean()).
