@@ -23,6 +23,7 @@
 #include "mlp_fused.cuh"
 #include "rowwise.cuh"
 #include "resnet.cuh"
+#include "small_eval.cuh"
 #include "backward.cuh"
 #include "optimizer.cuh"
 
@@ -222,6 +223,12 @@ struct mode_engine {
   float *x, *cvec, *xnorm, *state_tok, *goal_tok, *x_work, *sig_dev, *coefs_dev, *tok_sqerr, *zbuf;
   float* d_prev;  // previous step's denoised actions (multistep samplers)
   float *x_probe = nullptr, *hist = nullptr, *prog_dev = nullptr, *noise_buf = nullptr;  // sampler programs (mode_sample_program)
+  // persistent small-batch kernel (small_eval.cuh): phase tables per sampler loop, recorded by the enqueue functions
+  std::vector<SmallPhase>* rec = nullptr;                 // non-null while a table is being recorded (nothing is launched)
+  struct SmallProgram { SmallPhase* dev; int n; };
+  std::map<std::string, SmallProgram> small_programs;
+  unsigned* small_barrier = nullptr;
+  bool small_fused = false;                               // MODE_SMALL_FUSED=1 opts in (measured slower, see mode_create)
   std::map<std::string, cudaGraphExec_t> prog_graphs;
   std::map<std::string, int64_t> prog_graph_launches;
   float *in_state, *in_goal, *in_x;  // device staging of the *_host entry points
@@ -545,6 +552,7 @@ extern "C" void mode_destroy(mode_engine_t* e) {
   destroy_train(e->train);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
   for (auto& g : e->prog_graphs) cudaGraphExecDestroy(g.second);
+  for (auto& sp : e->small_programs) cudaFree(sp.second.dev);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->weights_ready) cudaEventDestroy(e->weights_ready);
   for (void* p : e->allocs) cudaFree(p);
@@ -600,6 +608,10 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
     e->small_m = !(small_env && atoi(small_env) == 0);
     const char* trim_env = getenv("MODE_TRIM_LAST");
     e->trim_rows = (trim_env && atoi(trim_env) == 0) ? 0 : e->A;
+    // persistent one-launch sampler for B <= 2 (small_eval.cuh): correct (tested) but measured SLOWER than the CUDA graph of
+    // per-phase kernels on B200 (8.6 vs 7.2 ms per 10-step sample at B = 1, profiles/r02_small_fused.log) -> opt-in
+    const char* sf_env = getenv("MODE_SMALL_FUSED");
+    e->small_fused = sf_env && atoi(sf_env) != 0;
     env = getenv("MODE_MLP_FUSED");
     e->mlp_fused = e->pair && (env ? atoi(env) != 0 : false);  // measured +1.5 % only: opt-in
   }
@@ -874,6 +886,8 @@ static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
   for (auto& g : e->prog_graphs) cudaGraphExecDestroy(g.second);
   e->prog_graphs.clear();
   e->prog_graph_launches.clear();
+  for (auto& sp : e->small_programs) cudaFree(sp.second.dev);
+  e->small_programs.clear();
   e->cur_B = B;
   return MODE_OK;
 }
@@ -979,6 +993,33 @@ static void enable_stream_k(mode_engine* e, GemmParams& p) {
   } while (0)
 
 static inline unsigned row_blocks(int rows) { return (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS); }
+
+// ---- recording of the persistent small-batch kernel's phase table (small_eval.cuh)
+template <typename P>
+static void rec_phase(mode_engine* e, int kind, const P& params, int ntasks, int epi = 0, int slabs = 1) {
+  static_assert(sizeof(P) <= SMALL_PHASE_RAW, "parameter struct does not fit a phase descriptor");
+  SmallPhase ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.kind = kind; ph.ntasks = ntasks; ph.epi = epi; ph.slabs = slabs;
+  memcpy(ph.raw, &params, sizeof(P));
+  e->rec->push_back(ph);
+}
+// LAUNCH_ROW_KERNEL or, while recording, one phase of `kind`
+#define ROW_PHASE(KIND, KERNEL, d, grid, st, params)                  \
+  do {                                                                \
+    if (e->rec)                                                       \
+      rec_phase(e, (KIND), (params), (int)(grid));                    \
+    else                                                              \
+      LAUNCH_ROW_KERNEL(KERNEL, d, grid, st, params);                 \
+  } while (0)
+static int small_gemm(mode_engine* e, int epi, cudaStream_t st, const SmallGemmParams& p, int n_cols, int max_tiles, int max_rows) {
+  if (e->rec) {
+    const int per = small_slabs_per_task(epi), slabs = n_cols / 8;
+    rec_phase(e, SP_GEMM, p, ((slabs + per - 1) / per) * max_tiles, epi, slabs);
+    return MODE_OK;
+  }
+  return launch_gemm_small(epi, st, p, n_cols, max_tiles, max_rows);
+}
 
 // obs / goal token embeddings: computed once per trajectory, not per denoising step.
 static int enqueue_cond(mode_engine* e, cudaStream_t st, int B, const float* state_dev, const float* goal_dev) {
@@ -1090,7 +1131,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   {
     ProfScope ps(e, st, PC_QKV);
     if (small)
-      RET_IF(launch_gemm_small(EPI_BIAS_BF16, st, small_params(io.hA, e->w_qkv, d, e->dense_tiles, e->dense_counts, e->b_qkv,
+      RET_IF(small_gemm(e, EPI_BIAS_BF16, st, small_params(io.hA, e->w_qkv, d, e->dense_tiles, e->dense_counts, e->b_qkv,
                                                                io.qkv, 3 * d, l * 3 * d), 3 * d, 1, M));
     else if (!(skip >> PC_QKV & 1)) RET_IF(launch_gemm(EPI_BIAS_BF16, e->pair, e->num_sms, st, p));
   }
@@ -1101,7 +1142,9 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   a.drop = dropout_spec(e, e->stoch.p_attn, RNG_ATTN, l);
   {
     ProfScope ps(e, st, PC_ATTN);
-    if (!(skip >> PC_ATTN & 1)) RET_IF(launch_attn(st, a, e->Dh));
+    if (e->rec)
+      rec_phase(e, SP_ATTN, a, (B * e->H + SMALL_M_WARPS - 1) / SMALL_M_WARPS);
+    else if (!(skip >> PC_ATTN & 1)) RET_IF(launch_attn(st, a, e->Dh));
   }
   p = gemm_params(io.tm_attn, e->tm_wproj, io.to_x1, e->dense_tiles, e->dense_counts, d, d, nullptr);  // x1 += acc
   p.w_row_off = l * d;
@@ -1110,7 +1153,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   {
     ProfScope ps(e, st, PC_PROJ);
     if (small)
-      RET_IF(launch_gemm_small(EPI_RESID_F32, st, small_params(io.attn, e->w_proj, d, e->dense_tiles, e->dense_counts, nullptr,
+      RET_IF(small_gemm(e, EPI_RESID_F32, st, small_params(io.attn, e->w_proj, d, e->dense_tiles, e->dense_counts, nullptr,
                                                                io.x1, d, l * d), d, 1, M));
     else if (!(skip >> PC_PROJ & 1)) RET_IF(launch_gemm(EPI_RESID_F32, e->pair, e->num_sms, st, p));
   }
@@ -1128,7 +1171,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   n2.n_zero = 1 + e->max_tiles;
   {
     ProfScope ps(e, st, PC_LN2);
-    if (!(skip >> PC_LN2 & 1)) LAUNCH_ROW_KERNEL(ln2_permute_kernel, d, row_blocks(M), st, n2);
+    if (!(skip >> PC_LN2 & 1)) ROW_PHASE(SP_LN2, ln2_permute_kernel, d, row_blocks(M), st, n2);
   }
   CU_OK(cudaGetLastError());
   p = gemm_params(io.tm_perm, e->tm_wup, io.to_h, e->up_tiles + lt * e->max_tiles, e->num_tiles + lt, 8 * d, d,
@@ -1156,7 +1199,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
         p.drop = mlp_drop; p.row_token = row_token; p.drop_rows_per_expert = 8 * d; p.drop_E = e->E; p.drop_half_F = e->F / 2;
         RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
       } else if (small) {
-        RET_IF(launch_gemm_small(EPI_SWIGLU_BF16, st, small_params(io.perm, e->w_up, d, e->up_tiles + lt * e->max_tiles,
+        RET_IF(small_gemm(e, EPI_SWIGLU_BF16, st, small_params(io.perm, e->w_up, d, e->up_tiles + lt * e->max_tiles,
                                                                    e->num_tiles + lt, e->b_up, io.h, e->F, 0), e->F, small_groups, M));
       } else if (!(skip >> PC_UP & 1)) {
         RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
@@ -1172,7 +1215,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     {
       ProfScope ps(e, st, PC_DOWN);
       if (small)
-        RET_IF(launch_gemm_small(EPI_PLAIN_BF16, st, small_params(io.h, e->w_down, e->F, e->down_tiles + lt * e->max_tiles,
+        RET_IF(small_gemm(e, EPI_PLAIN_BF16, st, small_params(io.h, e->w_down, e->F, e->down_tiles + lt * e->max_tiles,
                                                                   e->num_tiles + lt, nullptr, io.y, d, 0), d, small_groups, M));
       else if (!(skip >> PC_DOWN & 1)) RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
     }
@@ -1186,7 +1229,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   c.B = rv.units; c.T = rv.rt; c.Tc = e->T; c.K = e->K; c.d = d; c.mode = combine_mode; c.eps = e->cfg.rms_eps; c.inv_sqrt_d = e->inv_sqrt_d;
   {
     ProfScope ps(e, st, PC_COMBINE);
-    if (!(skip >> PC_COMBINE & 1)) LAUNCH_ROW_KERNEL(combine_kernel, d, row_blocks(M), st, c);
+    if (!(skip >> PC_COMBINE & 1)) ROW_PHASE(SP_COMBINE, combine_kernel, d, row_blocks(M), st, c);
   }
   CU_OK(cudaGetLastError());
   e->launch_count += fused_mlp ? 6 : 7;
@@ -1216,7 +1259,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   em.drop = dropout_spec(e, e->stoch.p_embed, RNG_EMBED, 0);
   {
     ProfScope ps(e, st, PC_EMBED);
-    LAUNCH_ROW_KERNEL(embed_kernel, e->d, row_blocks(B * e->T), st, em);
+    ROW_PHASE(SP_EMBED, embed_kernel, e->d, row_blocks(B * e->T), st, em);
   }
   CU_OK(cudaGetLastError());
   for (int l = 0; l < e->L; ++l)
@@ -1233,7 +1276,7 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   h.B = B; h.T = e->T; h.A = e->A; h.action_dim = e->adim; h.d = e->d; h.mode = head_mode;
   {
     ProfScope ps(e, st, PC_HEAD);
-    LAUNCH_ROW_KERNEL(head_kernel, e->d, row_blocks(B * e->A), st, h);
+    ROW_PHASE(SP_HEAD, head_kernel, e->d, row_blocks(B * e->A), st, h);
   }
   CU_OK(cudaGetLastError());
   e->launch_count += 2;
@@ -1314,6 +1357,65 @@ extern "C" int mode_loss(mode_engine_t* e, const float* state_dev, const float* 
   return MODE_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent small-batch kernel
+static bool small_fused_ok(const mode_engine* e, int B) {
+  const int M = B * e->T, nvec = e->d / 128;
+  return e->small_fused && e->small_m && M <= SMALL_M_MAX_ROWS && e->T <= 16 && e->d % 256 == 0 &&
+         ((nvec == 2 && e->Dh == 64) || (nvec == 4 && e->Dh == 128) || (nvec == 8 && e->Dh == 128));
+}
+template <int NVEC, int DH, int MT>
+static int launch_small_eval_t(mode_engine* e, cudaStream_t st, const mode_engine::SmallProgram& prog) {
+  static int grid = 0;
+  constexpr int smem = small_eval_smem_bytes<DH, MT>();
+  if (!grid) {
+    CU_OK(cudaFuncSetAttribute(small_eval_kernel<NVEC, DH, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    CU_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, small_eval_kernel<NVEC, DH, MT>, SMALL_EVAL_THREADS, smem));
+    if (occ < 1) return fail(MODE_ERR_CUDA, "small-batch kernel does not fit on an SM");
+    grid = e->num_sms * occ;  // all CTAs resident at once: required by the grid barrier (cooperative launch checks it)
+  }
+  CU_OK(cudaMemsetAsync(e->small_barrier, 0, sizeof(unsigned), st));
+  const SmallPhase* dev = prog.dev;
+  int n = prog.n;
+  unsigned* bar = e->small_barrier;
+  void* args[] = {(void*)&dev, (void*)&n, (void*)&bar};
+  CU_OK(cudaLaunchCooperativeKernel((const void*)small_eval_kernel<NVEC, DH, MT>, dim3(grid), dim3(SMALL_EVAL_THREADS), args, smem, st));
+  return MODE_OK;
+}
+static int launch_small_eval(mode_engine* e, cudaStream_t st, const mode_engine::SmallProgram& prog, int B) {
+  const int nvec = e->d / 128;
+  const bool two = B * e->T > 16;
+  if (nvec == 2) return two ? launch_small_eval_t<2, 64, 2>(e, st, prog) : launch_small_eval_t<2, 64, 1>(e, st, prog);
+  if (nvec == 4) return two ? launch_small_eval_t<4, 128, 2>(e, st, prog) : launch_small_eval_t<4, 128, 1>(e, st, prog);
+  return two ? launch_small_eval_t<8, 128, 2>(e, st, prog) : launch_small_eval_t<8, 128, 1>(e, st, prog);
+}
+// Records (once per key) the phase table of `n_evals` network evaluations; eval_fn(i) enqueues evaluation i.
+template <typename F>
+static int get_small_program(mode_engine* e, const std::string& key, int n_evals, F eval_fn, mode_engine::SmallProgram* out) {
+  auto it = e->small_programs.find(key);
+  if (it != e->small_programs.end()) {
+    *out = it->second;
+    return MODE_OK;
+  }
+  if (!e->small_barrier) RET_IF(dev_alloc(e, &e->small_barrier, 1));
+  std::vector<SmallPhase> v;
+  e->rec = &v;
+  int rc = MODE_OK;
+  for (int i = 0; i < n_evals && rc == MODE_OK; ++i) rc = eval_fn(i);
+  e->rec = nullptr;
+  RET_IF(rc);
+  mode_engine::SmallProgram pr;
+  pr.n = (int)v.size();
+  void* q = nullptr;
+  CU_OK(cudaMalloc(&q, v.size() * sizeof(SmallPhase)));
+  pr.dev = reinterpret_cast<SmallPhase*>(q);
+  CU_OK(cudaMemcpy(pr.dev, v.data(), v.size() * sizeof(SmallPhase), cudaMemcpyHostToDevice));
+  e->small_programs[key] = pr;
+  *out = pr;
+  return MODE_OK;
+}
+
 // head_mode: 2 DDIM, 4 Euler, 5 DPM-Solver++(2M) (HeadParams::mode)
 static int get_sampler_graph(mode_engine* e, int B, int n, int head_mode, cudaGraphExec_t* exec) {
   const auto key = std::make_pair(B, n + 128 * head_mode);
@@ -1391,7 +1493,17 @@ extern "C" int mode_sample(mode_engine_t* e, int sampler, const float* state_dev
   e->launch_count = 0;
   cudaGraphExec_t exec = nullptr;
   const int head_mode = sampler == MODE_SAMPLER_DDIM ? 2 : (sampler == MODE_SAMPLER_EULER ? 4 : 5);
-  RET_IF(get_sampler_graph(e, B, n, head_mode, &exec));
+  const bool fused_small = small_fused_ok(e, B);  // rollout-sized batch: the whole loop is one persistent kernel
+  mode_engine::SmallProgram sp{nullptr, 0};
+  if (fused_small) {
+    const std::string key = "s:" + std::to_string(B) + ":" + std::to_string(n) + ":" + std::to_string(head_mode);
+    RET_IF(get_small_program(e, key, n, [&](int i) {
+      return enqueue_eval(e, nullptr, B, e->sig_dev + i, 0, e->x_work, 1, head_mode, e->x_work, e->coefs_dev + SCHED_COEFS * i, nullptr, i);
+    }, &sp));
+    e->launch_count = 0;
+  } else {
+    RET_IF(get_sampler_graph(e, B, n, head_mode, &exec));
+  }
   ScheduleArg sa;
   sampler_schedule(sampler, sigmas_host, n, &sa);
   set_schedule_kernel<<<1, 64, 0, st>>>(sa, e->sig_dev, e->coefs_dev);
@@ -1401,7 +1513,10 @@ extern "C" int mode_sample(mode_engine_t* e, int sampler, const float* state_dev
   // route the whole sigma schedule (n steps x L layers) in one router + one plan launch, ahead of the captured loop
   RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, nullptr, 0, e->L, 0, n, 1, e->trim_rows));
   RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
-  CU_OK(cudaGraphLaunch(exec, st));
+  if (fused_small)
+    RET_IF(launch_small_eval(e, st, sp, B));
+  else
+    CU_OK(cudaGraphLaunch(exec, st));
   CU_OK(cudaMemcpyAsync(x_inout_dev, e->x_work, xbytes, cudaMemcpyDeviceToDevice, st));
   e->launch_count += 1;
   return MODE_OK;
@@ -1453,8 +1568,18 @@ extern "C" int mode_sample_program(mode_engine_t* e, const float* state_dev, con
   std::string key = std::to_string(B) + (noise_dev ? ":n:" : ":-:");
   for (int i = 0; i < n_evals; ++i) key.push_back(reads_probe_host[i] ? 'P' : 'X');
   const size_t cur_el = (size_t)B * e->A * e->adim;
+  const bool fused_small = small_fused_ok(e, B);
+  mode_engine::SmallProgram sp{nullptr, 0};
+  if (fused_small)
+    RET_IF(get_small_program(e, "p:" + key, n_evals, [&](int i) {
+      return enqueue_eval(e, nullptr, B, e->sig_dev + i, 0, reads_probe_host[i] ? e->x_probe : e->x_work, 1, 6, nullptr, nullptr,
+                          nullptr, i, nullptr, e->prog_dev + (size_t)i * HEAD_PROG_FLOATS,
+                          noise_dev ? e->noise_buf + (size_t)i * cur_el : nullptr);
+    }, &sp));
   auto it = e->prog_graphs.find(key);
-  if (it == e->prog_graphs.end()) {
+  if (fused_small) {
+    e->launch_count = 0;
+  } else if (it == e->prog_graphs.end()) {
     const int64_t before = e->launch_count;
     cudaGraph_t graph = nullptr;
     CU_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
@@ -1495,7 +1620,10 @@ extern "C" int mode_sample_program(mode_engine_t* e, const float* state_dev, con
   CU_OK(cudaMemcpyAsync(e->x_probe, x_inout_dev, cur_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RET_IF(enqueue_routing(e, st, B, e->sig_dev, 0, nullptr, 0, e->L, 0, n_evals, 1, e->trim_rows));
   RET_IF(enqueue_cond(e, st, B, state_dev, goal_dev));
-  CU_OK(cudaGraphLaunch(it->second, st));
+  if (fused_small)
+    RET_IF(launch_small_eval(e, st, sp, B));
+  else
+    CU_OK(cudaGraphLaunch(it->second, st));
   CU_OK(cudaMemcpyAsync(x_inout_dev, e->x_work, cur_el * sizeof(float), cudaMemcpyDeviceToDevice, st));
   e->launch_count += 1;
   return MODE_OK;

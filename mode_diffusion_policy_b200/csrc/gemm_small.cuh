@@ -132,6 +132,105 @@ __device__ __forceinline__ void gemm_small_body(const SmallGemmParams& p, int sl
   __syncthreads();  // `red` is reused by the caller's next task
 }
 
+// S slabs per task (persistent small-batch kernel): the same arithmetic as gemm_small_body for slabs
+// [slab0, slab0 + S) of one group — same K split over the warps, same chunk order, same fixed-order reduction, hence
+// bit-identical results — but every lane keeps S (x2 for SwiGLU) independent 16-byte weight loads in flight per K chunk.
+// With ONE resident CTA per SM (the persistent kernel's register budget) that is what brings the streamed bytes in
+// flight per SM to 48-64 KB, i.e. to what HBM latency x bandwidth / 148 SMs asks for. A rows are always read coherently.
+template <int EPI, int MT, int S>
+__device__ __forceinline__ void gemm_small_multi_body(const SmallGemmParams& p, int slab0, int n_slabs, int group, float* red_raw) {
+  constexpr bool GLU = (EPI == EPI_SWIGLU_BF16);
+  constexpr int NACC = GLU ? 2 : 1;
+  float (*red)[S][NACC][MT * 16 * 8] = reinterpret_cast<float (*)[S][NACC][MT * 16 * 8]>(red_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  if (group >= *p.num_m_tiles) return;
+  const GemmMTile tile = p.m_tiles[group];
+  const int wr = p.w_row_off + tile.w_row_base;
+  const __nv_bfloat16* w0[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int slab = min(slab0 + s, n_slabs - 1);  // a task past the last slab re-reads it and stores nothing
+    const int row = GLU ? (slab * 8 / 128) * 256 + (slab * 8) % 128 + g : slab * 8 + g;
+    w0[s] = p.W + static_cast<size_t>(wr + row) * p.K;
+  }
+  const __nv_bfloat16* a_lo = p.A + static_cast<size_t>(tile.a_row0 + g) * p.K;
+  float acc[S][MT][NACC][4];
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) acc[s][m][i][0] = acc[s][m][i][1] = acc[s][m][i][2] = acc[s][m][i][3] = 0.f;
+  const int k_per_warp = p.K / SMALL_M_WARPS;
+  const int k0 = warp * k_per_warp + tq * 8;
+#pragma unroll(MT == 1 ? 4 : 2)
+  for (int kc = 0; kc < k_per_warp; kc += 32) {
+    uint4 wv[S], gv[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      wv[s] = __ldg(reinterpret_cast<const uint4*>(w0[s] + k0 + kc));
+      if (GLU) gv[s] = __ldg(reinterpret_cast<const uint4*>(w0[s] + static_cast<size_t>(128) * p.K + k0 + kc));
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const uint4 al = *reinterpret_cast<const uint4*>(a_lo + static_cast<size_t>(m * 16) * p.K + k0 + kc);
+      const uint4 ah = *reinterpret_cast<const uint4*>(a_lo + static_cast<size_t>(m * 16 + 8) * p.K + k0 + kc);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        mma_bf16_16816_acc(acc[s][m][0], al.x, ah.x, al.y, ah.y, wv[s].x, wv[s].y);
+        mma_bf16_16816_acc(acc[s][m][0], al.z, ah.z, al.w, ah.w, wv[s].z, wv[s].w);
+        if (GLU) {
+          mma_bf16_16816_acc(acc[s][m][NACC - 1], al.x, ah.x, al.y, ah.y, gv[s].x, gv[s].y);
+          mma_bf16_16816_acc(acc[s][m][NACC - 1], al.z, ah.z, al.w, ah.w, gv[s].z, gv[s].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        float* dst = red[warp][s][i] + m * 128;
+        dst[g * 8 + 2 * tq] = acc[s][m][i][0];
+        dst[g * 8 + 2 * tq + 1] = acc[s][m][i][1];
+        dst[(g + 8) * 8 + 2 * tq] = acc[s][m][i][2];
+        dst[(g + 8) * 8 + 2 * tq + 1] = acc[s][m][i][3];
+      }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < S * MT * 128; idx += SMALL_M_WARPS * 32) {
+    const int s = idx / (MT * 128), e = idx % (MT * 128);
+    const int slab = slab0 + s;
+    const int r = e >> 3, c = e & 7;
+    float v[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < SMALL_M_WARPS; ++w) sum += red[w][s][i][e];  // fixed order: deterministic
+      v[i] = sum;
+    }
+    if (r >= tile.rows_valid || slab >= n_slabs) continue;
+    const size_t o = static_cast<size_t>(tile.out_row0 + r) * p.ldo + slab * 8 + c;
+    if constexpr (EPI == EPI_BIAS_BF16) {
+      reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(v[0] + p.bias[wr + slab * 8 + c]);
+    } else if constexpr (EPI == EPI_RESID_F32) {
+      reinterpret_cast<float*>(p.out)[o] += v[0];
+    } else if constexpr (EPI == EPI_SWIGLU_BF16) {
+      const int prow = wr + (slab * 8 / 128) * 256 + (slab * 8) % 128 + c;
+      const float proj = v[0] + p.bias[prow], gate = v[1] + p.bias[prow + 128];
+      reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(proj * silu_f(gate));
+    } else if constexpr (EPI == EPI_PLAIN_BF16) {
+      reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(v[0]);
+    } else {
+      reinterpret_cast<float*>(p.out)[o] = v[0];
+    }
+  }
+  __syncthreads();  // `red` is reused by the caller's next task
+}
+
 // grid (N / 8 column slabs [hidden units / 8 for SwiGLU], max M-tiles); 256 threads. MT = 16-row tiles per group
 // (1 or 2): every weight fragment a lane loads is used for all MT row tiles.
 template <int EPI, int MT>

@@ -391,3 +391,32 @@ def test_small_batch_path_at_calvin_widths(monkeypatch):
         res[flag] = eng.denoise(cu(state[:1]), cu(xs), cu(goal[:1]), cu(sig)).cpu().numpy()
     want = O.denoiser_forward(sd, cfg, state[:1], xs, goal[:1], sig, "bf16")
     assert rel_l2(res["1"], want) < TOL and rel_l2(res["0"], want) < TOL and rel_l2(res["1"], res["0"]) < TOL
+
+
+@pytest.mark.parametrize("tag", list(MODELS))
+def test_persistent_small_batch_kernel_is_bit_identical(tag, monkeypatch):
+    """MODE_SMALL_FUSED=1 (csrc/small_eval.cuh): the whole sampler loop of a rollout-sized batch as ONE cooperative launch
+    — the bodies of the row kernels, the attention and the weight-streaming GEMM run as phases of a resident grid separated
+    by grid barriers. Same device code, same summation order: the result must equal the CUDA-graph path bit for bit, for
+    the fused DDIM / DPM++(2M) loops and for a sampler program (Heun), at B = 1 and B = 2."""
+    from mode_diffusion_policy_b200 import gc_sampling as S
+    from test_reference_full_gpu import _modules
+
+    cfg, _ = MODELS[tag]
+    sd = O.make_weights(cfg, seed=1234, router_gain=30.0)
+    state, goal, x0 = O.make_inputs(cfg, 2, seed=4321)
+    sigmas = O.get_sigmas_exponential(10, 1e-3, 80.0)
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MODE_SMALL_FUSED", flag)
+        inner, model = _modules(cfg, sd, max_batch=2)
+        res = []
+        for B in (1, 2):
+            st = {"state_images": cu(state[:B])}
+            res.append(S.sample_ddim(model, st, cu(x0[:B]), cu(goal[:B]), cu(sigmas), disable=True))
+            res.append(S.sample_dpmpp_2m(model, st, cu(x0[:B]), cu(goal[:B]), cu(sigmas), disable=True))
+            res.append(S.sample_heun(model, st, cu(x0[:B]), cu(goal[:B]), cu(sigmas), disable=True))
+        outs[flag] = [r.clone() for r in res]
+        del inner, model
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.isfinite(a).all() and torch.equal(a, b)
