@@ -240,6 +240,11 @@ struct mode_engine {
   unsigned long long *usage, *tokens;
   int dense_cap;  // tiles per dense table
   int cur_B = -1;
+  // dense M-tile tables per batch size seen so far: switching between batch sizes (a rollout server alternating B) only
+  // swaps pointers and rebuilds tensor maps on the host — no device synchronisation, and the CUDA graphs / phase tables
+  // captured for the other batch sizes stay valid (they reference their own tables)
+  struct BatchCtx { GemmMTile* tiles; int* counts; };
+  std::map<int, BatchCtx> batch_ctx;
   int last_slot = ROUTE_SLOT_EVAL;  // slot holding the routing of the most recent evaluation (mode_get_routing)
 
   CUtensorMap tm_hA, tm_attn, tm_perm, tm_h, tm_st, tm_goal;
@@ -553,6 +558,10 @@ extern "C" void mode_destroy(mode_engine_t* e) {
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
   for (auto& g : e->prog_graphs) cudaGraphExecDestroy(g.second);
   for (auto& sp : e->small_programs) cudaFree(sp.second.dev);
+  for (auto& c : e->batch_ctx) {
+    cudaFree(c.second.tiles);
+    cudaFree(c.second.counts);
+  }
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->weights_ready) cudaEventDestroy(e->weights_ready);
   for (void* p : e->allocs) cudaFree(p);
@@ -687,8 +696,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
   A_(dev_alloc(e, &e->downT_tiles, ROUTE_SLOTS * (size_t)L * e->max_tiles));
   A_(dev_alloc(e, &e->num_tiles, ROUTE_SLOTS * (size_t)L));
   e->dense_cap = maxM_pad / 128;  // enough for either tile size
-  A_(dev_alloc(e, &e->dense_tiles, (size_t)3 * e->dense_cap));
-  A_(dev_alloc(e, &e->dense_counts, 3));
+  e->dense_tiles = nullptr;  // per batch size, see ensure_batch
+  e->dense_counts = nullptr;
   A_(dev_alloc(e, &e->sk_partials, (size_t)e->num_sms * 8 * 8 * 128, false));
   A_(dev_alloc(e, &e->sk_flags, (size_t)e->num_sms * 4));
   A_(dev_alloc(e, &e->mlp_sync, (size_t)1 + e->max_tiles));
@@ -846,25 +855,51 @@ static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
     e->weights_wait_pending = false;
   }
   if (B == e->cur_B) return MODE_OK;
-  std::vector<GemmMTile> tiles(3 * (size_t)e->dense_cap);
-  int counts[3];
-  const int rows[3] = {B * e->T, B * e->S, B};
-  for (int k = 0; k < 3; ++k) {
-    const int tm = e->tile_m;
-    const int n = (rows[k] + tm - 1) / tm;
-    counts[k] = n;
-    for (int i = 0; i < n; ++i) {
-      GemmMTile t;
-      t.a_row0 = i * tm;
-      t.out_row0 = i * tm;
-      t.rows_valid = rows[k] - i * tm < tm ? rows[k] - i * tm : tm;
-      t.w_row_base = 0;
-      tiles[(size_t)k * e->dense_cap + i] = t;
+  auto ctx = e->batch_ctx.find(B);
+  if (ctx == e->batch_ctx.end()) {
+    if (e->batch_ctx.size() >= 32) {  // bounded cache: drop everything captured for the old batch sizes
+      CU_OK(cudaDeviceSynchronize());
+      for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+      e->graphs.clear();
+      e->graph_launches.clear();
+      for (auto& g : e->prog_graphs) cudaGraphExecDestroy(g.second);
+      e->prog_graphs.clear();
+      e->prog_graph_launches.clear();
+      for (auto& sp : e->small_programs) cudaFree(sp.second.dev);
+      e->small_programs.clear();
+      for (auto& c : e->batch_ctx) {
+        cudaFree(c.second.tiles);
+        cudaFree(c.second.counts);
+      }
+      e->batch_ctx.clear();
     }
+    std::vector<GemmMTile> tiles(3 * (size_t)e->dense_cap);
+    int counts[3];
+    const int rows_[3] = {B * e->T, B * e->S, B};
+    for (int k = 0; k < 3; ++k) {
+      const int tm = e->tile_m;
+      const int n = (rows_[k] + tm - 1) / tm;
+      counts[k] = n;
+      for (int i = 0; i < n; ++i) {
+        GemmMTile t;
+        t.a_row0 = i * tm;
+        t.out_row0 = i * tm;
+        t.rows_valid = rows_[k] - i * tm < tm ? rows_[k] - i * tm : tm;
+        t.w_row_base = 0;
+        tiles[(size_t)k * e->dense_cap + i] = t;
+      }
+    }
+    mode_engine::BatchCtx c{nullptr, nullptr};
+    RET_IF(dev_alloc<GemmMTile>(nullptr, &c.tiles, tiles.size(), false));
+    RET_IF(dev_alloc<int>(nullptr, &c.counts, 3, false));
+    // fresh allocations nothing else reads: plain synchronous copies, no device-wide synchronisation
+    CU_OK(cudaMemcpy(c.tiles, tiles.data(), tiles.size() * sizeof(GemmMTile), cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(c.counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
+    ctx = e->batch_ctx.emplace(B, c).first;
   }
-  CU_OK(cudaDeviceSynchronize());
-  CU_OK(cudaMemcpy(e->dense_tiles, tiles.data(), tiles.size() * sizeof(GemmMTile), cudaMemcpyHostToDevice));
-  CU_OK(cudaMemcpy(e->dense_counts, counts, sizeof(counts), cudaMemcpyHostToDevice));
+  e->dense_tiles = ctx->second.tiles;
+  e->dense_counts = ctx->second.counts;
+  const int rows[3] = {B * e->T, B * e->S, B};
   // output maps clip at the exact row count, so partially filled 32-row store boxes never touch rows >= M
   RET_IF(make_out_tmap(&e->to_qkv, e->qkv, rows[0], 3 * e->d, 2));
   RET_IF(make_out_tmap(&e->to_x, e->x, rows[0], e->d, 4));
@@ -880,14 +915,6 @@ static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
     io.to_qkv = e->to_qkv; io.to_x1 = e->to_x; io.to_h = e->to_h; io.to_y = e->to_y;
     RET_IF(make_tmap(&io.tm_qkv_attn, e->qkv, rows[0], 3 * e->d, 16 * ((e->T + 15) / 16)));
   }
-  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);  // captured kernels embed the old maps
-  e->graphs.clear();
-  e->graph_launches.clear();
-  for (auto& g : e->prog_graphs) cudaGraphExecDestroy(g.second);
-  e->prog_graphs.clear();
-  e->prog_graph_launches.clear();
-  for (auto& sp : e->small_programs) cudaFree(sp.second.dev);
-  e->small_programs.clear();
   e->cur_B = B;
   return MODE_OK;
 }
