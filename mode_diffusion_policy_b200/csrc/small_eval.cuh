@@ -10,6 +10,12 @@
 // host; per-step scalars (sigma, update coefficients) are read from device tables at run time, so every schedule of a
 // sampler replays the same table.
 //
+// STATUS: correct and deterministic (tests/test_engine_gpu.py), but on B200 it is SLOWER than the CUDA graph of per-phase
+// kernels it was meant to replace: 8.6 ms vs 7.2 ms per 10-step sample at B = 1 (profiles/r02_small_fused.log). The
+// union of all phases needs ~196 registers, i.e. one CTA of 8 warps per SM, and a phase that is a dependent chain of
+// 3-4 L2 round trips (every row phase) does not get shorter by removing its launch: the graph path overlaps those
+// chains with programmatic dependent launch, the barrier serialises them. Opt-in (MODE_SMALL_FUSED=1).
+//
 // Memory ordering: a phase reads what other CTAs wrote in the phase before. Writers: plain stores, then
 // __syncthreads(), then thread 0 fences (gpu scope) and arrives on the barrier counter. Readers: thread 0 spins with
 // ld.acquire.gpu, fences, __syncthreads(). Activations are therefore never read through the non-coherent path inside this

@@ -394,11 +394,14 @@ def test_small_batch_path_at_calvin_widths(monkeypatch):
 
 
 @pytest.mark.parametrize("tag", list(MODELS))
-def test_persistent_small_batch_kernel_is_bit_identical(tag, monkeypatch):
+def test_persistent_small_batch_kernel_matches_the_graph_path(tag, monkeypatch):
     """MODE_SMALL_FUSED=1 (csrc/small_eval.cuh): the whole sampler loop of a rollout-sized batch as ONE cooperative launch
     — the bodies of the row kernels, the attention and the weight-streaming GEMM run as phases of a resident grid separated
-    by grid barriers. Same device code, same summation order: the result must equal the CUDA-graph path bit for bit, for
-    the fused DDIM / DPM++(2M) loops and for a sampler program (Heun), at B = 1 and B = 2."""
+    by grid barriers. Same device functions, same summation orders in the GEMMs; the compiler contracts a few fp32
+    multiply-adds of the row bodies differently inside the big kernel, so agreement with the CUDA-graph path is to fp32
+    rounding amplified by bf16 flips (measured <= 8e-4 absolute on O(1) actions, scripts/small_fused_check.py), not bitwise.
+    Asserted: within the parity tolerance of the graph path, bit-identical from run to run, for the fused DDIM /
+    DPM++(2M) loops and a sampler program (Heun), at B = 1 and B = 2."""
     from mode_diffusion_policy_b200 import gc_sampling as S
     from test_reference_full_gpu import _modules
 
@@ -407,8 +410,8 @@ def test_persistent_small_batch_kernel_is_bit_identical(tag, monkeypatch):
     state, goal, x0 = O.make_inputs(cfg, 2, seed=4321)
     sigmas = O.get_sigmas_exponential(10, 1e-3, 80.0)
     outs = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("MODE_SMALL_FUSED", flag)
+    for flag in ("0", "1", "1 again"):
+        monkeypatch.setenv("MODE_SMALL_FUSED", flag[0])
         inner, model = _modules(cfg, sd, max_batch=2)
         res = []
         for B in (1, 2):
@@ -418,8 +421,9 @@ def test_persistent_small_batch_kernel_is_bit_identical(tag, monkeypatch):
             res.append(S.sample_heun(model, st, cu(x0[:B]), cu(goal[:B]), cu(sigmas), disable=True))
         outs[flag] = [r.clone() for r in res]
         del inner, model
-    for a, b in zip(outs["0"], outs["1"]):
-        assert torch.isfinite(a).all() and torch.equal(a, b)
+    for a, b, c in zip(outs["0"], outs["1"], outs["1 again"]):
+        assert torch.isfinite(b).all() and torch.equal(b, c)
+        assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < TOL
 
 
 @pytest.mark.parametrize("E,B", [(2, 24), (8, 24), (16, 40), (4, 128)])
