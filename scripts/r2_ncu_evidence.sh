@@ -8,6 +8,6 @@ ncu --metrics "$M" --clock-control none -k regex:"$K" -s 90 -c 90 --csv --log-fi
     python scripts/profile_step.py --evals 2 --layers 12 > gpurun_out/r2h_ncu_metrics.stdout 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 1800 --csv --log-file gpurun_out/r2h_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > gpurun_out/r2h_ncu_bench.stdout 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05_2cta_kernel<\(int\)2>|combine_kernel|attention_tma' -s 30 -c 6 -o gpurun_out/r2h_prof_full -f \
+ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05_2cta_kernel|combine_kernel|attention_tma_kernel' -s 20 -c 8 -o gpurun_out/r2h_prof_full -f \
     python scripts/profile_step.py --evals 2 --layers 3 > gpurun_out/r2h_prof_full.stdout 2>&1
 ls -la gpurun_out/ | grep r2h
