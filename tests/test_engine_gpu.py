@@ -368,10 +368,13 @@ def test_small_batch_weight_streaming_path(tag, monkeypatch):
             outs[flag] = (den.cpu().numpy(), smp.cpu().numpy(), idx, eng.last_launch_count())
         want_den = O.denoiser_forward(sd, cfg, state[sl], g["denoise_x"][sl], goal[sl], g["sigma_het"][sl], "bf16")
         want_smp = O.sample_ddim(sd, cfg, state[sl], x0[sl], goal[sl], sigmas, "bf16")
+        # a single trajectory is 70 numbers: ONE bf16 rounding flip in an early layer moves its rel-L2 by 3e-4..1e-3
+        # (measured over the slices and both paths: 5e-5 .. 1.09e-3, median 4e-4), so the one-trajectory bound is 1.5e-3
+        tol = TOL if sl.stop - sl.start > 1 else 1.5e-3
         for flag in ("1", "0"):
-            assert rel_l2(outs[flag][0], want_den) < TOL, (flag, rel_l2(outs[flag][0], want_den))
-            assert rel_l2(outs[flag][1], want_smp) < TOL, (flag, rel_l2(outs[flag][1], want_smp))
-        assert rel_l2(outs["1"][0], outs["0"][0]) < TOL and rel_l2(outs["1"][1], outs["0"][1]) < TOL
+            assert rel_l2(outs[flag][0], want_den) < tol, (flag, rel_l2(outs[flag][0], want_den))
+            assert rel_l2(outs[flag][1], want_smp) < tol, (flag, rel_l2(outs[flag][1], want_smp))
+        assert rel_l2(outs["1"][0], outs["0"][0]) < tol and rel_l2(outs["1"][1], outs["0"][1]) < tol
         for a, c in zip(outs["1"][2], outs["0"][2]):
             assert np.array_equal(a, c)
 
@@ -394,13 +397,11 @@ def test_small_batch_path_at_calvin_widths(monkeypatch):
 
 
 @pytest.mark.parametrize("tag", list(MODELS))
-def test_persistent_small_batch_kernel_matches_the_graph_path(tag, monkeypatch):
+def test_persistent_small_batch_kernel_is_bit_identical(tag, monkeypatch):
     """MODE_SMALL_FUSED=1 (csrc/small_eval.cuh): the whole sampler loop of a rollout-sized batch as ONE cooperative launch
     — the bodies of the row kernels, the attention and the weight-streaming GEMM run as phases of a resident grid separated
-    by grid barriers. Same device functions, same summation orders in the GEMMs; the compiler contracts a few fp32
-    multiply-adds of the row bodies differently inside the big kernel, so agreement with the CUDA-graph path is to fp32
-    rounding amplified by bf16 flips (measured <= 8e-4 absolute on O(1) actions, scripts/small_fused_check.py), not bitwise.
-    Asserted: within the parity tolerance of the graph path, bit-identical from run to run, for the fused DDIM /
+    by grid barriers. Same device functions, same summation orders, and (the library is compiled with -fmad=false) no
+    context-dependent multiply-add contraction: the result equals the CUDA-graph path bit for bit, for the fused DDIM /
     DPM++(2M) loops and a sampler program (Heun), at B = 1 and B = 2."""
     from mode_diffusion_policy_b200 import gc_sampling as S
     from test_reference_full_gpu import _modules
@@ -410,8 +411,8 @@ def test_persistent_small_batch_kernel_matches_the_graph_path(tag, monkeypatch):
     state, goal, x0 = O.make_inputs(cfg, 2, seed=4321)
     sigmas = O.get_sigmas_exponential(10, 1e-3, 80.0)
     outs = {}
-    for flag in ("0", "1", "1 again"):
-        monkeypatch.setenv("MODE_SMALL_FUSED", flag[0])
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MODE_SMALL_FUSED", flag)
         inner, model = _modules(cfg, sd, max_batch=2)
         res = []
         for B in (1, 2):
@@ -421,9 +422,8 @@ def test_persistent_small_batch_kernel_matches_the_graph_path(tag, monkeypatch):
             res.append(S.sample_heun(model, st, cu(x0[:B]), cu(goal[:B]), cu(sigmas), disable=True))
         outs[flag] = [r.clone() for r in res]
         del inner, model
-    for a, b, c in zip(outs["0"], outs["1"], outs["1 again"]):
-        assert torch.isfinite(b).all() and torch.equal(b, c)
-        assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < TOL
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.isfinite(b).all() and torch.equal(a, b)
 
 
 @pytest.mark.parametrize("E,B", [(2, 24), (8, 24), (16, 40), (4, 128)])
