@@ -228,6 +228,7 @@ struct mode_engine {
   struct SmallProgram { SmallPhase* dev; int n; };
   std::map<std::string, SmallProgram> small_programs;
   unsigned* small_barrier = nullptr;
+  bool band_down = true;                                  // MODE_GEMM_BAND=0: column-block-major tile order for the down GEMM
   bool small_fused = false;                               // MODE_SMALL_FUSED=1 opts in (measured slower, see mode_create)
   std::map<std::string, cudaGraphExec_t> prog_graphs;
   std::map<std::string, int64_t> prog_graph_launches;
@@ -619,6 +620,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
     e->trim_rows = (trim_env && atoi(trim_env) == 0) ? 0 : e->A;
     // persistent one-launch sampler for B <= 2 (small_eval.cuh): correct (tested) but measured SLOWER than the CUDA graph of
     // per-phase kernels on B200 (8.6 vs 7.2 ms per 10-step sample at B = 1, profiles/r02_small_fused.log) -> opt-in
+    const char* band_env = getenv("MODE_GEMM_BAND");
+    e->band_down = !(band_env && atoi(band_env) == 0);
     const char* sf_env = getenv("MODE_SMALL_FUSED");
     e->small_fused = sf_env && atoi(sf_env) != 0;
     env = getenv("MODE_MLP_FUSED");
@@ -934,6 +937,7 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.ldo = 0;
   p.out_rows = 0;
   p.conv = ConvEpilogue{nullptr, 0, 0, nullptr, nullptr, 1, 0};
+  p.band = 0;
   p.k_blocks = Kdim / GEMM_BLOCK_K;
   p.bias = bias;
   p.w_row_off = 0;
@@ -1239,6 +1243,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
       RET_IF(narrow_gemm(e, pd, choose_bn((routed + e->tile_m - 1) / e->tile_m, d, pairs), 2, e->w_down,
                          (uint64_t)e->L * e->E * d, e->F, io.y, d, e->perm_rows));
     }
+    if (e->pair && e->band_down) pd.band = std::max(1, (e->num_sms >> 1) / pd.n_blocks);  // one wave = one band x all column blocks
     {
       ProfScope ps(e, st, PC_DOWN);
       if (small)

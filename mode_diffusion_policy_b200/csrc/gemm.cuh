@@ -91,6 +91,12 @@ struct alignas(64) GemmParams {
   // n_blocks = ceil(n_total / bn); tmap_w has a bn/2-row box; columns [bn/64*64, bn) of a tile (bf16 outputs; bn/32*32
   // for fp32) are stored straight from registers through out_ptr, everything else through tmap_out as before.
   ConvEpilogue conv;           // EPI_CONV_BF16 only
+  // Tile order of the CTA-pair kernel. band = 0: tile t -> (mt = t % n_m, nb = t / n_m), i.e. all M-tiles of one column
+  // block before the next. band = G > 0: bands of G M-tiles; inside a band all column blocks of those rows are walked
+  // (M fastest), so one wave of tiles re-uses a band of A rows for every column block while they are still in L2. Used
+  // for the expert down-projection, whose A operand (h, 58.7 MB at B = 256) does not survive in L2 across the 4-5 passes of
+  // the column-block-major order (ncu: 102.7 MB DRAM reads for 75.5 MB of operands). Values do not depend on the order.
+  int band;
   int bn;
   int n_total;                 // N of the whole GEMM (output columns / weight rows per problem)
   void* out_ptr;               // raw output base, row stride ldo elements, rows >= out_rows are never written
@@ -152,6 +158,19 @@ struct SkIter {
     return n;
   }
 };
+
+__device__ __forceinline__ void decode_tile(int t, int n_m, int n_blocks, int band, int& mt, int& nb) {
+  if (band <= 0) {
+    mt = t % n_m;
+    nb = t / n_m;
+    return;
+  }
+  const int per_band = band * n_blocks;
+  const int b = t / per_band, idx = t - b * per_band;
+  const int rows = min(band, n_m - b * band);  // the last band may be short
+  mt = b * band + idx % rows;
+  nb = idx / rows;
+}
 
 // silu(g) = g / (1 + 2^(-g*log2 e)) with the SFU's ex2/rcp approximations (~2^-22 relative error each; the result is
 // rounded to bf16 right after). 5 instructions per element: the SwiGLU epilogue must stay below the MMA time of a tile.
@@ -685,7 +704,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       SkIter it(pair, n_pairs, total, k_blocks, p.sk_enable & 1);
       int t, kb0, kb1;
       while (it.next(t, kb0, kb1)) {
-        const int mt = t % n_m, nb = t / n_m;
+        int mt, nb;
+        decode_tile(t, n_m, p.n_blocks, p.band, mt, nb);
         const GemmMTile tile = p.m_tiles[mt];
         const int a_row = tile.a_row0 + static_cast<int>(rank) * GEMM_BLOCK_M;
         const int w_row = p.w_row_off + tile.w_row_base + nb * bn + static_cast<int>(rank) * half_n;
@@ -753,7 +773,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     int t, kb0, kb1;
     constexpr size_t kSlot = 8 * 8 * 128;  // float4 per CTA slot
     for (; it.next(t, kb0, kb1); ++iter) {
-      const int mt = t % n_m, nb = t / n_m;
+      int mt, nb;
+      decode_tile(t, n_m, p.n_blocks, p.band, mt, nb);
       const GemmMTile tile = p.m_tiles[mt];
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
