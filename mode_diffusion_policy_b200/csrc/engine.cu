@@ -962,7 +962,9 @@ static int choose_bn(int n_m, int N, int pairs) {
   if (forced >= 64 && forced <= 256 && forced % 16 == 0) return forced;
   int best = GEMM_BLOCK_N;
   long best_cost = -1;
-  for (int bn = GEMM_BLOCK_N; bn >= 128; bn -= 16) {
+  // down to 64 columns: with a handful of M-tiles (B <= 64) narrow tiles are what puts every CTA pair to work, and a
+  // K = 4096 chain of 64-wide MMAs is a quarter of the 256-wide one (expert down-projection at B = 32: 16 -> 64 tiles)
+  for (int bn = GEMM_BLOCK_N; bn >= 64; bn -= 16) {
     const long tiles = (long)n_m * ((N + bn - 1) / bn);
     const long cost = ((tiles + pairs - 1) / pairs) * (bn + 32);
     if (best_cost < 0 || cost < best_cost) {

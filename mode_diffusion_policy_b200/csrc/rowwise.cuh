@@ -606,8 +606,12 @@ struct Ln2Params {
 // (B, T) of the routed kernels are ROUTING units x rows per unit: (samples, tokens per sample) when all tokens of a
 // sample share their experts (eval / arg-max routing), (B*T tokens, 1) under per-token multinomial routing.
 // body of ln2_permute_kernel for virtual block `vblock` (also a phase of the persistent small-batch kernel, small_eval.cuh)
-template <int NVEC>
-__device__ __forceinline__ void ln2_permute_body(const Ln2Params& p, int vblock) {
+// KFIX = 2: the top-2 routing of every shipped configuration, fully unrolled — the generic variant (KFIX = 0) predicates its
+// loops over MAX_TOPK = 8 slots, i.e. issues four times the instructions of the two live ones (ncu: 1 765 instructions
+// per row in combine_kernel, IPC-bound at 19 % of DRAM bandwidth).
+template <int NVEC, int KFIX>
+__device__ __forceinline__ void ln2_permute_impl(const Ln2Params& p, int vblock) {
+  constexpr int KMAX = KFIX ? KFIX : MAX_TOPK;
   if (vblock == 0 && p.zero)
     for (int i = threadIdx.x; i < p.n_zero; i += ROW_WARPS * 32) p.zero[i] = 0;
   const int row = vblock * ROW_WARPS + (threadIdx.x >> 5);
@@ -627,8 +631,8 @@ __device__ __forceinline__ void ln2_permute_body(const Ln2Params& p, int vblock)
   const float rn = rms_inv_denominator(ss, p.inv_sqrt_d, p.eps);
   int dst_row[MAX_TOPK];
 #pragma unroll
-  for (int k = 0; k < MAX_TOPK; ++k)
-    if (k < p.K) dst_row[k] = p.pos[b * p.K + k] + t;
+  for (int k = 0; k < KMAX; ++k)
+    if (KFIX || k < p.K) dst_row[k] = p.pos[b * p.K + k] + t;
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) {
       const int col = (i * 32 + lane) * 4;
@@ -639,14 +643,21 @@ __device__ __forceinline__ void ln2_permute_body(const Ln2Params& p, int vblock)
       *reinterpret_cast<float4*>(p.x_out + static_cast<size_t>(row) * p.d + col) = y;
       const uint2 pk = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
 #pragma unroll
-      for (int k = 0; k < MAX_TOPK; ++k)
-        if (k < p.K) *reinterpret_cast<uint2*>(p.perm + static_cast<size_t>(dst_row[k]) * p.d + col) = pk;
+      for (int k = 0; k < KMAX; ++k)
+        if (KFIX || k < p.K) *reinterpret_cast<uint2*>(p.perm + static_cast<size_t>(dst_row[k]) * p.d + col) = pk;
     }
   if (p.row_token && lane == 0) {
 #pragma unroll
-    for (int k = 0; k < MAX_TOPK; ++k)
-      if (k < p.K) p.row_token[dst_row[k]] = row;
+    for (int k = 0; k < KMAX; ++k)
+      if (KFIX || k < p.K) p.row_token[dst_row[k]] = row;
   }
+}
+template <int NVEC>
+__device__ __forceinline__ void ln2_permute_body(const Ln2Params& p, int vblock) {
+  if (p.K == 2)
+    ln2_permute_impl<NVEC, 2>(p, vblock);
+  else
+    ln2_permute_impl<NVEC, 0>(p, vblock);
 }
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) ln2_permute_kernel(const Ln2Params p) {
@@ -679,8 +690,12 @@ struct CombineParams {
   float inv_sqrt_d;  // float(d ** -0.5), computed on the host exactly as RMSNorm.__init__ does (modedit.py:75)
 };
 // body of combine_kernel for virtual block `vblock` (also a phase of the persistent small-batch kernel, small_eval.cuh)
-template <int NVEC>
-__device__ __forceinline__ void combine_body(const CombineParams& p, int vblock) {
+// KFIX = 2: the top-2 routing of every shipped configuration, fully unrolled — the generic variant (KFIX = 0) predicates its
+// loops over MAX_TOPK = 8 slots, i.e. issues four times the instructions of the two live ones (ncu: 1 765 instructions
+// per row in combine_kernel, IPC-bound at 19 % of DRAM bandwidth).
+template <int NVEC, int KFIX>
+__device__ __forceinline__ void combine_impl(const CombineParams& p, int vblock) {
+  constexpr int KMAX = KFIX ? KFIX : MAX_TOPK;
   const int row = vblock * ROW_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.B * p.T) return;
@@ -689,8 +704,8 @@ __device__ __forceinline__ void combine_body(const CombineParams& p, int vblock)
   int src_row[MAX_TOPK];
   float wk[MAX_TOPK];
 #pragma unroll
-  for (int k = 0; k < MAX_TOPK; ++k)
-    if (k < p.K) {
+  for (int k = 0; k < KMAX; ++k)
+    if (KFIX || k < p.K) {
       src_row[k] = p.pos[b * p.K + k] + t;
       wk[k] = p.w[b * p.K + k];
     }
@@ -708,8 +723,8 @@ __device__ __forceinline__ void combine_body(const CombineParams& p, int vblock)
       const int col = (i * 32 + lane) * 4;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < MAX_TOPK; ++k)
-        if (k < p.K) {
+      for (int k = 0; k < KMAX; ++k)
+        if (KFIX || k < p.K) {
           const uint2 raw = *reinterpret_cast<const uint2*>(p.y + static_cast<size_t>(src_row[k]) * p.d + col);
           const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
           const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
@@ -754,6 +769,13 @@ __device__ __forceinline__ void combine_body(const CombineParams& p, int vblock)
       else
         *reinterpret_cast<float4*>(p.xnorm + static_cast<size_t>(row) * p.d + col) = y;
     }
+}
+template <int NVEC>
+__device__ __forceinline__ void combine_body(const CombineParams& p, int vblock) {
+  if (p.K == 2)
+    combine_impl<NVEC, 2>(p, vblock);
+  else
+    combine_impl<NVEC, 0>(p, vblock);
 }
 template <int NVEC>
 __global__ void __launch_bounds__(ROW_WARPS * 32, 4) combine_kernel(const CombineParams p) {

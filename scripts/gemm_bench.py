@@ -24,3 +24,8 @@ for (M, N, K, epi) in [(3584, 16384, 1024, 2), (7168, 1024, 4096, 3), (8192, 819
     run_gemm(M, N, K, epi, pair=True)
     print("  ^ normal   v every other weight-tile load skipped")
     run_gemm(M, N, K, epi, pair=True, skip_b=True)
+
+# few M-tiles (B = 32 per GPU: 448 token rows, 896 routed rows): narrow tiles put all 74 CTA pairs to work
+for (M, N, K, epi) in [(448, 3072, 1024, 0), (448, 1024, 1024, 1), (896, 1024, 4096, 3), (1792, 1024, 4096, 3)]:
+    for bn in (256, 192, 128, 96, 64):
+        run_gemm(M, N, K, epi, pair=True, bn=bn)

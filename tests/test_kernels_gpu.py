@@ -72,7 +72,7 @@ def test_gemm_matches_fp32_reference(M, N, K, epi, mode):
 
 
 @pytest.mark.parametrize("epi", [0, 1, 3, 4])
-@pytest.mark.parametrize("bn", [208, 160, 128, 240, 176])
+@pytest.mark.parametrize("bn", [208, 160, 128, 240, 176, 96, 64])
 @pytest.mark.parametrize("M,N,K", [(3584, 1024, 1024), (3584, 3072, 1024), (7168, 1024, 4096), (300, 1024, 512), (1000, 3072, 256)])
 def test_gemm_tile_widths_are_bit_identical(M, N, K, epi, bn):
     """CTA-pair kernel with `bn`-wide tiles (wave filling, engine.cu choose_bn): the column tiling changes which tile owns
