@@ -936,8 +936,11 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.out_ptr = nullptr;
   p.ldo = 0;
   p.out_rows = 0;
-  p.conv = ConvEpilogue{nullptr, 0, 0, nullptr, nullptr, 1, 0};
+  p.conv = ConvEpilogue{nullptr, 0, 0, nullptr, nullptr, 1, 0, 0, 0};
   p.band = 0;
+  p.n_taps = 0;
+  p.kb_per_tap = 1;
+  for (int i = 0; i < 9; ++i) p.tap_off[i] = 0;
   p.k_blocks = Kdim / GEMM_BLOCK_K;
   p.bias = bias;
   p.w_row_off = 0;
@@ -951,22 +954,23 @@ static GemmParams gemm_params(const CUtensorMap& ta, const CUtensorMap& tw, cons
   p.drop_half_F = 0;
   return p;
 }
-// Tile width of a CTA-pair GEMM with `n_m` M-tiles and N output columns: the multiple of 16 whose column tiling fills
-// whole waves of the `pairs` CTA pairs best. Cost model: waves x (width + 32); the 32 stands for the per-tile fixed
-// cost (pipeline ramp, accumulator hand-over). Ties go to the wider tile (fewer re-reads of the A rows).
-// At B = 256 (14 M-tiles of 256 rows, 74 pairs): QKV N = 3072 -> 208 (15 x 14 = 210 tiles = 3 waves of 0.81 instead of
-// 168 = 3 waves of 1.0), c_proj N = 1024 -> 208 (70 tiles, one wave), expert down (28 M-tiles) -> 208 (140 tiles = 2
-// waves of 0.81 instead of 112 = 2 waves of 1.0).
-static int choose_bn(int n_m, int N, int pairs) {
+// Tile width of a CTA-pair GEMM with `n_m` M-tiles, N output columns and k_blocks 64-wide K steps: the multiple of 16 that
+// minimises  waves x (k_blocks x max(width, 240) + 12 x width + 1024).  The three terms are the measured structure of a
+// tile's time (profiles/r02_gemm_tile_widths.log, r02_gemm_small_m.log): a k-block costs the same below ~240 columns (the
+// 6-stage TMA pipeline is latency-bound there: K = 4096 at M = 896 takes 24.4 us at every width from 64 to 256), the
+// epilogue is proportional to the width (K = 1024 at M = 448: 18.2 -> 13.4 us from 256 to 128), and every tile pays a fixed
+// ramp. So narrow tiles pay off when they fill idle CTA pairs or whole waves, never by shortening the K loop; ties go to
+// the wider tile. At B = 256 (14 M-tiles, 74 pairs): QKV N = 3072 -> 208 (210 tiles = 3 waves of 0.81 instead of 168 =
+// 3 waves of 1.0), c_proj -> 208 (70 tiles, one wave), expert down (28 M-tiles) -> 208 (140 tiles = 2 waves).
+static int choose_bn(int n_m, int N, int pairs, int k_blocks) {
   static const int forced = getenv("MODE_GEMM_BN") ? atoi(getenv("MODE_GEMM_BN")) : 0;
   if (forced >= 64 && forced <= 256 && forced % 16 == 0) return forced;
   int best = GEMM_BLOCK_N;
   long best_cost = -1;
-  // down to 64 columns: with a handful of M-tiles (B <= 64) narrow tiles are what puts every CTA pair to work, and a
-  // K = 4096 chain of 64-wide MMAs is a quarter of the 256-wide one (expert down-projection at B = 32: 16 -> 64 tiles)
   for (int bn = GEMM_BLOCK_N; bn >= 64; bn -= 16) {
     const long tiles = (long)n_m * ((N + bn - 1) / bn);
-    const long cost = ((tiles + pairs - 1) / pairs) * (bn + 32);
+    const long per_tile = (long)k_blocks * (bn > 240 ? bn : 240) + 12L * bn + 1024;
+    const long cost = ((tiles + pairs - 1) / pairs) * per_tile;
     if (best_cost < 0 || cost < best_cost) {
       best = bn;
       best_cost = cost;
@@ -1157,7 +1161,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   const int pairs = e->num_sms >> 1;
   const int n_m_dense = (M + e->tile_m - 1) / e->tile_m;
   if (!e->train_forward)
-    RET_IF(narrow_gemm(e, p, choose_bn(n_m_dense, 3 * d, pairs), 0, e->w_qkv, (uint64_t)e->L * 3 * d, d, io.qkv, 3 * d, M));
+    RET_IF(narrow_gemm(e, p, choose_bn(n_m_dense, 3 * d, pairs, d / GEMM_BLOCK_K), 0, e->w_qkv, (uint64_t)e->L * 3 * d, d, io.qkv, 3 * d, M));
   // rollout-sized batch: every group has <= 16 rows -> weight-streaming kernels (gemm_small.cuh)
   const bool small = e->small_m && !io.z && !e->train_forward && M <= SMALL_M_MAX_ROWS && d % 256 == 0;
   const int small_groups = e->E < B * e->K ? e->E : B * e->K;  // upper bound on routed groups
@@ -1182,7 +1186,7 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   p = gemm_params(io.tm_attn, e->tm_wproj, io.to_x1, e->dense_tiles, e->dense_counts, d, d, nullptr);  // x1 += acc
   p.w_row_off = l * d;
   if (!e->train_forward)
-    RET_IF(narrow_gemm(e, p, choose_bn(n_m_dense, d, pairs), 1, e->w_proj, (uint64_t)e->L * d, d, io.x1, d, M));
+    RET_IF(narrow_gemm(e, p, choose_bn(n_m_dense, d, pairs, d / GEMM_BLOCK_K), 1, e->w_proj, (uint64_t)e->L * d, d, io.x1, d, M));
   {
     ProfScope ps(e, st, PC_PROJ);
     if (small)
@@ -1241,8 +1245,10 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     enable_stream_k(e, pd);
     if (!e->train_forward) {
       // routed rows of this block (the last block only keeps its action rows), before group padding
-      const int routed = e->K * rv.units * (rv.rt - t_skip);
-      RET_IF(narrow_gemm(e, pd, choose_bn((routed + e->tile_m - 1) / e->tile_m, d, pairs), 2, e->w_down,
+      // M-tiles of the grouped GEMM: every routed expert's group is padded to whole tiles; with one sigma for the batch
+      // (samplers) all rows go to the same K experts, which is also the estimate used for heterogeneous batches
+      const int group_rows = rv.units * (rv.rt - t_skip);
+      RET_IF(narrow_gemm(e, pd, choose_bn(e->K * ((group_rows + e->tile_m - 1) / e->tile_m), d, pairs, e->F / GEMM_BLOCK_K), 2, e->w_down,
                          (uint64_t)e->L * e->E * d, e->F, io.y, d, e->perm_rows));
     }
     if (e->pair && e->band_down) pd.band = std::max(1, (e->num_sms >> 1) / pd.n_blocks);  // one wave = one band x all column blocks

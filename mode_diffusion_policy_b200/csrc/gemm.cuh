@@ -51,7 +51,10 @@ struct ConvEpilogue {
   int relu;
   const float* film_g;       // [images, film_c] or nullptr
   const float* film_b;
-  int film_hw, film_c;
+  int film_hw, film_c;       // rows per image (film_hw) for the FiLM / border lookups
+  // zero-bordered activation layout (resnet.inc, implicit 3x3 convolutions): every image is stored as (pad_h + 2) x pad_w2
+  // positions with a one-pixel zero border; rows that are border positions are written as zeros. pad_w2 = 0: dense layout.
+  int pad_w2, pad_h;
 };
 
 // One M-tile of work. For grouped GEMMs consecutive tiles may belong to different experts.
@@ -97,6 +100,12 @@ struct alignas(64) GemmParams {
   // for the expert down-projection, whose A operand (h, 58.7 MB at B = 256) does not survive in L2 across the 4-5 passes of
   // the column-block-major order (ncu: 102.7 MB DRAM reads for 75.5 MB of operands). Values do not depend on the order.
   int band;
+  // Implicit convolution (resnet.inc): n_taps > 0 splits the K loop into n_taps groups of kb_per_tap k-blocks; group t reads
+  // the A rows shifted by tap_off[t] (a 3x3 tap of a zero-bordered NHWC activation is a row offset) at columns
+  // [0, 64 * kb_per_tap); the weight columns advance through all n_taps * kb_per_tap k-blocks as usual. Rows that fall
+  // outside the tensor are zero-filled by TMA.
+  int n_taps, kb_per_tap;
+  int tap_off[9];
   int bn;
   int n_total;                 // N of the whole GEMM (output columns / weight rows per problem)
   void* out_ptr;               // raw output base, row stride ldo elements, rows >= out_rows are never written
@@ -108,7 +117,7 @@ struct EpiGeom {
   int n_total = 0x7fffffff;
   void* out = nullptr;
   int ldo = 0, out_rows = 0;
-  ConvEpilogue conv = ConvEpilogue{nullptr, 0, 0, nullptr, nullptr, 1, 0};
+  ConvEpilogue conv = ConvEpilogue{nullptr, 0, 0, nullptr, nullptr, 1, 0, 0, 0};
 };
 
 // Work decomposition of the CTA-pair kernel. Tiles of full waves are data-parallel (tile = worker + i * P). The last,
@@ -315,6 +324,11 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
     const int row = out_row0 + lane;
     const bool row_ok = row < g.out_rows;
     const int img = row_ok ? row / g.conv.film_hw : 0;
+    bool border = false;
+    if (g.conv.pad_w2 > 0 && row_ok) {
+      const int q = row - img * g.conv.film_hw, y = q / g.conv.pad_w2, x = q - y * g.conv.pad_w2;
+      border = y == 0 || y > g.conv.pad_h || x == 0 || x == g.conv.pad_w2 - 1;
+    }
 #pragma unroll 1
     for (int c = 0; c < nfull; ++c) {
       if (col0 + c * 64 >= g.n_total) break;
@@ -361,6 +375,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const CUtensorMap* tmap_out, 
             v[2] = fmaf(1.f + g0.z, v[2], e0.z); v[3] = fmaf(1.f + g0.w, v[3], e0.w);
             v[4] = fmaf(1.f + g1.x, v[4], e1.x); v[5] = fmaf(1.f + g1.y, v[5], e1.y);
             v[6] = fmaf(1.f + g1.z, v[6], e1.z); v[7] = fmaf(1.f + g1.w, v[7], e1.w);
+          }
+          if (border) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = 0.f;
           }
           st_shared_v4(chunk_addr(buf, hh * 4 + j), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                        pack_bf16x2(v[6], v[7]));
@@ -721,7 +739,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             mbar_arrive_expect_tx(full_bar(stage), skip_b ? 2 * GEMM_A_BYTES : 2 * stage_tx);
           else
             mbar_arrive_cluster(leader_full);
-          tma_load_2d_2sm(a_dst, &p.tmap_a, leader_full, kb * GEMM_BLOCK_K, a_row);
+          if (p.n_taps > 0) {
+            const int tap = kb / p.kb_per_tap;
+            tma_load_2d_2sm(a_dst, &p.tmap_a, leader_full, (kb - tap * p.kb_per_tap) * GEMM_BLOCK_K, a_row + p.tap_off[tap]);
+          } else {
+            tma_load_2d_2sm(a_dst, &p.tmap_a, leader_full, kb * GEMM_BLOCK_K, a_row);
+          }
           if (!skip_b) tma_load_2d_2sm(b_dst, &p.tmap_w, leader_full, kb * GEMM_BLOCK_K, w_row);
           if (++stage == G2_STAGES) {
             stage = 0;

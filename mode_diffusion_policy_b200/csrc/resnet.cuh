@@ -117,6 +117,84 @@ __global__ void maxpool3x3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ in, _
                                                 pack_bf16x2(m[6], m[7]));
 }
 
+// ---- zero-bordered layout (implicit 3x3 convolutions): an image of H x W positions is stored as (H + 2) x (W + 2)
+// positions whose one-pixel border is zero, so the tap (kh, kw) of a stride-1 3x3 convolution is the row offset
+// (kh - 1) * (W + 2) + (kw - 1) of the [positions, C] matrix and the GEMM reads it straight from the activation.
+
+// MaxPool2d(3, 2, 1): dense NHWC in -> zero-bordered NHWC out.
+__global__ void maxpool3x3s2_to_padded_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n_img,
+                                              int C, int H, int W, int Ho, int Wo) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c8n = C >> 3, Wp = Wo + 2, Hp = Ho + 2;
+  if (i >= static_cast<unsigned>(n_img) * Hp * Wp * c8n) return;
+  const unsigned c8 = i % c8n, row = i / c8n;
+  const int xo = row % Wp, yo = (row / Wp) % Hp, n = row / (Wp * Hp);
+  uint4 r = make_uint4(0, 0, 0, 0);
+  if (xo >= 1 && xo <= Wo && yo >= 1 && yo <= Ho) {
+    const int wo = xo - 1, ho = yo - 1;
+    float m[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m[u] = -INFINITY;
+    for (int dh = 0; dh < 3; ++dh) {
+      const int h = ho * 2 - 1 + dh;
+      if (h < 0 || h >= H) continue;
+      for (int dw = 0; dw < 3; ++dw) {
+        const int w = wo * 2 - 1 + dw;
+        if (w < 0 || w >= W) continue;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(n) * H + h) * W + w) * C) + c8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __bfloat1622float2(h2[u]);
+          m[2 * u] = fmaxf(m[2 * u], f.x);
+          m[2 * u + 1] = fmaxf(m[2 * u + 1], f.y);
+        }
+      }
+    }
+    r = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+  }
+  reinterpret_cast<uint4*>(out)[i] = r;
+}
+
+// im2col of a STRIDED convolution (the 3x3/2 and the 1x1/2 projection of a stage's first block) from a zero-bordered
+// input to rows in zero-bordered OUTPUT order: row (n, yo, xo) of the (Ho + 2) x (Wo + 2) grid; border rows are zero. The
+// input border supplies the convolution's padding, so no bounds checks are needed (pad <= 1).
+__global__ void im2col_padded_kernel(const __nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ col, int n_img, int C,
+                                     int H, int W, int Ho, int Wo, int KH, int KW, int stride, int pad) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c8n = C >> 3, taps = KH * KW, Wpo = Wo + 2, Hpo = Ho + 2;
+  if (i >= static_cast<unsigned>(n_img) * Hpo * Wpo * taps * c8n) return;
+  const unsigned c8 = i % c8n, t = i / c8n, tap = t % taps, row = t / taps;
+  const int kw = tap % KW, kh = tap / KW;
+  const int xo = row % Wpo, yo = (row / Wpo) % Hpo, n = row / (Wpo * Hpo);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (xo >= 1 && xo <= Wo && yo >= 1 && yo <= Ho) {
+    const int h = (yo - 1) * stride - pad + kh + 1, w = (xo - 1) * stride - pad + kw + 1;  // +1: position in the bordered input
+    v = __ldg(reinterpret_cast<const uint4*>(act + ((static_cast<size_t>(n) * (H + 2) + h) * (W + 2) + w) * C) + c8);
+  }
+  reinterpret_cast<uint4*>(col)[i] = v;
+}
+
+// Global average pool over the interior of a zero-bordered map (the border is zero: summing everything is the same).
+__global__ void avgpool_padded_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int n_img, int H, int W, int C) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const int c2n = C >> 1;
+  if (i >= static_cast<size_t>(n_img) * c2n) return;
+  const int c2 = static_cast<int>(i % c2n), n = static_cast<int>(i / c2n);
+  const int rows = (H + 2) * (W + 2);
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(in + static_cast<size_t>(n) * rows * C) + c2;
+  float a = 0.f, b = 0.f;
+  for (int y = 1; y <= H; ++y)
+    for (int x = 1; x <= W; ++x) {
+      const float2 f = __bfloat1622float2(p[static_cast<size_t>(y * (W + 2) + x) * c2n]);
+      a += f.x;
+      b += f.y;
+    }
+  const float inv = 1.0f / static_cast<float>(H * W);
+  out[static_cast<size_t>(n) * C + 2 * c2] = a * inv;
+  out[static_cast<size_t>(n) * C + 2 * c2 + 1] = b * inv;
+}
+
 // Global average pool: NHWC bf16 [images, hw, C] -> fp32 [images, C] (timm global_pool, pretrained_resnets.py:57-58).
 // One thread per (image, channel pair); consecutive threads read consecutive channels: coalesced.
 __global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int n_img, int hw, int C) {

@@ -47,18 +47,22 @@ def test_loss_and_gradients_match_reference_autograd(tag):
     eng = engine_for(cfg, sd, 8)
     loss, F = eng.train_step(cu(state), cu(acts), cu(goal), cu(g["loss_noise"]), cu(g["sigma_het"]))
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(gt["loss"])) <= 3e-2 * abs(float(gt["loss"])), (float(loss), float(gt["loss"]))
+    # tolerances = observed x 1.5 (profiles/r02_train_parity.log: loss <= 1.4e-4, sampled entries <= 2.6e-2, norms <= 2.4e-2)
+    assert abs(float(loss) - float(gt["loss"])) <= 5e-4 * abs(float(gt["loss"])), (float(loss), float(gt["loss"]))
     rows = grad_report(eng, cfg, gt)
     bad = []
     for name, wn, gn, err in rows:
         if wn == 0.0:  # un-routed expert: the reference leaves .grad = None
             ok = gn == 0.0
         else:
-            ok = err < 6e-2 and abs(gn - wn) <= 0.06 * wn
+            ok = err < 4e-2 and abs(gn - wn) <= 0.037 * wn
         if not ok:
             bad.append((name, wn, gn, err))
     worst = sorted(rows, key=lambda r: -r[3] if r[1] > 0 else 0)[:8]
     print("worst sampled-entry relative errors:", [(n, round(e, 4)) for n, _, _, e in worst])
+    print(f"TRAIN-PARITY {tag} deterministic: loss rel {abs(float(loss) - float(gt['loss'])) / abs(float(gt['loss'])):.3e}, "
+          f"max sampled-entry rel {max(e for _, wn, _, e in rows if wn > 0):.3e}, "
+          f"max norm rel {max(abs(gn - wn) / wn for _, wn, gn, _ in rows if wn > 0):.3e}")
     assert not bad, bad[:12]
     # deterministic: a second step reproduces every gradient bit for bit
     flat = eng.flat_grads().clone()
@@ -288,21 +292,26 @@ def test_stochastic_training_matches_reference_with_the_same_masks(tag, prefix):
         idx, w = eng.token_routing(layer, B)
         assert np.array_equal(idx, gs[f"routing/{layer}"]), f"layer {layer}: expert draws differ"
         assert np.allclose(w.sum(axis=1), 1.0, atol=1e-6)
-    assert abs(float(loss) - float(gs["loss"])) <= 3e-2 * abs(float(gs["loss"])), (float(loss), float(gs["loss"]))
+    assert abs(float(loss) - float(gs["loss"])) <= 5e-4 * abs(float(gs["loss"])), (float(loss), float(gs["loss"]))
     Fg = F.cpu().numpy()
-    assert np.linalg.norm(Fg - gs["F"]) <= 2e-2 * np.linalg.norm(gs["F"]), np.linalg.norm(Fg - gs["F"]) / np.linalg.norm(gs["F"])
+    assert np.linalg.norm(Fg - gs["F"]) <= 4e-3 * np.linalg.norm(gs["F"]), np.linalg.norm(Fg - gs["F"]) / np.linalg.norm(gs["F"])
     rows = grad_report(eng, cfg, gs)
     bad = []
     for name, wn, gn, err in rows:
-        ok = (gn == 0.0) if wn == 0.0 else (err < 6e-2 and abs(gn - wn) <= 0.06 * wn)
+        ok = (gn == 0.0) if wn == 0.0 else (err < 4e-2 and abs(gn - wn) <= 0.037 * wn)
         if not ok:
             bad.append((name, wn, gn, err))
     worst = sorted(rows, key=lambda r: -r[3] if r[1] > 0 else 0)[:8]
     print("worst sampled-entry relative errors (stochastic):", [(n, round(e, 4)) for n, _, _, e in worst])
+    print(f"TRAIN-PARITY {prefix}_{tag} stochastic: loss rel {abs(float(loss) - float(gs['loss'])) / abs(float(gs['loss'])):.3e}, "
+          f"F rel {np.linalg.norm(Fg - gs['F']) / np.linalg.norm(gs['F']):.3e}, "
+          f"max sampled-entry rel {max(e for _, wn, _, e in rows if wn > 0):.3e}, "
+          f"max norm rel {max(abs(gn - wn) / wn for _, wn, gn, _ in rows if wn > 0):.3e}")
     assert not bad, bad[:12]
     ds, dg = eng.input_grads(B, state.shape, goal.shape)
     for got, want in ((ds, gs["d_state"]), (dg, gs["d_goal"])):
         got = got.cpu().numpy().reshape(want.shape)
+        print(f"TRAIN-PARITY {prefix}_{tag} input gradient rel {np.linalg.norm(got - want) / np.linalg.norm(want):.3e}")
         assert np.linalg.norm(got - want) <= 6e-2 * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
     # the goal gradient is exactly zero where the goal feature was masked
     from oracle import mode_rng as R
