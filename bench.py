@@ -288,7 +288,7 @@ def train_leg(world, rank, steps, warmup, batch=128):
             dist.barrier()
         torch.cuda.synchronize()
         (ms,) = parallel.max_over_ranks([e0.elapsed_time(e1)], "cuda")
-        return ms / steps, float(loss)
+        return ms / steps, float(loss.detach())
 
     local_ms, _ = timed(False)                       # forward + backward + optimizer, no exchange (what one GPU does)
     full_ms, loss = timed(True) if world > 1 else (local_ms, _)
