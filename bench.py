@@ -232,9 +232,10 @@ def run_reference(args, rank):
 def train_leg(world, rank, steps, warmup, batch=128):
     """BASELINE.json configs[3] — the one path with a collective (reference mode/training_calvin.py:92-103, DDP): training
     step of the full MoDE (12 L, d=1024, 4 experts), noised-action MSE, per-GPU batch 128 (global 1024 on 8 GPUs), bf16
-    tensor-core operands, fused forward+backward, NCCL all-reduce of the flat fp32 gradient buffer pipelined per layer with
-    the fused AdamW (+ weight re-pack). Also times the same step WITHOUT the exchange on every rank: the difference is
-    the communication that stays exposed. Returns the `train` sub-record (rank 0) or None."""
+    tensor-core operands, fused forward+backward, optimizer state sharded over the ranks (NCCL reduce-scatter of the flat
+    fp32 gradient buffer per block during the backward, 1/world of the fused AdamW per rank, all-gather of the new bf16
+    weights during the next forward). Also times the same step WITHOUT the exchange on every rank: the difference is the
+    communication that stays exposed. Returns the `train` sub-record (rank 0) or None."""
     import torch
     import torch.distributed as dist
 
@@ -262,27 +263,29 @@ def train_leg(world, rank, steps, warmup, batch=128):
     names = [n for n, _ in inner.named_parameters() if n != "gripper_embed.weight"]
     reducer = [None]
 
-    def step(exchange):
+    def step(exchange, master_sync="lazy"):
         loss, _ = model.loss({"state_images": S}, A_, G, noise, sigma)
         loss.backward()
         if exchange and world > 1:
             if reducer[0] is None:
-                reducer[0] = parallel.GradAllReduce(inner._engine, names, cfg.n_layers)
-            opt.step_overlapped(reducer[0])
+                reducer[0] = parallel.ShardedGradExchange(inner._engine, names, cfg.n_layers)
+            opt.step_sharded(reducer[0], master_sync=master_sync)
         else:
             opt.step()
         return loss
 
-    def timed(exchange):
+    def timed(exchange, master_sync="lazy"):
         for _ in range(warmup):
-            step(exchange)
+            step(exchange, master_sync)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            loss = step(exchange)
+            loss = step(exchange, master_sync)
+        if getattr(opt, "_opt_stream", None) is not None:  # the last step's updates still in flight on the optimizer's stream
+            torch.cuda.current_stream().wait_stream(opt._opt_stream)
         e1.record()
         if world > 1:
             dist.barrier()
@@ -292,19 +295,28 @@ def train_leg(world, rank, steps, warmup, batch=128):
 
     local_ms, _ = timed(False)                       # forward + backward + optimizer, no exchange (what one GPU does)
     full_ms, loss = timed(True) if world > 1 else (local_ms, _)
+    sync_ms = timed(True, "step")[0] if world > 1 else local_ms   # fp32 masters re-gathered on every step
+    if world > 1:
+        opt.synchronize_parameters()                 # what a checkpoint does once: every rank sees every fp32 master
+        torch.cuda.synchronize()
     inner._engine.close()
     if rank != 0:
         return None
     flat_bytes = 4 * sum(p.numel() for n, p in inner.named_parameters() if n != "gripper_embed.weight")
     return {"metric": "training-samples/sec", "value": world * B / (full_ms * 1e-3), "unit": "samples/s",
             "ms_per_step": full_ms, "ms_per_step_without_exchange": local_ms, "exposed_exchange_ms": full_ms - local_ms,
+            "ms_per_step_masters_gathered_every_step": sync_ms,
             "steps": steps, "warmup": warmup, "global_batch": world * B, "batch_per_gpu": B, "scaling": "weak",
             "loss": loss, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[3]: MoDE 12L d=1024 4 experts top-2, noised-action MSE, fwd + bwd + "
                                    "gradient exchange + fused AdamW + weight re-pack, reference regularisation (attention "
                                    "dropout 0.3, expert dropout 0.1, goal masking 0.1, per-token multinomial routing)",
-                       "collective": (f"NCCL all_reduce(AVG) of the flat fp32 gradient buffer ({flat_bytes / 1e9:.2f} GB), per-layer "
-                                      "coalesced buckets pipelined with per-layer fused AdamW launches") if world > 1
+                       "collective": (f"sharded optimizer state over the {world} ranks (optim.EngineAdamW.step_sharded): per block, "
+                                      f"NCCL reduce_scatter(AVG) of the fp32 gradients ({flat_bytes / 1e9:.2f} GB in all) overlapped "
+                                      f"with the backward, 1/{world} of the fused AdamW per rank, all_gather of the new bf16 weights "
+                                      "overlapped with the next forward; small tensors all-reduced and replicated. ms_per_step: "
+                                      "fp32 masters gathered on demand (checkpoint time); ms_per_step_masters_gathered_every_step: "
+                                      "also an fp32 all_gather of the masters every step (DDP's every-rank-holds-everything)") if world > 1
                        else "none (one GPU)"}}
 
 

@@ -151,6 +151,27 @@ int mode_adamw_step(mode_engine_t* e, float lr, float beta1, float beta2, float 
 int mode_adamw_step_group(mode_engine_t* e, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                           const float* grad_scale_dev, int group, void* stream);
 int mode_optimizer_state(mode_engine_t* e, float** exp_avg_dev, float** exp_avg_sq_dev, int64_t* numel);
+/* Sharded optimizer state for data-parallel training (replaces DDP's all-reduce + replicated torch.optim.AdamW,
+ * reference mode/training_calvin.py:92-103 + mode_agent.py:267-301, with reduce-scatter -> 1/world of the update per
+ * rank -> all-gather of the bf16 weights). After mode_optimizer_set_sharding(rank, world > 1):
+ *   - group l (0..n_layers-1) holds block l's large tensors that can be split evenly (bf16-packed, 1024-element blocks
+ *     divisible by world; mode_optimizer_shard_tensors lists their (offset, numel) spans of the flat buffers — the
+ *     caller reduce-scatters exactly these, rank r keeping elements [r, r+1) * numel / world of each); every other
+ *     tensor moves to group n_layers and stays replicated (all-reduced by the caller);
+ *   - mode_adamw_step_group(l) updates only this rank's part of each tensor (fp32 master, moments, EMA) and writes the new
+ *     weights as bf16 into the staging buffer (mode_optimizer_staging: gradient layout) instead of the packed copies;
+ *   - after the caller all-gathered the staging spans, mode_optimizer_pack_group(l) writes every packed copy of the group.
+ * The fp32 masters, moments and EMA of a sharded tensor are only current on the owning rank until the caller gathers
+ * them (optim.EngineAdamW.synchronize_parameters / state_dict). world <= 1 switches sharding off. */
+int mode_optimizer_set_sharding(mode_engine_t* e, int rank, int world);
+int mode_optimizer_shard_tensors(mode_engine_t* e, int group, int64_t* offsets, int64_t* numels, int capacity, int* n);
+int mode_optimizer_staging(mode_engine_t* e, void** staging_dev, int64_t* numel);
+int mode_optimizer_pack_group(mode_engine_t* e, int group, void* stream);
+/* Block `layer`'s packed weights become current when the work enqueued so far on `stream` has finished (the engine records
+ * an event it owns). The next call that reads them waits on its own stream: mode_train_step block by block — so the
+ * forward of block 0 starts while the sharded optimizer is still gathering blocks 1..n-1 — every other entry for all
+ * pending blocks before its first launch. */
+int mode_weights_record_ready(mode_engine_t* e, int layer, void* stream);
 /* Exponential moving average of the bound parameters inside the optimizer launch (reference mode/callbacks/ema.py:
  * ema -= (1 - decay) * (ema - w) after every step, :119-126; +8 bytes per parameter instead of a separate pass over
  * all weights). decay in [0, 1] enables it for the following steps (may change every step: ema.py:84-92 warm-up

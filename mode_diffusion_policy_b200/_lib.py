@@ -70,6 +70,11 @@ SYMBOLS = {
     "mode_optimizer_bind": (C.c_int, [_P, C.c_char_p, C.c_void_p, C.c_int]),
     "mode_optimizer_unbind_all": (C.c_int, [_P]),
     "mode_adamw_step": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "mode_optimizer_set_sharding": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mode_optimizer_shard_tensors": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)]),
+    "mode_optimizer_staging": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "mode_optimizer_pack_group": (C.c_int, [_P, C.c_int, C.c_void_p]),
+    "mode_weights_record_ready": (C.c_int, [_P, C.c_int, C.c_void_p]),
     "mode_adamw_step_group": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "mode_optimizer_set_ema": (C.c_int, [_P, C.c_double]),
     "mode_optimizer_ema_state": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

@@ -262,6 +262,12 @@ struct mode_engine {
   int64_t launch_count = 0;
   LayerIO io;                   // inference buffer set (rebuilt by ensure_batch)
   bool train_weights_dirty = true;  // transposed weight copies of the training path are stale
+  // Per-block "packed weights are current" events (mode_weights_record_ready): a sharded data-parallel optimizer finishes
+  // block l's weights on a side stream while the next step's forward is already running; the first launch that reads
+  // block l waits for its event (training forward: block by block; every other entry: all of them up front).
+  std::vector<cudaEvent_t> block_w_ready;
+  std::vector<char> block_w_pending;
+  bool defer_block_waits = false;   // true while mode_train_step enqueues
   cudaEvent_t weights_ready = nullptr;  // recorded on the default stream after the last (re)pack
   bool weights_wait_pending = false;
   TrainState* train = nullptr;  // lazily created by the first training call
@@ -565,6 +571,8 @@ extern "C" void mode_destroy(mode_engine_t* e) {
   }
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->weights_ready) cudaEventDestroy(e->weights_ready);
+  for (cudaEvent_t ev : e->block_w_ready)
+    if (ev) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
 }
@@ -849,9 +857,22 @@ extern "C" int mode_finalize_weights_on_stream(mode_engine_t* e, void* stream) {
 extern "C" int mode_finalize_weights(mode_engine_t* e) { return mode_finalize_weights_on_stream(e, nullptr); }
 
 // ------------------------------------------------------------------------------------------------ batch tables
+// layer < 0: every block with a pending event
+static int wait_block_weights(mode_engine* e, cudaStream_t st, int layer) {
+  if (e->block_w_pending.empty()) return MODE_OK;
+  const int l0 = layer < 0 ? 0 : layer, l1 = layer < 0 ? e->L : layer + 1;
+  for (int l = l0; l < l1; ++l)
+    if (e->block_w_pending[l]) {
+      CU_OK(cudaStreamWaitEvent(st, e->block_w_ready[l], 0));
+      e->block_w_pending[l] = 0;
+    }
+  return MODE_OK;
+}
+
 static int ensure_batch(mode_engine* e, int B, cudaStream_t st) {
   if (B < 1 || B > e->maxB) return fail(MODE_ERR_INVALID, "batch %d outside [1, max_batch=%d]", B, e->maxB);
   if (!e->finalized) return fail(MODE_ERR_STATE, "mode_finalize_weights has not been called");
+  if (!e->defer_block_waits) RET_IF(wait_block_weights(e, st, -1));
   if (e->weights_wait_pending) {
     // weights were (re)packed on the default stream without host synchronisation: order this stream after them
     CU_OK(cudaStreamWaitEvent(st, e->weights_ready, 0));
@@ -1302,8 +1323,10 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
     ROW_PHASE(SP_EMBED, embed_kernel, e->d, row_blocks(B * e->T), st, em);
   }
   CU_OK(cudaGetLastError());
-  for (int l = 0; l < e->L; ++l)
+  for (int l = 0; l < e->L; ++l) {
+    RET_IF(wait_block_weights(e, st, l));
     RET_IF(enqueue_block(e, st, B, l, l + 1 < e->L ? 0 : 1, slot, layer_io ? layer_io[l] : e->io, l + 1 < e->L ? 0 : trim));
+  }
   if (head_mode < 0) {  // training forward: the loss/head backward kernel consumes the final-ln output directly
     e->launch_count += 1;
     return MODE_OK;
@@ -1320,6 +1343,19 @@ static int enqueue_eval(mode_engine* e, cudaStream_t st, int B, const float* sig
   }
   CU_OK(cudaGetLastError());
   e->launch_count += 2;
+  return MODE_OK;
+}
+
+extern "C" int mode_weights_record_ready(mode_engine_t* e, int layer, void* stream) {
+  if (!e) return fail(MODE_ERR_INVALID, "null engine");
+  if (layer < 0 || layer >= e->L) return fail(MODE_ERR_INVALID, "block %d out of range", layer);
+  if (e->block_w_ready.empty()) {
+    e->block_w_ready.assign(e->L, nullptr);
+    e->block_w_pending.assign(e->L, 0);
+  }
+  if (!e->block_w_ready[layer]) CU_OK(cudaEventCreateWithFlags(&e->block_w_ready[layer], cudaEventDisableTiming));
+  CU_OK(cudaEventRecord(e->block_w_ready[layer], reinterpret_cast<cudaStream_t>(stream)));
+  e->block_w_pending[layer] = 1;
   return MODE_OK;
 }
 

@@ -40,7 +40,36 @@ struct AdamWParams {
   float* ema;
   float ema_one_minus_decay;
   int ema_init;
+  // Sharded update (data-parallel ranks each own 1/shard_world of every tensor of the launch, mode_optimizer_set_sharding):
+  // the launch has 1/shard_world of the blocks; block j of a tensor's shard is block shard_rank * (blocks / shard_world) + j
+  // of the tensor. The updated weights go to `staging` (bf16, gradient layout) instead of the packed copy: the ranks
+  // all-gather the staging spans and re-pack them locally (pack_from_staging_kernel). shard_world <= 1: off.
+  int shard_rank, shard_world;
+  __nv_bfloat16* staging;
 };
+
+// block -> (tensor, first element). Shards: every tensor of the launch has a block count divisible by shard_world (host
+// checked), so block0 / shard_world indexes the launch's blocks.
+__device__ __forceinline__ OptTensor opt_find_tensor(const AdamWParams& a, size_t& base) {
+  const unsigned W = a.shard_world > 1 ? a.shard_world : 1;
+  const unsigned q = blockIdx.x + a.block_base / W;
+  int lo = 0, hi = a.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (a.tab[mid].block0 / W <= q)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const OptTensor t = a.tab[lo];
+  unsigned blk = q - t.block0 / W;
+  if (W > 1) {
+    const size_t numel = static_cast<size_t>(t.rows) * t.cols;
+    blk += a.shard_rank * static_cast<unsigned>(numel / OPT_BLOCK_ELEMS / W);
+  }
+  base = static_cast<size_t>(blk) * OPT_BLOCK_ELEMS;
+  return t;
+}
 
 __device__ __forceinline__ float ema_update(float ema, float p_old, float p_new, const AdamWParams& a) {
   const float e = a.ema_init ? p_old : ema;
@@ -64,17 +93,9 @@ __device__ __forceinline__ float adamw_update(float p, float g, float& m, float&
 
 __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
   // which tensor does this block belong to? (binary search over the first-block table; a few hundred entries)
-  int lo = 0, hi = a.n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (a.tab[mid].block0 <= blockIdx.x + a.block_base)
-      lo = mid;
-    else
-      hi = mid - 1;
-  }
-  const OptTensor t = a.tab[lo];
+  size_t base;
+  const OptTensor t = opt_find_tensor(a, base);
   const size_t numel = static_cast<size_t>(t.rows) * t.cols;
-  const size_t base = static_cast<size_t>(blockIdx.x + a.block_base - t.block0) * OPT_BLOCK_ELEMS;
   const float gs = a.grad_scale ? *a.grad_scale : 1.0f;
   const float decay_mul = t.decay ? 1.0f - a.lr * a.wd : 1.0f;
   if (!t.transpose && (t.cols & 3) == 0 && (t.g_off & 3) == 0 && (reinterpret_cast<uintptr_t>(t.p) & 15) == 0) {
@@ -101,6 +122,13 @@ __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
       em.z = ema_update(em.z, p_old.z, p.z, a);
       em.w = ema_update(em.w, p_old.w, p.w, a);
       *reinterpret_cast<float4*>(a.ema + gi) = em;
+    }
+    if (a.staging) {  // sharded: bf16 in gradient layout, packed after the all-gather (host: to_bf16 tensors only)
+      uint2 pk;
+      pk.x = pack_bf16x2(p.x, p.y);
+      pk.y = pack_bf16x2(p.z, p.w);
+      *reinterpret_cast<uint2*>(a.staging + gi) = pk;
+      return;
     }
     const int r = static_cast<int>(i / t.cols), c = static_cast<int>(i % t.cols);
     const size_t o = (t.dst_row0 + opt_dst_row(r, t.swiglu_half)) * static_cast<size_t>(t.cols) + c;
@@ -136,6 +164,20 @@ __global__ void __launch_bounds__(256) adamw_pack_kernel(const AdamWParams a) {
         reinterpret_cast<float*>(t.dst)[o] = p;
     }
   }
+}
+
+// After the all-gather of a sharded group's staging spans: every rank writes the packed bf16 copies of ALL of the group's
+// tensors (SwiGLU row interleave, row offsets) from the gathered bf16 values. Same block -> tensor table, whole tensors.
+__global__ void __launch_bounds__(256) pack_from_staging_kernel(AdamWParams a) {
+  a.shard_world = 1;
+  size_t base;
+  const OptTensor t = opt_find_tensor(a, base);
+  const size_t i = base + threadIdx.x * 4;
+  if (i >= static_cast<size_t>(t.rows) * t.cols) return;
+  const uint2 pk = *reinterpret_cast<const uint2*>(a.staging + t.g_off + i);
+  const int r = static_cast<int>(i / t.cols), c = static_cast<int>(i % t.cols);
+  const size_t o = (t.dst_row0 + opt_dst_row(r, t.swiglu_half)) * static_cast<size_t>(t.cols) + c;
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t.dst) + o) = pk;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

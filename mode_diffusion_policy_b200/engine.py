@@ -272,6 +272,44 @@ class ModeEngine:
         h.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         return torch.as_tensor(h, device=self.device)
 
+    def set_optimizer_sharding(self, rank: int, world: int) -> None:
+        """Each data-parallel rank updates 1/world of every large per-block tensor (`mode_optimizer_set_sharding`);
+        world <= 1 switches it off."""
+        self.has_train_state = True
+        _lib.check(self.lib.mode_optimizer_set_sharding(self._h, int(rank), max(int(world), 1)))
+
+    def optimizer_shard_tensors(self, group: int):
+        """(offset, numel) spans of the flat buffers that block `group`'s optimizer launch covers (the tensors a sharded
+        step reduce-scatters / all-gathers)."""
+        n = C.c_int()
+        _lib.check(self.lib.mode_optimizer_shard_tensors(self._h, int(group), None, None, 0, C.byref(n)))
+        offs, nums = (C.c_int64 * max(n.value, 1))(), (C.c_int64 * max(n.value, 1))()
+        _lib.check(self.lib.mode_optimizer_shard_tensors(self._h, int(group), offs, nums, n.value, C.byref(n)))
+        return [(int(offs[i]), int(nums[i])) for i in range(n.value)]
+
+    def optimizer_staging(self) -> torch.Tensor:
+        """Zero-copy bf16 view of the sharded optimizer's all-gather buffer (gradient-buffer layout)."""
+        self.has_train_state = True
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.mode_optimizer_staging(self._h, C.byref(p), C.byref(n)))
+
+        class _Dev:
+            pass
+
+        h = _Dev()
+        h.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<i2", "data": (p.value, False), "version": 2}
+        return torch.as_tensor(h, device=self.device).view(torch.bfloat16)
+
+    def optimizer_pack_group(self, group: int, stream: Optional["torch.cuda.Stream"] = None) -> None:
+        """Packed bf16 copies of block `group`'s tensors from the (all-gathered) staging buffer."""
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
+        _lib.check(self.lib.mode_optimizer_pack_group(self._h, int(group), st))
+
+    def weights_record_ready(self, layer: int, stream: "torch.cuda.Stream") -> None:
+        """Block `layer`'s packed weights are current once `stream`'s work so far is done; the next engine call that reads
+        them waits for that on its own stream (`mode_weights_record_ready`)."""
+        _lib.check(self.lib.mode_weights_record_ready(self._h, int(layer), C.c_void_p(stream.cuda_stream)))
+
     def set_ema(self, decay: Optional[float]) -> None:
         """Moving average of the bound parameters inside the optimizer launch (reference mode/callbacks/ema.py);
         None switches it off."""

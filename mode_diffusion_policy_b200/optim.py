@@ -52,6 +52,7 @@ class EngineAdamW(torch.optim.Optimizer):
     def ema_state_dict(self):
         """name -> EMA tensor (reference layout, views of the engine's buffer) for every parameter this optimizer updates."""
         eng = self.inner._engine
+        self._gather_sharded_state(eng)
         flat = eng.ema_state()
         params = dict(self.inner.named_parameters())
         out = {}
@@ -144,6 +145,8 @@ class EngineAdamW(torch.optim.Optimizer):
         eng = getattr(self.inner, "_engine", None)
         if eng is None:
             raise RuntimeError("EngineAdamW.step_overlapped before any GCDenoiser.loss call")
+        if getattr(self, "_exchange", None) is not None and reducer is not self._exchange:
+            raise RuntimeError("this optimizer's state is sharded over the ranks (step_sharded was used): keep using step_sharded")
         self._bind(eng)
         self._check_fresh_gradients(eng)
         g = self.param_groups[0]
@@ -194,6 +197,170 @@ class EngineAdamW(torch.optim.Optimizer):
         mark("adamw_rest", opt_stream)
         main.wait_stream(opt_stream)
 
+    @torch.no_grad()
+    def step_sharded(self, exchange, loss_scale=None, master_sync: str = "step", overlap_forward: bool = True,
+                     timeline=None) -> None:
+        """Data-parallel step with the optimizer state sharded over the ranks (`parallel.ShardedGradExchange`).
+
+        Replaces DDP's all-reduce + replicated AdamW (reference mode/training_calvin.py:92-103, mode_agent.py:267-301):
+        per block, last block first, (1) reduce-scatter(mean) of the block's large gradient tensors as soon as its
+        backward is done, (2) this rank's 1/world of the fused AdamW (+ EMA) launch, which writes the new weights as bf16
+        into the staging buffer, (3) all-gather of the staging spans, (4) re-pack of the block's bf16 GEMM operands from
+        the gathered values; collectives on the exchange stream, updates and re-packs on a second one, so block l's
+        HBM-bound update runs while block l+1's weights are on the wire. The remaining (small / non-block) tensors are all-reduced
+        and updated on every rank as in `step_overlapped`. The same elements are averaged and updated by the same
+        arithmetic as in the replicated step — each by exactly one rank — so every rank ends the step with identical
+        packed weights; the wire carries 6 instead of 8 bytes per parameter and the HBM-bound optimizer pass shrinks by
+        the number of ranks.
+
+        `loss_scale`: as in `step_overlapped` (None = wait for autograd's incoming gradient of the loss, i.e. for the
+        end of the backward, before the first update; a float = the caller guarantees that constant, updates start as
+        soon as a block's gradients are reduced).
+
+        `overlap_forward`: the caller's stream only waits for the small replicated tensors; each block's new weights are
+        handed to the engine with a per-block event (`mode_weights_record_ready`), so the next `loss()` starts its forward
+        while later blocks are still being updated / gathered, and any other engine call waits for all of them. False: the
+        caller's stream waits for the whole step.
+
+        `master_sync`: the fp32 master parameters, the moments and the EMA of a sharded tensor are only current on the
+        rank that owns the element. "step" (default): the masters are all-gathered at the end of every step on the
+        exchange stream, off the critical path (the next step's forward does not read them; `synchronize_parameters()`
+        makes the caller's stream wait for it). "lazy": only when `synchronize_parameters()` is called (a collective:
+        every rank must call it, e.g. before `state_dict()` / checkpointing / evaluation through other modules)."""
+        eng = getattr(self.inner, "_engine", None)
+        if eng is None:
+            raise RuntimeError("EngineAdamW.step_sharded before any GCDenoiser.loss call")
+        if not exchange.active():
+            return self.step_overlapped(exchange, timeline=timeline, loss_scale=loss_scale)
+        self._bind(eng)
+        exchange.prepare()
+        self._exchange = exchange
+        self._check_fresh_gradients(eng)
+        g = self.param_groups[0]
+        self._step += 1
+        self._set_ema(eng)
+        dev = eng.device
+        if loss_scale is None:
+            scale = self.inner._loss_grad_scale
+        elif float(loss_scale) == 1.0:
+            scale = None
+        else:
+            if getattr(self, "_const_scale", None) is None or float(self._const_scale[0]) != float(loss_scale):
+                self._const_scale = (float(loss_scale), torch.full((1,), float(loss_scale), dtype=torch.float32, device=dev))
+                torch.cuda.current_stream(dev).synchronize()
+            scale = self._const_scale[1]
+        args = (g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._step, scale)
+        main = torch.cuda.current_stream(dev)
+        xs = exchange.stream
+
+        def mark(label, stream):
+            if timeline is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                timeline.append((label, ev))
+
+        mark("backward_done", main)
+        L = exchange.n_layers
+        if getattr(self, "_opt_stream", None) is None:
+            self._opt_stream = torch.cuda.Stream(device=dev)
+        os_ = self._opt_stream  # updates and re-packs (HBM-bound) run next to the collectives (NVLink-bound) of other blocks
+
+        def update(layer):     # this rank's 1/world of block `layer`, once its gradients are reduced
+            os_.wait_event(scattered[layer])
+            eng.adamw_step(*args, group=layer, stream=os_)
+            updated[layer] = torch.cuda.Event()
+            updated[layer].record(os_)
+
+        def gather(layer):     # the block's new bf16 weights from every rank, then the packed GEMM operands
+            xs.wait_event(updated[layer])
+            exchange.gather_weights_layer(layer)
+            ev = torch.cuda.Event()
+            ev.record(xs)
+            os_.wait_event(ev)
+            eng.optimizer_pack_group(layer, stream=os_)
+            if overlap_forward:
+                eng.weights_record_ready(layer, os_)  # the next forward waits for this block only when it gets there
+            mark(f"weights_{layer}", os_)
+
+        def rest():            # small and non-block tensors: all-reduced, updated on every rank
+            exchange.reduce_tail()
+            os_.wait_stream(xs)
+            eng.adamw_step(*args, group=L, stream=os_)
+            mark("adamw_rest", os_)
+            if overlap_forward:
+                main.wait_stream(os_)  # embeddings, norms, router: read by the first launches of the next forward
+
+        scattered, updated = {}, {}
+        backward_order = list(range(L - 1, -1, -1))  # the backward finishes the last block first
+        if loss_scale is None:
+            # the scale is produced on the caller's stream after the backward: reduce-scatter everything while the
+            # backward runs, then update + gather, software-pipelined over the two streams — block 0 first when the next
+            # forward may overlap (it needs block 0 first)
+            for layer in backward_order:
+                exchange.reduce_scatter_layer(layer)
+                scattered[layer] = torch.cuda.Event()
+                scattered[layer].record(xs)
+                mark(f"scatter_{layer}", xs)
+            os_.wait_stream(main)
+            rest()
+            order = list(range(L)) if overlap_forward else backward_order
+            for i, layer in enumerate(order):
+                update(layer)
+                if i >= 1:
+                    gather(order[i - 1])
+            gather(order[-1])
+        else:
+            # collectives in the order scatter(l), gather(l + 1): the update of block l runs while block l - 1 is on the wire
+            order = backward_order
+            for i, layer in enumerate(order):
+                exchange.reduce_scatter_layer(layer)
+                scattered[layer] = torch.cuda.Event()
+                scattered[layer].record(xs)
+                mark(f"scatter_{layer}", xs)
+                update(layer)
+                if i >= 1:
+                    gather(order[i - 1])
+            rest()
+            gather(order[-1])
+        if not overlap_forward:
+            main.wait_stream(os_)
+        self._masters_stale = True
+        if master_sync == "step":
+            self._gather_masters()
+        elif master_sync != "lazy":
+            raise ValueError("master_sync must be 'step' or 'lazy'")
+
+    def _gather_masters(self) -> None:
+        ex = getattr(self, "_exchange", None)
+        if ex is None or not getattr(self, "_masters_stale", False):
+            return
+        ex.stream.wait_stream(self._opt_stream)  # every owner's update of this step
+        ex.gather_parameters(dict(self.inner.named_parameters()))
+        self._masters_ready = torch.cuda.Event()
+        self._masters_ready.record(ex.stream)
+        self._masters_stale = False
+
+    def synchronize_parameters(self) -> None:
+        """After sharded steps: make the caller's stream see fully updated fp32 master parameters on every rank (a
+        collective if the gather is still pending: call it on all ranks)."""
+        self._gather_masters()
+        ev = getattr(self, "_masters_ready", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.inner._engine.device).wait_event(ev)
+
+    def _gather_sharded_state(self, eng) -> None:
+        """Moments and EMA of sharded tensors live on the owning rank: gather them before they are read whole."""
+        ex = getattr(self, "_exchange", None)
+        if ex is None or ex.layers is None or self._step == 0:
+            return
+        m, v = eng.optimizer_state()
+        bufs = [m, v] + ([eng.ema_state()] if self._ema_decay is not None else [])
+        if getattr(self, "_opt_stream", None) is not None:
+            ex.stream.wait_stream(self._opt_stream)
+        for b in bufs:
+            ex.gather_flat(b)
+        torch.cuda.current_stream(eng.device).wait_stream(ex.stream)
+
     def state_dict(self):
         """Moments, the EMA buffer (the reference's EMA callback checkpoints its averages, ema.py:137-160) and the
         position of the counter-based train-mode random stream, so a resumed run neither re-seeds the average nor replays
@@ -202,6 +369,7 @@ class EngineAdamW(torch.optim.Optimizer):
               "train_rng": (getattr(self.inner, "_train_seed", None), getattr(self.inner, "_train_step", 0))}
         eng = getattr(self.inner, "_engine", None)
         if eng is not None and self._step > 0:
+            self._gather_sharded_state(eng)  # sharded steps: a collective, state_dict() must then run on every rank
             m, v = eng.optimizer_state()
             sd["exp_avg"], sd["exp_avg_sq"] = m.clone(), v.clone()
             if self._ema_decay is not None:

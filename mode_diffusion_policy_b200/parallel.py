@@ -7,7 +7,9 @@ gathering the (B, 10, 7) action chunks for a single caller.
 Training: the one exchange step is the all-reduce (mean) of the engine's flat gradient buffer. `GradAllReduce` issues it
 bucketed by layer on a side stream, gated by the engine's per-layer "gradients final" events, so NCCL moves layer l's
 weight gradients over NVLink while the backward of layers l-1..0 is still running (what DDP's reducer hooks do in the
-reference, mode/training_calvin.py:97)."""
+reference, mode/training_calvin.py:97). `ShardedGradExchange` splits that all-reduce around the optimizer:
+reduce-scatter -> each rank updates 1/world of every large tensor -> all-gather of the bf16 weights (half the bytes of
+the fp32 gradients), which also divides the HBM-bound AdamW pass by the number of ranks."""
 from __future__ import annotations
 
 import torch
@@ -144,3 +146,124 @@ class GradAllReduce:
             self.reduce_layer(layer)
         self.reduce_tail()
         main.wait_stream(self.stream)
+
+
+def shard_span(off: int, numel: int, rank: int, world: int) -> tuple[int, int]:
+    """Rank `rank`'s contiguous 1/world of the span (offset, numel); numel must divide evenly."""
+    if numel % world:
+        raise ValueError(f"span of {numel} elements does not split over {world} ranks")
+    n = numel // world
+    return off + rank * n, n
+
+
+def plan_shards(tensors_per_layer: list[list[tuple[int, int]]], total: int):
+    """Exchange plan of the sharded optimizer: tensors_per_layer[l] = (offset, numel) of block l's sharded tensors (what
+    `mode_optimizer_shard_tensors` lists). Returns (per-layer spans sorted by offset, tail) where `tail` are the spans of
+    [0, total) no sharded tensor covers (replicated parameters: all-reduced as before)."""
+    layers = [sorted(t) for t in tensors_per_layer]
+    tail, cur = [], 0
+    for off, n in sorted(sp for lay in layers for sp in lay):
+        if off < cur:
+            raise ValueError("overlapping sharded tensors")
+        if off > cur:
+            tail.append((cur, off - cur))
+        cur = off + n
+    if cur < total:
+        tail.append((cur, total - cur))
+    return layers, tail
+
+
+def reduce_scatter_mean(span: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """In place: afterwards this rank's 1/world slice of `span` holds the mean over ranks (the other slices are
+    unspecified). NCCL: one reduce_scatter(AVG) whose output aliases its slot of the input; other backends (the CPU
+    tests run gloo, which has neither reduce_scatter nor AVG): all_reduce + divide."""
+    off, n = shard_span(0, span.numel(), rank, world)
+    mine = span[off: off + n]
+    if span.is_cuda:
+        dist.reduce_scatter_tensor(mine, span, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(span, group=group)
+        mine /= world
+    return mine
+
+
+def all_gather_in_place(span: torch.Tensor, rank: int, world: int, group=None) -> None:
+    """Every rank contributes its 1/world slice of `span`; afterwards all of `span` is current everywhere."""
+    off, n = shard_span(0, span.numel(), rank, world)
+    if span.is_cuda:
+        dist.all_gather_into_tensor(span, span[off: off + n], group=group)
+    else:
+        parts = [torch.empty(n, dtype=span.dtype) for _ in range(world)]
+        dist.all_gather(parts, span[off: off + n].clone(), group=group)
+        for r, part in enumerate(parts):
+            span[r * n: (r + 1) * n] = part
+
+
+class ShardedGradExchange(GradAllReduce):
+    """Exchange half of the sharded data-parallel step (`optim.EngineAdamW.step_sharded`).
+
+    Per block, on the side stream: reduce-scatter(mean) of the block's large gradient tensors, so that rank r holds the
+    averaged gradient of elements [r, r+1) * numel / world of each; after that rank's optimizer launch wrote its part
+    of the new weights (bf16, staging buffer), all-gather of the staging spans. Everything else (small tensors,
+    non-block parameters, tensors that do not split evenly) is all-reduced at the end like `GradAllReduce.reduce_tail`.
+    Compared with all-reduce + a replicated update, the wire carries 4 + 2 instead of 4 + 4 bytes per parameter and every
+    rank runs 1/world of the HBM-bound optimizer pass."""
+
+    def __init__(self, engine, param_names, n_layers: int, group=None):
+        self.engine, self.group, self.n_layers = engine, group, n_layers
+        self.param_names = list(param_names)
+        self.flat = engine.flat_grads()
+        self.stream = torch.cuda.Stream(device=self.flat.device)
+        self.coalesce = hasattr(dist, "_coalescing_manager")
+        self.rank = dist.get_rank(group) if self.active() else 0
+        self.world = dist.get_world_size(group) if self.active() else 1
+        self.layers = None  # planned by prepare(), once the optimizer has bound its parameters
+
+    def prepare(self) -> None:
+        """Switch the engine's optimizer to sharded groups and read back which tensors it shards (idempotent)."""
+        if self.layers is not None:
+            return
+        eng = self.engine
+        eng.set_optimizer_sharding(self.rank, self.world)
+        self.layers, self.tail = plan_shards([eng.optimizer_shard_tensors(l) for l in range(self.n_layers)], self.flat.numel())
+        self.staging = eng.optimizer_staging()
+        by_offset = {eng.grad_range(n)[0]: n for n in self.param_names}
+        self.names = [[by_offset[off] for off, _ in lay] for lay in self.layers]  # parameter of every sharded span
+
+    def _spans(self, buf, layer):
+        return [buf[off: off + n] for off, n in self.layers[layer]]
+
+    def _grouped(self, fn, views) -> None:
+        """One NCCL group launch for a block's ~12 spans."""
+        if not views:
+            return
+        with torch.cuda.stream(self.stream):
+            if self.coalesce and len(views) > 1:
+                with dist._coalescing_manager(group=self.group, device=self.flat.device, async_ops=False):
+                    for v in views:
+                        fn(v)
+            else:
+                for v in views:
+                    fn(v)
+
+    def reduce_scatter_layer(self, layer: int) -> None:
+        self.engine.wait_grads(layer, self.stream)
+        self._grouped(lambda v: reduce_scatter_mean(v, self.rank, self.world, self.group), self._spans(self.flat, layer))
+
+    def gather_weights_layer(self, layer: int) -> None:
+        """All-gather block `layer`'s bf16 staging spans (enqueue after that block's optimizer launch on this stream)."""
+        self._grouped(lambda v: all_gather_in_place(v, self.rank, self.world, self.group), self._spans(self.staging, layer))
+
+    def gather_flat(self, buf: torch.Tensor) -> None:
+        """All-gather every sharded span of a flat buffer with the gradient layout (moments, EMA) on the side stream."""
+        for layer in range(self.n_layers):
+            self._grouped(lambda v: all_gather_in_place(v, self.rank, self.world, self.group), self._spans(buf, layer))
+
+    def gather_parameters(self, params: dict) -> None:
+        """All-gather the fp32 masters of the sharded tensors (each rank only updated its part) on the side stream."""
+        for layer in range(self.n_layers):
+            views = [params[n].data.view(-1) for n in self.names[layer]]
+            self._grouped(lambda v: all_gather_in_place(v, self.rank, self.world, self.group), views)
+
+    def run(self) -> None:
+        raise RuntimeError("ShardedGradExchange is driven by optim.EngineAdamW.step_sharded")

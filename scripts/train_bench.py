@@ -66,7 +66,9 @@ reducer = None
 
 TIMELINE = [] if os.environ.get("MODE_TRAIN_TIMELINE") == "1" else None  # per-stream event marks of the last step
 # MODE_TRAIN_PIPELINE: 1 = exchange + optimizer pipelined per layer behind the backward (default for N > 1);
-# 2 = additionally let block l's update start while blocks l-1..0 are still in backward (also valid on one GPU)
+# 2 = additionally let block l's update start while blocks l-1..0 are still in backward (also valid on one GPU);
+# 3 = sharded optimizer (reduce-scatter -> 1/world AdamW -> bf16 all-gather, optim.EngineAdamW.step_sharded) behind the
+# backward; 4 = sharded with updates starting during the backward. MODE_TRAIN_MASTER_SYNC=step|lazy (sharded modes)
 pipe_mode = int(os.environ.get("MODE_TRAIN_PIPELINE", "1" if world > 1 else "0"))
 pipelined = pipe_mode > 0 and hasattr(opt, "step_overlapped")
 
@@ -75,6 +77,18 @@ def step():
     global reducer
     opt.zero_grad(set_to_none=True)
     loss, _ = model.loss({"state_images": S}, A_, G, noise, sigma)
+    if pipelined and pipe_mode >= 3 and world > 1:
+        if reducer is None:
+            reducer = parallel.ShardedGradExchange(inner._engine, [n for n, _ in inner.named_parameters()
+                                                                   if n != "gripper_embed.weight"], a.layers)
+        sync = os.environ.get("MODE_TRAIN_MASTER_SYNC", "step")
+        ofw = os.environ.get("MODE_TRAIN_OVERLAP_FWD", "1") == "1"
+        if pipe_mode >= 4:
+            opt.step_sharded(reducer, loss_scale=1.0, master_sync=sync, overlap_forward=ofw, timeline=TIMELINE)
+        else:
+            loss.backward()
+            opt.step_sharded(reducer, master_sync=sync, overlap_forward=ofw, timeline=TIMELINE)
+        return loss
     if pipelined:  # exchange and optimizer pipelined per layer (optim.EngineAdamW.step_overlapped)
         if reducer is None:
             reducer = parallel.GradAllReduce(inner._engine, [n for n, _ in inner.named_parameters()
@@ -111,6 +125,8 @@ for _ in range(a.steps):
         t_start = torch.cuda.Event(enable_timing=True)
         t_start.record()
     loss = step()
+if getattr(opt, "_opt_stream", None) is not None:  # the last step's updates still in flight on the optimizer's stream
+    torch.cuda.current_stream().wait_stream(opt._opt_stream)
 e1.record()
 if world > 1:
     dist.barrier()
@@ -127,6 +143,6 @@ if rank == 0:
                       "approx_tflops": 3 * fwd_flops * a.steps / (ms * 1e-3) / 1e12,
                       "config": {"workload": f"MoDE {a.layers}L d=1024 E=4 top-2, B={B}/GPU, fwd+bwd+all-reduce+AdamW+repack",
                                  "regularisation": ("attn_pdrop 0.3, mlp_pdrop 0.1, goal_drop 0.1, per-token multinomial routing" if a.stochastic else "none (deterministic mode)"), "optimizer": opt_name,
-                                 "grad_allreduce": ("per-layer NCCL all-reduce buckets pipelined with per-layer fused AdamW launches (step_overlapped)" if pipelined else "per-layer NCCL all-reduce buckets of the flat fp32 gradient buffer, overlapped with backward" if ap_overlap else "one NCCL all-reduce over the flat fp32 gradient buffer")}}), flush=True)
+                                 "grad_allreduce": (f"sharded optimizer (reduce-scatter, 1/{world} AdamW per rank, bf16 all-gather; mode {pipe_mode}, master sync {os.environ.get('MODE_TRAIN_MASTER_SYNC', 'step')})" if pipelined and pipe_mode >= 3 and world > 1 else "per-layer NCCL all-reduce buckets pipelined with per-layer fused AdamW launches (step_overlapped)" if pipelined else "per-layer NCCL all-reduce buckets of the flat fp32 gradient buffer, overlapped with backward" if ap_overlap else "one NCCL all-reduce over the flat fp32 gradient buffer")}}), flush=True)
 if world > 1:
     dist.destroy_process_group()

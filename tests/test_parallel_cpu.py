@@ -106,3 +106,74 @@ def _bucket_worker(rank, world, port):
 
 def test_two_rank_bucketed_gradient_average_equals_mean():
     mp.spawn(_bucket_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_shard_plan_covers_the_flat_buffer_and_splits_evenly():
+    per_layer, total, _ = _layout()
+    big = [[sp for sp in lay if sp[1] >= 64] for lay in per_layer]  # what the engine would list as sharded tensors
+    layers, tail = P.plan_shards(big, total)
+    seen = torch.zeros(total, dtype=torch.int32)
+    for off, n in [sp for lay in layers for sp in lay] + tail:
+        seen[off: off + n] += 1
+    assert bool((seen == 1).all())
+    for world in (2, 4, 8):
+        for off, n in layers[0]:
+            parts = [P.shard_span(off, n, r, world) for r in range(world)]
+            assert parts[0][0] == off and sum(m for _, m in parts) == n
+            assert all(parts[r][0] + parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+    with pytest.raises(ValueError):
+        P.shard_span(0, 10, 0, 4)
+    with pytest.raises(ValueError):
+        P.plan_shards([[(0, 100)], [(50, 100)]], 200)
+
+
+def _adam_like(p, g, m, v):
+    """Any element-wise optimizer arithmetic (what matters: every element sees the same inputs in both schedules)."""
+    m.mul_(0.9).add_(g, alpha=0.1)
+    v.mul_(0.95).addcmul_(g, g, value=0.05)
+    p.mul_(1 - 1e-3).addcdiv_(m, v.sqrt() + 1e-8, value=-1e-2)
+
+
+def _sharded_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        per_layer, total, _ = _layout()
+        layers, tail = P.plan_shards([[sp for sp in lay if sp[1] >= 64] for lay in per_layer], total)
+        gen = torch.Generator().manual_seed(3)
+        p0 = torch.randn(total, generator=gen)
+        # replicated schedule: all-reduce(mean) everything, every rank updates everything
+        pa, ma, va = p0.clone(), torch.zeros(total), torch.zeros(total)
+        # sharded schedule: reduce-scatter, update the own 1/world of every sharded span, all-gather the new values
+        pb, mb, vb = p0.clone(), torch.zeros(total), torch.zeros(total)
+        for step in range(3):
+            g_local = torch.randn(total, generator=torch.Generator().manual_seed(100 * step + rank))
+            ga = g_local.clone()
+            dist.all_reduce(ga)
+            ga /= world
+            _adam_like(pa, ga, ma, va)
+            gb = g_local.clone()
+            for layer in range(len(layers) - 1, -1, -1):
+                for off, n in layers[layer]:
+                    mine = P.reduce_scatter_mean(gb[off: off + n], rank, world)
+                    so, sn = P.shard_span(off, n, rank, world)
+                    assert mine.data_ptr() == gb[so: so + sn].data_ptr()
+                    _adam_like(pb[so: so + sn], mine, mb[so: so + sn], vb[so: so + sn])
+                    P.all_gather_in_place(pb[off: off + n], rank, world)
+            for off, n in tail:
+                dist.all_reduce(gb[off: off + n])
+                gb[off: off + n] /= world
+                _adam_like(pb[off: off + n], gb[off: off + n], mb[off: off + n], vb[off: off + n])
+        assert torch.equal(pa, pb)  # identical weights on every rank, bit for bit (each element updated once, by one rank)
+        for buf_a, buf_b in ((ma, mb), (va, vb)):  # moments: current on the owner until gathered
+            for lay in layers:
+                for off, n in lay:
+                    P.all_gather_in_place(buf_b[off: off + n], rank, world)
+            assert torch.equal(buf_a, buf_b)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_update_equals_replicated_update():
+    mp.spawn(_sharded_worker, args=(2, _free_port()), nprocs=2, join=True)
