@@ -479,6 +479,99 @@ def test_grouped_optimizer_launches_equal_the_single_launch():
     assert torch.equal(ma, mb) and torch.equal(va, vb)
 
 
+def test_sharded_optimizer_groups_equal_the_replicated_update():
+    """The sharded data-parallel step on ONE GPU, with two engines playing ranks 0 and 1 of a world of 2 on the same
+    batch (so the "averaged" gradient is the local one): each updates its half of every large tensor
+    (`mode_optimizer_set_sharding` + `mode_adamw_step_group`), the halves of the bf16 staging buffer are exchanged by
+    hand (what the all-gather does), `mode_optimizer_pack_group` re-packs, `mode_weights_record_ready` hands the block to
+    the next forward. Against the replicated `step()`: bit-identical next losses (packed weights + the backward's
+    transposed copies), masters / moments / EMA identical on the owner's half and untouched on the other."""
+    from mode_diffusion_policy_b200 import parallel
+    from mode_diffusion_policy_b200.optim import EngineAdamW
+
+    cfg = O.ModeConfig(obs_dim=64, goal_dim=64, action_dim=7, embed_dim=1024, n_layers=2, n_heads=8, n_state_tokens=2,
+                       action_seq_len=10, num_experts=2, top_k=2)
+    B, L = 6, 2
+    sd = O.make_weights_fast(cfg, seed=1234)
+    state, goal, x0 = O.make_inputs(cfg, B, seed=4321)
+    rng = np.random.default_rng(5)
+    st = {"state_images": cu(state)}
+    acts, goal_t = cu((x0 / np.float32(80.0)).astype(np.float32)), cu(goal)
+    noise = cu(rng.standard_normal(x0.shape).astype(np.float32))
+    sig = cu(np.exp(rng.uniform(np.log(1e-3), np.log(80.0), B)).astype(np.float32))
+    hp = dict(lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05, ema_decay=0.99)
+    (inner_r, model_r), ranks = _tiny_denoiser(sd, cfg), [_tiny_denoiser(sd, cfg) for _ in range(2)]
+    opt_r, opts = EngineAdamW(inner_r, **hp), [EngineAdamW(inner, **hp) for inner, _ in ranks]
+    side = torch.cuda.Stream()
+    plans = None
+    for it in range(3):
+        lr_, _ = model_r.loss(st, acts, goal_t, noise, sig)
+        lr_.backward()
+        opt_r.step()
+        losses = []
+        for (inner, model), opt in zip(ranks, opts):
+            l, _ = model.loss(st, acts, goal_t, noise, sig)
+            l.backward()
+            losses.append(float(l))
+        assert losses == [float(lr_)] * 2, (it, losses, float(lr_))
+        engs = [inner._engine for inner, _ in ranks]
+        for r, (eng, opt) in enumerate(zip(engs, opts)):
+            opt._bind(eng)
+            eng.set_optimizer_sharding(r, 2)
+            opt._step += 1
+            opt._set_ema(eng)
+        if plans is None:
+            plans = [engs[0].optimizer_shard_tensors(l) for l in range(L)]
+            assert all(len(p) == 4 + 2 * cfg.num_experts for p in plans)  # q, k, v, c_proj, expert up / down
+            layers, tail = parallel.plan_shards(plans, engs[0].flat_grads().numel())
+            assert layers == [sorted(p) for p in plans] and len(tail) >= 1
+            with pytest.raises(RuntimeError, match="sharded"):
+                engs[0].adamw_step(hp["lr"], 0.9, 0.95, 1e-8, 0.05, 1)  # the single-launch update would skip the gather
+        g = (hp["lr"], hp["betas"][0], hp["betas"][1], hp["eps"], hp["weight_decay"])
+        torch.cuda.current_stream().synchronize()
+        for l in range(L):
+            for r, (eng, opt) in enumerate(zip(engs, opts)):
+                eng.adamw_step(*g, opt._step, opt.inner._loss_grad_scale, group=l, stream=side)
+            stg = [eng.optimizer_staging() for eng in engs]
+            with torch.cuda.stream(side):
+                for off, n in plans[l]:  # the all-gather: every rank receives the other rank's half
+                    stg[1][off: off + n // 2] = stg[0][off: off + n // 2]
+                    stg[0][off + n // 2: off + n] = stg[1][off + n // 2: off + n]
+            for eng in engs:
+                eng.optimizer_pack_group(l, stream=side)
+                eng.weights_record_ready(l, side)  # the next loss() waits for this on its own stream, block by block
+        for eng, opt in zip(engs, opts):
+            eng.adamw_step(*g, opt._step, opt.inner._loss_grad_scale, group=L, stream=side)
+        torch.cuda.current_stream().wait_stream(side)  # group n_layers: embeddings etc., read by the first launches
+    torch.cuda.synchronize()
+    ref = dict(inner_r.named_parameters())
+    m_r, v_r = inner_r._engine.optimizer_state()
+    ema_r = inner_r._engine.ema_state()
+    init = {k: torch.from_numpy(v).cuda() for k, v in sd.items()}
+    sharded_names = {inner_r._engine.grad_range(n)[0]: n for n in ref if n != "gripper_embed.weight"}
+    for r, (inner, _) in enumerate(ranks):
+        mine = dict(inner.named_parameters())
+        m, v = inner._engine.optimizer_state()
+        ema = inner._engine.ema_state()
+        covered = set()
+        for off, n in [sp for p in plans for sp in p]:
+            name = sharded_names[off]
+            covered.add(name)
+            lo, hi = (0, n // 2) if r == 0 else (n // 2, n)
+            other = (n // 2, n) if r == 0 else (0, n // 2)
+            flat, want = mine[name].detach().view(-1), ref[name].detach().view(-1)
+            assert torch.equal(flat[lo:hi], want[lo:hi]), name
+            assert torch.equal(flat[other[0]:other[1]], init[name].view(-1)[other[0]:other[1]]), name  # owner-only master
+            for buf, buf_r in ((m, m_r), (v, v_r), (ema, ema_r)):
+                assert torch.equal(buf[off + lo: off + hi], buf_r[off + lo: off + hi]), name
+        for name, p in mine.items():  # replicated tensors: updated whole on every rank
+            if name not in covered and name != "gripper_embed.weight":
+                assert torch.equal(p.detach(), ref[name].detach()), name
+    # a fourth forward reads the packed weights (and, in training mode, the transposed copies) of both "ranks"
+    l4 = [float(model.loss(st, acts, goal_t, noise, sig)[0]) for _, model in [(inner_r, model_r)] + ranks]
+    assert l4[0] == l4[1] == l4[2]
+
+
 def test_fused_ema_and_gradient_norms():
     """the EMA of the weights kept inside the optimizer launch equals the reference callback's
     arithmetic (mode/callbacks/ema.py:119-126: diff = ema - w; diff *= 1 - decay; ema -= diff, seeded with the initial
