@@ -830,11 +830,11 @@ static int refresh_derived(mode_engine* e, cudaStream_t st) {
   matvec_f64_kernel<<<(d + 7) / 8, 256, 0, st>>>(e->sig_w2, e->sig_w1, nullptr, e->sig_u, d, d);
   matvec_f64_kernel<<<(d + 7) / 8, 256, 0, st>>>(e->sig_w2, e->sig_b1, nullptr, e->sig_v, d, d);
   // router first Linear on c = emb_t(s): s * (W1 u) + (W1 v + b1)            (modedit.py:304-310, :336)
-  for (int l = 0; l < e->L; ++l) {
-    const float* W1 = e->r_w1 + (size_t)l * Hd * d;
-    matvec_f64_kernel<<<(Hd + 7) / 8, 256, 0, st>>>(W1, e->sig_u, nullptr, e->r_a + (size_t)l * Hd, Hd, d);
-    matvec_f64_kernel<<<(Hd + 7) / 8, 256, 0, st>>>(W1, e->sig_v, e->r_b1 + (size_t)l * Hd, e->r_b + (size_t)l * Hd, Hd, d);
-  }
+  // all blocks in one launch each: r_w1 [L, Hd, d], r_a / r_b1 / r_b [L, Hd] are contiguous over the blocks (this runs
+  // after every optimizer step of the training path, not only at load time)
+  const int rows = e->L * Hd;
+  matvec_f64_kernel<<<(rows + 7) / 8, 256, 0, st>>>(e->r_w1, e->sig_u, nullptr, e->r_a, rows, d);
+  matvec_f64_kernel<<<(rows + 7) / 8, 256, 0, st>>>(e->r_w1, e->sig_v, e->r_b1, e->r_b, rows, d);
   CU_OK(cudaGetLastError());
   return MODE_OK;
 }

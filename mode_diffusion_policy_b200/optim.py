@@ -302,10 +302,11 @@ class EngineAdamW(torch.optim.Optimizer):
                 scattered[layer].record(xs)
                 mark(f"scatter_{layer}", xs)
             os_.wait_stream(main)
-            rest()
             order = list(range(L)) if overlap_forward else backward_order
             for i, layer in enumerate(order):
                 update(layer)
+                if i == 0:
+                    rest()  # behind the first block's update (which only needs its own reduce-scatter), ahead of its gather
                 if i >= 1:
                     gather(order[i - 1])
             gather(order[-1])

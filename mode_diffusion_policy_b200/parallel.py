@@ -218,6 +218,7 @@ class ShardedGradExchange(GradAllReduce):
         self.rank = dist.get_rank(group) if self.active() else 0
         self.world = dist.get_world_size(group) if self.active() else 1
         self.layers = None  # planned by prepare(), once the optimizer has bound its parameters
+        self.min_replicated_bucket = 1 << 18
 
     def prepare(self) -> None:
         """Switch the engine's optimizer to sharded groups and read back which tensors it shards (idempotent)."""
@@ -225,10 +226,21 @@ class ShardedGradExchange(GradAllReduce):
             return
         eng = self.engine
         eng.set_optimizer_sharding(self.rank, self.world)
-        self.layers, self.tail = plan_shards([eng.optimizer_shard_tensors(l) for l in range(self.n_layers)], self.flat.numel())
+        self.layers, _ = plan_shards([eng.optimizer_shard_tensors(l) for l in range(self.n_layers)], self.flat.numel())
         self.staging = eng.optimizer_staging()
         by_offset = {eng.grad_range(n)[0]: n for n in self.param_names}
         self.names = [[by_offset[off] for off, _ in lay] for lay in self.layers]  # parameter of every sharded span
+        # replicated per-block tensors that are worth their own all-reduce during the backward (the router's first
+        # Linear: 4 MB per block) instead of riding in the tail after it
+        sharded = {off for lay in self.layers for off, _ in lay}
+        self.layer_replicated = [[] for _ in range(self.n_layers)]
+        for name in self.param_names:
+            if name.startswith("blocks."):
+                off, n = eng.grad_range(name)
+                if off not in sharded and n >= self.min_replicated_bucket:
+                    self.layer_replicated[int(name.split(".")[1])].append((off, n))
+        covered = [sorted(self.layers[l] + self.layer_replicated[l]) for l in range(self.n_layers)]
+        _, self.tail = plan_shards(covered, self.flat.numel())
 
     def _spans(self, buf, layer):
         return [buf[off: off + n] for off, n in self.layers[layer]]
@@ -249,6 +261,7 @@ class ShardedGradExchange(GradAllReduce):
     def reduce_scatter_layer(self, layer: int) -> None:
         self.engine.wait_grads(layer, self.stream)
         self._grouped(lambda v: reduce_scatter_mean(v, self.rank, self.world, self.group), self._spans(self.flat, layer))
+        self._reduce_spans(self.layer_replicated[layer])
 
     def gather_weights_layer(self, layer: int) -> None:
         """All-gather block `layer`'s bf16 staging spans (enqueue after that block's optimizer launch on this stream)."""
