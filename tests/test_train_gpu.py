@@ -13,6 +13,10 @@ from test_engine_gpu import MODELS, cu, engine_for
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
+# relative L2 bounds against the reference's autograd (fp32): observed x 1.5, see the TRAIN-PARITY prints (`-s`) and
+# profiles/r02_train_parity.log
+INPUT_GRAD_TOL = 1.2e-2  # observed <= 7.5e-3
+ENTRY_TOL = 2.5e-2       # module-surface runs: observed <= 1.53e-2
 
 
 def sample_indices(numel, tensor_pos):
@@ -100,9 +104,11 @@ def test_autograd_integration_and_optimizer_step():
     loss.backward()
     for got, want in ((st["state_images"].grad, gt["d_state"]), (goal_t.grad, gt["d_goal"])):
         got = got.cpu().numpy().reshape(want.shape)
-        assert np.linalg.norm(got - want) <= 6e-2 * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
+        print(f"TRAIN-PARITY module surface input gradient rel {np.linalg.norm(got - want) / np.linalg.norm(want):.3e}")
+        assert np.linalg.norm(got - want) <= INPUT_GRAD_TOL * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
     st = {"state_images": st["state_images"].detach()}
     params = dict(inner.named_parameters())
+    worst = 0.0
     assert params["blocks.0.router.router.mlp.0.weight"].grad is None and params["gripper_embed.weight"].grad is None
     for pos, (name, shape) in enumerate(O.state_dict_spec(cfg)):
         if "router" in name or name == "gripper_embed.weight":
@@ -113,7 +119,9 @@ def test_autograd_integration_and_optimizer_step():
             assert not got.any()
             continue
         idx = sample_indices(got.size, pos)
-        assert np.linalg.norm(got[idx] - want) <= 6e-2 * np.linalg.norm(want), name
+        worst = max(worst, np.linalg.norm(got[idx] - want) / np.linalg.norm(want))
+        assert np.linalg.norm(got[idx] - want) <= ENTRY_TOL * np.linalg.norm(want), name
+    print(f"TRAIN-PARITY module surface (autograd) max sampled-entry rel {worst:.3e}")
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
     losses = [float(loss)]
     for _ in range(5):
@@ -312,7 +320,7 @@ def test_stochastic_training_matches_reference_with_the_same_masks(tag, prefix):
     for got, want in ((ds, gs["d_state"]), (dg, gs["d_goal"])):
         got = got.cpu().numpy().reshape(want.shape)
         print(f"TRAIN-PARITY {prefix}_{tag} input gradient rel {np.linalg.norm(got - want) / np.linalg.norm(want):.3e}")
-        assert np.linalg.norm(got - want) <= 6e-2 * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
+        assert np.linalg.norm(got - want) <= INPUT_GRAD_TOL * np.linalg.norm(want), np.linalg.norm(got - want) / np.linalg.norm(want)
     # the goal gradient is exactly zero where the goal feature was masked
     from oracle import mode_rng as R
     keep = R.goal_keep_mask(seed, step, B, cfg.goal_dim, p_goal)
@@ -385,6 +393,7 @@ def test_module_surface_trains_with_the_reference_default_regularisation():
     inner.set_train_rng(int(gs["seed"]), int(gs["step"]))
     loss0, _ = model.loss(st, acts, goal_t, noise, sig)
     loss0.backward()
+    worst = 0.0
     # the same (seed, step) as the reference-generated golden: same loss, same gradients
     assert abs(float(loss0) - float(gs["loss"])) <= 3e-2 * abs(float(gs["loss"]))
     params = dict(inner.named_parameters())
@@ -394,7 +403,9 @@ def test_module_surface_trains_with_the_reference_default_regularisation():
         got = params[name].grad.reshape(-1).cpu().numpy()
         idx = sample_indices(got.size, pos)
         want = gs[f"val/{name}"]
-        assert np.linalg.norm(got[idx] - want) <= 6e-2 * np.linalg.norm(want), name
+        worst = max(worst, np.linalg.norm(got[idx] - want) / np.linalg.norm(want))
+        assert np.linalg.norm(got[idx] - want) <= ENTRY_TOL * np.linalg.norm(want), name
+    print(f"TRAIN-PARITY module surface (stochastic) max sampled-entry rel {worst:.3e}")
     # per-token load-balancing term (reference modedit.py:584-593) from the engine's token-level draws
     lb = float(inner.load_balancing_loss())
     T, E = cfg.seq_len, cfg.num_experts
