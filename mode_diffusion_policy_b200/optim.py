@@ -41,9 +41,23 @@ class EngineAdamW(torch.optim.Optimizer):
         self._step = 0
         self._bound = {}
         self._consumed_generation = None  # engine.train_generation of the gradients the last step() used
+        self._masters_stale = False   # sharded steps with master_sync="lazy": fp32 masters current only on their owners
+        self._masters_ready = None    # event behind the last all-gather of the masters
+        inner_model.register_state_dict_pre_hook(self._state_dict_guard)
         inner_model._skip_param_grads = not materialize_grads
         inner_model._engine_keeps_sync = True  # step() re-packs what it updates: GCDenoiser.loss need not
         inner_model._loss_grad_scale = None
+
+    def _state_dict_guard(self, module, prefix, keep_vars):
+        """`state_dict()` of the model (checkpoints, the EMA callback, and the engine's own re-pack from the masters) must
+        not read masters that only their owning rank has updated."""
+        if self._masters_stale:
+            raise RuntimeError(
+                "EngineAdamW.step_sharded(master_sync='lazy'): the fp32 master parameters of the sharded tensors are only "
+                "current on their owning rank. Call optimizer.synchronize_parameters() on EVERY rank before reading "
+                "state_dict() / modifying parameters (it all-gathers them), or use master_sync='step'.")
+        if self._masters_ready is not None and torch.cuda.is_available():
+            torch.cuda.current_stream().wait_event(self._masters_ready)
 
     def _set_ema(self, eng):
         d = self._ema_decay
@@ -68,6 +82,7 @@ class EngineAdamW(torch.optim.Optimizer):
 
         @contextlib.contextmanager
         def ctx():
+            self.synchronize_parameters()  # after sharded steps: a collective, enter on every rank
             params = dict(self.inner.named_parameters())
             ema = self.ema_state_dict()
             saved = {n: params[n].detach().clone() for n in ema}
@@ -333,7 +348,7 @@ class EngineAdamW(torch.optim.Optimizer):
 
     def _gather_masters(self) -> None:
         ex = getattr(self, "_exchange", None)
-        if ex is None or not getattr(self, "_masters_stale", False):
+        if ex is None or not self._masters_stale:
             return
         ex.stream.wait_stream(self._opt_stream)  # every owner's update of this step
         ex.gather_parameters(dict(self.inner.named_parameters()))
@@ -343,11 +358,10 @@ class EngineAdamW(torch.optim.Optimizer):
 
     def synchronize_parameters(self) -> None:
         """After sharded steps: make the caller's stream see fully updated fp32 master parameters on every rank (a
-        collective if the gather is still pending: call it on all ranks)."""
+        collective if the gather is still pending: call it on all ranks). No-op otherwise."""
         self._gather_masters()
-        ev = getattr(self, "_masters_ready", None)
-        if ev is not None:
-            torch.cuda.current_stream(self.inner._engine.device).wait_event(ev)
+        if self._masters_ready is not None:
+            torch.cuda.current_stream(self.inner._engine.device).wait_event(self._masters_ready)
 
     def _gather_sharded_state(self, eng) -> None:
         """Moments and EMA of sharded tensors live on the owning rank: gather them before they are read whole."""

@@ -319,3 +319,25 @@ def test_synthetic_workload_equals_the_oracles_generators():
     src = (Path(__file__).resolve().parents[1] / "bench.py").read_text()
     main_src = src[src.index("def main():"):]
     assert "oracle" not in main_src.replace("oracle/ (the checker)", "")
+
+
+def test_sharded_optimizer_refuses_to_hand_out_stale_masters():
+    """After `EngineAdamW.step_sharded(master_sync="lazy")` the fp32 masters of the sharded tensors are current only on
+    their owning rank: `state_dict()` (checkpoints, the EMA callback, the engine's own re-pack) must raise until
+    `synchronize_parameters()` has gathered them, instead of silently returning half-updated tensors."""
+    from mode_diffusion_policy_b200.optim import EngineAdamW
+    from mode_diffusion_policy_b200.score_wrappers import GCDenoiser
+
+    m = MoDeDiT(obs_dim=128, goal_dim=64, device="cpu", goal_conditioned=True, action_dim=7, embed_dim=256, embed_pdrob=0,
+                attn_pdrop=0.0, n_layers=1, n_heads=4, goal_seq_len=1, obs_seq_len=1, action_seq_len=10, state_dim=7,
+                use_argmax=True)
+    wrapper = GCDenoiser(m, sigma_data=0.5)
+    opt = EngineAdamW(m, lr=1e-4)
+    assert "pos_emb" in m.state_dict() and any(k.endswith("pos_emb") for k in wrapper.state_dict())
+    opt._masters_stale = True  # what a lazy sharded step leaves behind
+    with pytest.raises(RuntimeError, match="synchronize_parameters"):
+        m.state_dict()
+    with pytest.raises(RuntimeError, match="synchronize_parameters"):
+        wrapper.state_dict()  # the reference checkpoints the wrapper / the whole agent
+    opt._masters_stale = False
+    assert "pos_emb" in m.state_dict()
