@@ -201,7 +201,9 @@ struct mode_engine {
   int perm_rows, max_tiles;
   float inv_sqrt_d, inv_sqrt_dh;
   bool pair;   // CTA-pair GEMM kernel (MODE_GEMM_CTA_PAIR, default on)
-  bool mlp_fused;  // expert up+down projections as one dynamically scheduled launch (MODE_MLP_FUSED=1, default off; needs pair)
+  bool mlp_fused;  // expert up+down projections as one dynamically scheduled launch for every batch (MODE_MLP_FUSED=1; needs pair)
+  int mlp_fused_max_rows;  // default: fused up to this many token rows (B <= 128: one launch less per block is worth 1-3 %
+                           // there, profiles/r02_batch_sweep.log; at B = 256 two launches with their own tile widths win)
   int* mlp_sync;   // its tile queue head + per-M-tile dependency counters
   int tile_m;  // rows per M-tile: 256 with CTA pairs, 128 otherwise
   bool small_m = true;  // rollout-sized batches (B*T <= 16 rows) use the weight-streaming GEMM (MODE_SMALL_M=0 disables)
@@ -633,7 +635,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
     const char* sf_env = getenv("MODE_SMALL_FUSED");
     e->small_fused = sf_env && atoi(sf_env) != 0;
     env = getenv("MODE_MLP_FUSED");
-    e->mlp_fused = e->pair && (env ? atoi(env) != 0 : false);  // measured +1.5 % only: opt-in
+    e->mlp_fused = e->pair && (env ? atoi(env) != 0 : false);
+    e->mlp_fused_max_rows = (e->pair && !env) ? 1792 : 0;
   }
   e->max_tiles = (K * e->maxM + e->tile_m - 1) / e->tile_m + E;
   e->perm_rows = e->max_tiles * e->tile_m;
@@ -1224,7 +1227,8 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
   const int t_skip = (trim_rows > 0 && !rv.per_token) ? e->T - trim_rows : 0;  // must match the plan of this layer
   n2.t_skip = t_skip;
   n2.B = rv.units; n2.T = rv.rt; n2.K = e->K; n2.d = d; n2.eps = e->cfg.rms_eps; n2.inv_sqrt_d = e->inv_sqrt_d;
-  const bool fused_mlp = e->mlp_fused && !io.z && !small;  // the training forward keeps the two-launch path (it saves z)
+  // the training forward keeps the two-launch path (it saves z)
+  const bool fused_mlp = (e->mlp_fused || M <= e->mlp_fused_max_rows) && !io.z && !e->train_forward && !small;
   n2.zero = fused_mlp ? e->mlp_sync : nullptr;
   n2.n_zero = 1 + e->max_tiles;
   {
@@ -1243,10 +1247,8 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
     mp.up = p;
     mp.down = pd;
     mp.sync = e->mlp_sync;
-    {
-      const char* env = getenv("MODE_MLP_FLAGS");
-      mp.flags = env ? atoi(env) : (1 | (18 << 8));  // deferred signalling, down tiles queued 18 M-tiles behind
-    }
+    static const int mlp_flags = getenv("MODE_MLP_FLAGS") ? atoi(getenv("MODE_MLP_FLAGS")) : (1 | (18 << 8));
+    mp.flags = mlp_flags;  // deferred signalling, down tiles queued 18 M-tiles behind
     CU_OK(launch_k(mlp_fused_2cta_kernel, dim3(e->num_sms & ~1), dim3(GEMM_THREADS), G2_SMEM_BYTES, st, mp));
   } else {
     enable_stream_k(e, p);
