@@ -249,6 +249,8 @@ class EngineAdamW(torch.optim.Optimizer):
             return self.step_overlapped(exchange, timeline=timeline, loss_scale=loss_scale)
         self._bind(eng)
         exchange.prepare()
+        if exchange.fallback is not None:  # no tensor splits evenly over this world size: replicated step
+            return self.step_overlapped(exchange.fallback, timeline=timeline, loss_scale=loss_scale)
         self._exchange = exchange
         self._check_fresh_gradients(eng)
         g = self.param_groups[0]

@@ -218,6 +218,7 @@ class ShardedGradExchange(GradAllReduce):
         self.rank = dist.get_rank(group) if self.active() else 0
         self.world = dist.get_world_size(group) if self.active() else 1
         self.layers = None  # planned by prepare(), once the optimizer has bound its parameters
+        self.fallback = None  # a GradAllReduce when no tensor can be sharded over this world size
         self.min_replicated_bucket = 1 << 18
 
     def prepare(self) -> None:
@@ -227,6 +228,14 @@ class ShardedGradExchange(GradAllReduce):
         eng = self.engine
         eng.set_optimizer_sharding(self.rank, self.world)
         self.layers, _ = plan_shards([eng.optimizer_shard_tensors(l) for l in range(self.n_layers)], self.flat.numel())
+        if not any(self.layers):
+            # nothing splits evenly over this many ranks (the 1024-element blocks of the large tensors do not divide by the
+            # world size): keep the replicated, pipelined all-reduce step
+            eng.set_optimizer_sharding(0, 1)
+            self.fallback = GradAllReduce(eng, self.param_names, self.n_layers, group=self.group)
+            self.fallback.stream = self.stream
+            self.tail = self.fallback.tail
+            return
         self.staging = eng.optimizer_staging()
         by_offset = {eng.grad_range(n)[0]: n for n in self.param_names}
         self.names = [[by_offset[off] for off, _ in lay] for lay in self.layers]  # parameter of every sharded span
