@@ -230,6 +230,8 @@ struct mode_engine {
   struct SmallProgram { SmallPhase* dev; int n; };
   std::map<std::string, SmallProgram> small_programs;
   unsigned* small_barrier = nullptr;
+  int small_prefetch_mask = -1;  // bit EPI_*: that weight-streaming GEMM prefetches its weights ahead of the dependency wait
+                                 // (MODE_SMALL_PREFETCH=mask; -1 = by batch size, see small_gemm)
   bool band_down = true;                                  // MODE_GEMM_BAND=0: column-block-major tile order for the down GEMM
   bool small_fused = false;                               // MODE_SMALL_FUSED=1 opts in (measured slower, see mode_create)
   std::map<std::string, cudaGraphExec_t> prog_graphs;
@@ -630,6 +632,8 @@ extern "C" int mode_create(const mode_config_t* c, mode_engine_t** out) {
     e->trim_rows = (trim_env && atoi(trim_env) == 0) ? 0 : e->A;
     // persistent one-launch sampler for B <= 2 (small_eval.cuh): correct (tested) but measured SLOWER than the CUDA graph of
     // per-phase kernels on B200 (8.6 vs 7.2 ms per 10-step sample at B = 1, profiles/r02_small_fused.log) -> opt-in
+    const char* pf_env = getenv("MODE_SMALL_PREFETCH");
+    e->small_prefetch_mask = pf_env ? atoi(pf_env) : -1;
     const char* band_env = getenv("MODE_GEMM_BAND");
     e->band_down = !(band_env && atoi(band_env) == 0);
     const char* sf_env = getenv("MODE_SMALL_FUSED");
@@ -1073,7 +1077,13 @@ static void rec_phase(mode_engine* e, int kind, const P& params, int ntasks, int
     else                                                              \
       LAUNCH_ROW_KERNEL(KERNEL, d, grid, st, params);                 \
   } while (0)
-static int small_gemm(mode_engine* e, int epi, cudaStream_t st, const SmallGemmParams& p, int n_cols, int max_tiles, int max_rows) {
+static int small_gemm(mode_engine* e, int epi, cudaStream_t st, const SmallGemmParams& p_in, int n_cols, int max_tiles, int max_rows,
+                      bool tables_final = true) {
+  SmallGemmParams p = p_in;
+  // measured (profiles/r02_small_fused.log): with one 16-row tile per group (B = 1) prefetching the expert weights ahead of
+  // the wait costs more than it hides (5.5 -> 6.8 ms per sample), QKV + c_proj are a small win; with two tiles (B = 2) all four help
+  const int mask = e->small_prefetch_mask >= 0 ? e->small_prefetch_mask : (max_rows <= 16 ? 3 : 15);
+  p.prefetch = (tables_final && (mask >> epi & 1)) ? 1 : 0;
   if (e->rec) {
     const int per = small_slabs_per_task(epi), slabs = n_cols / 8;
     rec_phase(e, SP_GEMM, p, ((slabs + per - 1) / per) * max_tiles, epi, slabs);
@@ -1260,7 +1270,8 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
         RET_IF(launch_gemm(EPI_SWIGLU_SAVE, e->pair, e->num_sms, st, p));
       } else if (small) {
         RET_IF(small_gemm(e, EPI_SWIGLU_BF16, st, small_params(io.perm, e->w_up, d, e->up_tiles + lt * e->max_tiles,
-                                                                   e->num_tiles + lt, e->b_up, io.h, e->F, 0), e->F, small_groups, M));
+                                                                   e->num_tiles + lt, e->b_up, io.h, e->F, 0), e->F, small_groups, M,
+                          /*tables_final=*/slot != ROUTE_SLOT_EVAL));  // a pre-routed schedule was planned before the launch chain
       } else if (!(skip >> PC_UP & 1)) {
         RET_IF(launch_gemm(EPI_SWIGLU_BF16, e->pair, e->num_sms, st, p));
       }
@@ -1279,7 +1290,8 @@ static int enqueue_block(mode_engine* e, cudaStream_t st, int B, int l, int comb
       ProfScope ps(e, st, PC_DOWN);
       if (small)
         RET_IF(small_gemm(e, EPI_PLAIN_BF16, st, small_params(io.h, e->w_down, e->F, e->down_tiles + lt * e->max_tiles,
-                                                                  e->num_tiles + lt, nullptr, io.y, d, 0), d, small_groups, M));
+                                                                  e->num_tiles + lt, nullptr, io.y, d, 0), d, small_groups, M,
+                          /*tables_final=*/slot != ROUTE_SLOT_EVAL));
       else if (!(skip >> PC_DOWN & 1)) RET_IF(launch_gemm(EPI_PLAIN_BF16, e->pair, e->num_sms, st, pd));
     }
   }

@@ -31,6 +31,11 @@ struct SmallGemmParams {
   void* out;                   // bf16 or fp32 [rows, ldo]
   int K, ldo;
   int w_row_off;
+  // 1: every CTA asks L2 for its own weight rows BEFORE waiting for the previous kernel (programmatic dependent launch:
+  // the CTAs are resident while a 14-row norm / attention kernel runs on a handful of SMs, and the weights do not depend
+  // on it), so the HBM stream of this GEMM overlaps its predecessor and the K loop reads L2. Only when the M-tile table
+  // is final before the launch chain starts (dense projections; expert GEMMs inside a pre-routed sampler graph).
+  int prefetch = 0;
 };
 
 __device__ __forceinline__ void mma_bf16_16816_acc(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -237,6 +242,18 @@ template <int EPI, int MT>
 __global__ void __launch_bounds__(SMALL_M_WARPS * 32) gemm_small_m_kernel(const SmallGemmParams p) {
   pdl_trigger();
   __shared__ float red[SMALL_M_WARPS * (EPI == EPI_SWIGLU_BF16 ? 2 : 1) * MT * 16 * 8];
+  if (p.prefetch && static_cast<int>(blockIdx.y) < *p.num_m_tiles) {
+    constexpr bool GLU = (EPI == EPI_SWIGLU_BF16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slab = blockIdx.x;
+    const int row0 = p.w_row_off + p.m_tiles[blockIdx.y].w_row_base + (GLU ? (slab * 8 / 128) * 256 + (slab * 8) % 128 : slab * 8);
+    const int k_per_warp = p.K / SMALL_M_WARPS;
+    const int lines = k_per_warp / 64;  // 128-byte lines of one weight row inside this warp's K slice
+    for (int i = lane; i < 8 * lines * (GLU ? 2 : 1); i += 32) {
+      const int row = row0 + (i / lines) % 8 + (i / (8 * lines)) * 128;
+      const __nv_bfloat16* src = p.W + static_cast<size_t>(row) * p.K + warp * k_per_warp + (i % lines) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+    }
+  }
   pdl_wait();
   gemm_small_body<EPI, MT, false>(p, blockIdx.x, blockIdx.y, red);
 }
