@@ -478,11 +478,112 @@ def sample_dpmpp_2s_ancestral(model, state, action, goal, sigmas, scaler=None, e
     return action
 
 
+class BrownianNoiseSampler:
+    """Noise sampler of the stochastic DPM-Solver++ (reference BrownianTreeNoiseSampler, gc_sampling.py:139-162): returns
+    the increment of ONE Brownian motion per sample element over [sigma, sigma_next], normalised to unit variance, so
+    overlapping intervals are correlated the way the SDE solver expects. The reference builds it on torchsde's
+    BrownianTree; this is a self-contained Brownian-bridge construction with the same interface and statistics (the
+    draws themselves are a different — seedable — stream). W is pinned at sigma_min (0) and sigma_max; a new time point is
+    sampled conditionally on its nearest known neighbours."""
+
+    def __init__(self, x, sigma_min, sigma_max, seed=None, transform=lambda v: v):
+        self.transform = transform
+        t0, t1 = float(transform(torch.as_tensor(sigma_min))), float(transform(torch.as_tensor(sigma_max)))
+        self.t0, self.t1 = min(t0, t1), max(t0, t1)
+        self.gen = None
+        if seed is not None:
+            self.gen = torch.Generator(device=x.device)
+            self.gen.manual_seed(int(seed))
+        self.like = x
+        self.times = [self.t0, self.t1]
+        self.values = [torch.zeros_like(x), self._randn() * math.sqrt(self.t1 - self.t0)]
+
+    def _randn(self):
+        return torch.randn(self.like.shape, dtype=self.like.dtype, device=self.like.device, generator=self.gen)
+
+    def _w(self, t):
+        import bisect
+        t = min(max(t, self.t0), self.t1)
+        k = bisect.bisect_left(self.times, t)
+        if self.times[k] == t:
+            return self.values[k]
+        ta, tb, wa, wb = self.times[k - 1], self.times[k], self.values[k - 1], self.values[k]
+        mean = wa + (wb - wa) * ((t - ta) / (tb - ta))                 # Brownian bridge between the known neighbours
+        w = mean + self._randn() * math.sqrt((t - ta) * (tb - t) / (tb - ta))
+        self.times.insert(k, t)
+        self.values.insert(k, w)
+        return w
+
+    def __call__(self, sigma, sigma_next):
+        a, b = float(self.transform(torch.as_tensor(sigma))), float(self.transform(torch.as_tensor(sigma_next)))
+        sign = 1.0 if a <= b else -1.0
+        lo, hi = min(a, b), max(a, b)
+        return (self._w(hi) - self._w(lo)) * (sign / math.sqrt(hi - lo))
+
+
+@torch.no_grad()
+def sample_dpmpp_sde(model, state, action, goal, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
+                     scaler=None, noise_sampler=None, r=1 / 2):
+    """DPM-Solver++ (stochastic), reference gc_sampling.py:736-793 (`sampler_type='dpmpp_2m_sde'`, mode_agent.py:827): two
+    network evaluations per step, the second on a probe at the intermediate time s = t + r h, both followed by a Brownian
+    increment from `noise_sampler(sigma, sigma_next)` (default: BrownianNoiseSampler). One engine launch; the increments
+    are requested here in the order the loop requests them."""
+    sig = torch.as_tensor(sigmas)
+    if noise_sampler is None:
+        noise_sampler = BrownianNoiseSampler(action, sig[sig > 0].min(), sig.max())
+    fac = 1 / (2 * r)
+    if _program_ok(model, sigmas, scaler, extra_args, callback):
+        sg, prog, draws, ok = _floats(sigmas), SamplerProgram(), [], True
+        for i in range(len(sg) - 1):
+            s0, s1 = sg[i], sg[i + 1]
+            if s1 == 0:
+                prog.eval(s0, cX=0.0, cD=1.0)  # Euler step to sigma = 0: x + (x - D) / s0 * (0 - s0) = D
+                continue
+            t, tn = -math.log(s0), -math.log(s1)
+            sm = math.exp(-(t + (tn - t) * r))                                     # sigma at the intermediate time
+            d1, u1 = (float(v) for v in get_ancestral_step(s0, sm, eta))
+            d2, u2 = (float(v) for v in get_ancestral_step(s0, s1, eta))
+            if d1 <= 0 or d2 <= 0:
+                ok = False
+                break
+            draws.append(noise_sampler(sig[i].new_tensor(s0), sig[i].new_tensor(sm)))
+            k1 = len(draws) - 1
+            draws.append(noise_sampler(sig[i].new_tensor(s0), sig[i].new_tensor(s1)))
+            k2 = len(draws) - 1
+            e1, e2 = -math.expm1(t + math.log(d1)), -math.expm1(t + math.log(d2))  # -(t - t_fn(sd)).expm1()
+            prog.eval(s0, cX=d1 / s0, cD=e1, cN=s_noise * u1, noise=k1, hD=1.0, slot=0, to_probe=True)   # P = x_2, H0 = D
+            prog.eval(sm, on_probe=True, cX=d2 / s0, cH=(e2 * (1 - fac), 0, 0, 0), cD=e2 * fac, cN=s_noise * u2, noise=k2)
+        if ok:
+            return prog.run(model, state, action, goal, draws)
+        raise ValueError("sample_dpmpp_sde: eta too large for this schedule (sigma_down = 0 inside the loop)")
+    lp = _Loop(model, state, goal, scaler, extra_args, callback, key="x")
+    x = action
+    for i in range(len(sigmas) - 1):
+        denoised = lp.denoise(x, sigmas[i])
+        lp.report(x, i, sigmas[i], sigmas[i], denoised)
+        if sigmas[i + 1] == 0:
+            x = x + to_d(x, sigmas[i], denoised) * (sigmas[i + 1] - sigmas[i])
+        else:
+            t, t_next = _t(sigmas[i]), _t(sigmas[i + 1])
+            s = t + (t_next - t) * r
+            sd, su = get_ancestral_step(_sig(t), _sig(s), eta)
+            s_ = _t(sd)
+            x_2 = (_sig(s_) / _sig(t)) * x - (t - s_).expm1() * denoised
+            x_2 = x_2 + noise_sampler(_sig(t), _sig(s)) * s_noise * su
+            denoised_2 = lp.denoise(x_2, _sig(s))
+            sd, su = get_ancestral_step(_sig(t), _sig(t_next), eta)
+            t_next_ = _t(sd)
+            denoised_d = (1 - fac) * denoised + fac * denoised_2
+            x = (_sig(t_next_) / _sig(t)) * x - (t - t_next_).expm1() * denoised_d
+            x = lp.clip(x + noise_sampler(_sig(t), _sig(t_next)) * s_noise * su)
+    return x
+
+
 SAMPLERS = {
     # sampler_type keys of MoDEAgent.sample_loop (reference mode_agent.py:771-840). 'dpm_fast', 'dpm_adaptive' raise in
-    # the reference (undefined names) and 'dpmpp_2m_sde' needs torchsde; they are not provided.
+    # the reference (undefined names, SURVEY.md A.4) and are not provided.
     "lms": sample_lms, "heun": sample_heun, "euler": sample_euler, "ancestral": sample_dpm_2_ancestral,
     "euler_ancestral": sample_euler_ancestral, "dpm": sample_dpm_2, "dpmpp_2s_ancestral": sample_dpmpp_2s_ancestral,
     "dpmpp_2m": sample_dpmpp_2m, "ddim": sample_ddim, "dpmpp_2s": sample_dpmpp_2s,
-    "debugging": sample_dpmpp_2_with_lms, "dpmpp_2_with_lms": sample_dpmpp_2_with_lms,
+    "debugging": sample_dpmpp_2_with_lms, "dpmpp_2_with_lms": sample_dpmpp_2_with_lms, "dpmpp_2m_sde": sample_dpmpp_sde,
 }

@@ -21,7 +21,7 @@ import torch
 from oracle import mode_oracle as O
 from mode_diffusion_policy_b200 import gc_sampling as S
 from test_engine_gpu import TINY, cu, engine_for, rel_l2
-from test_reference_goldens_cpu import SAMPLER_CALLS, NoiseTape
+from test_reference_goldens_cpu import SAMPLER_CALLS, NoiseTape, sampler_call
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -112,7 +112,7 @@ def test_every_sampler_against_the_reference_sampler(key, monkeypatch):
     sd = O.make_weights(TINY, seed=1234, router_gain=30.0)
     state, goal, x0 = O.make_inputs(TINY, 5, seed=4321)
     inner, model = _modules(TINY, sd)
-    name, kw = SAMPLER_CALLS[key]
+    name, kw = sampler_call(key, cu(x0))
     st = {"state_images": cu(state)}
     outs = {}
     for how, extra in (("dispatch", {}), ("host_loop", {"callback": lambda d: None})):

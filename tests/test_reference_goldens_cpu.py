@@ -116,7 +116,18 @@ SAMPLER_CALLS = {  # golden key -> (function name, kwargs) exactly as MoDEAgent.
     "euler_ancestral": ("sample_euler_ancestral", {}), "dpm": ("sample_dpm_2", {}),
     "dpmpp_2s_ancestral": ("sample_dpmpp_2s_ancestral", {}), "dpmpp_2m": ("sample_dpmpp_2m", {}),
     "ddim": ("sample_ddim", {}), "dpmpp_2s": ("sample_dpmpp_2s", {}), "dpmpp_2_with_lms": ("sample_dpmpp_2_with_lms", {}),
+    # the reference's default Brownian tree needs torchsde; the golden was generated with a noise_sampler that draws from
+    # the recorded tape (tests/golden/make_full_goldens.py), which pins the update arithmetic and the order of the requests
+    "dpmpp_2m_sde": ("sample_dpmpp_sde", dict(noise_sampler="tape")),
 }
+
+
+def sampler_call(key, like):
+    """(function name, kwargs) of a golden key; `like`: the action tensor the tape's draws are shaped after."""
+    name, kw = SAMPLER_CALLS[key]
+    if kw.get("noise_sampler") == "tape":
+        kw = dict(kw, noise_sampler=lambda sigma, sigma_next: torch.randn_like(like))
+    return name, kw
 
 
 @pytest.mark.parametrize("key", list(SAMPLER_CALLS))
@@ -128,7 +139,9 @@ def test_sampler_host_loops_match_reference_samplers(key, monkeypatch):
     model = _OracleDenoiser(sd, TINY)
     tape = NoiseTape(g["noise_tape"])
     monkeypatch.setattr(torch, "randn_like", tape)
-    name, kw = SAMPLER_CALLS[key]
+    name, kw = sampler_call(key, torch.from_numpy(x0))
+    if key == "dpmpp_2m_sde":
+        kw = dict(kw, callback=lambda d: None)  # the host loop (without a callback the sampler is one program, tested below)
     out = getattr(S, name)(model, {"state_images": torch.from_numpy(state)}, torch.from_numpy(x0), torch.from_numpy(goal),
                            torch.from_numpy(g["sigmas"]), disable=True, **kw)
     assert tape.i == int(g[key + "_draws"]), "the loop must consume the caller's RNG exactly like the reference"
@@ -161,7 +174,7 @@ class _ProgramOracle(_OracleDenoiser):
 
 
 PROGRAM_SAMPLERS = {"lms": 10, "heun": 19, "ancestral": 19, "euler_ancestral": 10, "dpm": 19, "dpmpp_2s_ancestral": 19,
-                    "dpmpp_2s": 19}  # golden key -> network evaluations of the 10-step schedule
+                    "dpmpp_2s": 19, "dpmpp_2m_sde": 19}  # golden key -> network evaluations of the 10-step schedule
 
 
 @pytest.mark.parametrize("key", list(PROGRAM_SAMPLERS))
@@ -174,9 +187,26 @@ def test_sampler_programs_match_reference_samplers(key, monkeypatch):
     model = _ProgramOracle(sd, TINY)
     tape = NoiseTape(g["noise_tape"])
     monkeypatch.setattr(torch, "randn_like", tape)
-    name, kw = SAMPLER_CALLS[key]
+    name, kw = sampler_call(key, torch.from_numpy(x0))
     out = getattr(S, name)(model, {"state_images": torch.from_numpy(state)}, torch.from_numpy(x0), torch.from_numpy(goal),
                            torch.from_numpy(g["sigmas"]), disable=True, **kw)
     assert model.evals == PROGRAM_SAMPLERS[key]  # the program path ran (not the host loop)
     assert tape.i == int(g[key + "_draws"])
     assert rel_l2(out.numpy(), g[key]) < 5e-5, rel_l2(out.numpy(), g[key])
+
+
+def test_brownian_noise_sampler_is_a_consistent_unit_variance_brownian_motion():
+    """Default noise source of `sample_dpmpp_sde` (the reference's BrownianTreeNoiseSampler needs torchsde): increments
+    over nested intervals add up, are normalised to unit variance, flip sign with the direction, and repeat for a seed."""
+    x = torch.zeros(64, 10, 7)
+    b = S.BrownianNoiseSampler(x, 1e-3, 80.0, seed=3)
+    s = [torch.tensor(v) for v in (80.0, 30.0, 5.0, 0.5)]
+    w01, w12, w02 = b(s[0], s[1]), b(s[1], s[2]), b(s[0], s[2])
+    assert torch.allclose(w02 * (75.0 ** 0.5), w01 * (50.0 ** 0.5) + w12 * (25.0 ** 0.5), atol=1e-4)
+    assert torch.allclose(b(s[1], s[0]), -w01) and torch.equal(b(s[0], s[1]), w01)
+    for w in (w01, w12, w02, b(s[2], s[3])):
+        assert abs(float(w.std()) - 1.0) < 0.08 and abs(float(w.mean())) < 0.08
+    b2 = S.BrownianNoiseSampler(x, 1e-3, 80.0, seed=3)
+    assert torch.equal(b2(s[0], s[1]), w01)
+    # independent increments over disjoint intervals
+    assert abs(float((w01 * w12).mean())) < 0.08
