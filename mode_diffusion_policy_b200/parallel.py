@@ -219,7 +219,11 @@ class ShardedGradExchange(GradAllReduce):
         self.world = dist.get_world_size(group) if self.active() else 1
         self.layers = None  # planned by prepare(), once the optimizer has bound its parameters
         self.fallback = None  # a GradAllReduce when no tensor can be sharded over this world size
-        self.min_replicated_bucket = 1 << 18
+        import os
+        # Replicated per-block tensors of at least this many elements would get their own all-reduce during the backward.
+        # Off by default: on 8 GPUs the 12 extra collectives (the router's first Linear, 4 MB per block) cost more than
+        # the shorter tail saves (14.1 vs 13.7 ms/step, profiles/r02_train_sharded.log); they ride in the tail instead.
+        self.min_replicated_bucket = int(os.environ.get("MODE_SHARD_MIN_REPLICATED_BUCKET", 1 << 62))
 
     def prepare(self) -> None:
         """Switch the engine's optimizer to sharded groups and read back which tensors it shards (idempotent)."""
@@ -239,8 +243,8 @@ class ShardedGradExchange(GradAllReduce):
         self.staging = eng.optimizer_staging()
         by_offset = {eng.grad_range(n)[0]: n for n in self.param_names}
         self.names = [[by_offset[off] for off, _ in lay] for lay in self.layers]  # parameter of every sharded span
-        # replicated per-block tensors that are worth their own all-reduce during the backward (the router's first
-        # Linear: 4 MB per block) instead of riding in the tail after it
+        # replicated per-block tensors that get their own all-reduce during the backward instead of riding in the tail
+        # after it (none by default, see min_replicated_bucket)
         sharded = {off for lay in self.layers for off, _ in lay}
         self.layer_replicated = [[] for _ in range(self.n_layers)]
         for name in self.param_names:
